@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI library (include/s2s_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  The library is loaded from
+stain2stain_b200/lib/ (in-tree, so the driver sees which .so the process mapped).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _build
+
+_LIB = None
+
+
+class S2SError(RuntimeError):
+    pass
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("C", C.c_int), ("taps", C.c_int), ("stride", C.c_int)]
+
+
+_vp, _i, _f, _u64, _ll = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_longlong
+
+# name -> argtypes (restype is int unless listed in _RESTYPES).  Must mirror include/s2s_b200.h exactly.
+SIGNATURES = {
+    "s2s_last_error": [],
+    "s2s_abi_version": [],
+    "s2s_num_sms": [],
+    "s2s_pack_conv_weight": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
+    "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
+    "s2s_conv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "s2s_unpack_wgrad": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp],
+    "s2s_patch27_pack": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "s2s_gn_stats": [_vp, _i, _i, _i, _vp, _i, _i, _vp],
+    "s2s_gn_coef": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
+    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _f, _u64, _vp],
+    "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _vp],
+    "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _vp],
+    "s2s_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_sumpool2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_zero_insert2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_channel_sum": [_vp, _ll, _i, _vp, _vp],
+    "s2s_fm_loss": [_vp, _vp, _vp, _ll, _vp, _vp, _vp],
+    "s2s_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
+    "s2s_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
+}
+_RESTYPES = {"s2s_last_error": C.c_char_p}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the .so is absent/stale and nvcc is present).  Raises if it cannot."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # stale-but-present is still usable; absent is fatal
+            if not os.path.exists(path):
+                raise S2SError(f"libs2s_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise S2SError(f"{path} not found: run `python -m stain2stain_b200._build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drifted apart
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().s2s_last_error()
+        raise S2SError(f"{what or 's2s call'} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses host tensors: the product path has no CPU fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise S2SError("stain2stain_b200 kernels need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()

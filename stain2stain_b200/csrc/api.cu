@@ -1,0 +1,431 @@
+// C-ABI entry points (include/s2s_b200.h): argument validation, TMA tensor-map construction and kernel launches.
+#include "../../include/s2s_b200.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+
+using namespace s2s;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return fail(S2S_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                               \
+    do {                                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                             \
+        if (_e != cudaSuccess) return fail(S2S_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+// bf16 tensor map, 128 B swizzle.  dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(S2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(S2S_ERR_TMAP, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                    (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                    (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                    (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+                    rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return S2S_OK;
+}
+
+// Activation NHWC [B,H,W,C] bf16 as the 5-D parity view {C*s, W/s, s, H/s, B} (s = 1 or 2), box {64,16,1,8,1}.
+int make_act_tmap(CUtensorMap* m, const void* x, int B, int H, int W, int C, int s) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "activation channels (%d) must be a multiple of 8", C);
+    if (s != 1 && s != 2) return fail(S2S_ERR_INVALID, "stride %d unsupported", s);
+    if (s == 2 && ((H | W) & 1)) return fail(S2S_ERR_INVALID, "stride-2 conv needs even H, W (got %d x %d)", H, W);
+    cuuint64_t dims[5] = {(cuuint64_t)C * s, (cuuint64_t)W / s, (cuuint64_t)s, (cuuint64_t)H / s, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)C * s * 2, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 2 * s,
+                         (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {64, kTileW, 1, kTileH, 1};
+    return make_tmap(m, x, 5, dims, str, box);
+}
+
+uint32_t pow2_cols(int n) {
+    uint32_t c = 32;
+    while ((int)c < n) c <<= 1;
+    return c;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return S2S_OK;
+}
+
+constexpr size_t kSmemBudget = 227 * 1024;
+
+int ew_grid(long long work_items, int threads = kEwThreads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// pixels per CTA for the (chunk, sample) grids of the normalisation kernels: ~4 CTAs per SM-wave, >= 64 pixel rows
+int pick_pix_per_cta(int B, int HW, int C) {
+    const int vpp = C / 8;
+    const int rows = kEwThreads / vpp;  // pixels touched per block iteration
+    long long target_ctas = (long long)num_sms() * 8;
+    long long chunks = (target_ctas + B - 1) / B;
+    if (chunks < 1) chunks = 1;
+    long long ppc = (HW + chunks - 1) / chunks;
+    const long long min_ppc = (long long)rows * 8;
+    if (ppc < min_ppc) ppc = min_ppc;
+    ppc = (ppc + rows - 1) / rows * rows;
+    if (ppc > HW) ppc = HW;
+    return (int)ppc;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int check_vec_layout(int C, const char* who) {
+    if (C % 8 || !is_pow2(C / 8) || C / 8 > kEwThreads)
+        return fail(S2S_ERR_INVALID, "%s: C = %d unsupported (need C/8 a power of two <= %d)", who, C, kEwThreads);
+    return S2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* s2s_last_error(void) { return g_err; }
+int s2s_abi_version(void) { return 1; }
+int s2s_num_sms(void) { return num_sms(); }
+
+int s2s_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst, int ld_k,
+                         int k_off, int transpose_flip, void* stream) {
+    if (!w || !dst || Cout <= 0 || ci_count <= 0 || ci_begin < 0 || ci_begin + ci_count > Cin || (taps != 1 && taps != 9))
+        return fail(S2S_ERR_INVALID, "pack_conv_weight: bad arguments");
+    const long long total = (long long)Cout * ci_count * taps;
+    pack_conv_weight_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+        w, Cout, Cin, taps, ci_begin, ci_count, (__nv_bfloat16*)dst, ld_k, k_off, transpose_flip);
+    LAUNCH_CHECK("pack_conv_weight_kernel");
+    return S2S_OK;
+}
+
+int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
+                 int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
+                 const float* axpy_x, float axpy_a, void* stream) {
+    if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
+    if ((out_bf16 != nullptr) == (out_f32 != nullptr))
+        return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.nseg = nsrc;
+    int kblocks = 0;
+    for (int s = 0; s < nsrc; ++s) {
+        const s2s_conv_src& sc = srcs[s];
+        if (sc.taps != 1 && sc.taps != 9) return fail(S2S_ERR_INVALID, "conv_fwd: taps = %d", sc.taps);
+        if (sc.taps == 1 && sc.stride != 1) return fail(S2S_ERR_INVALID, "conv_fwd: strided 1x1 unsupported");
+        int rc = make_act_tmap(&p.tmA[s], sc.x, B, Hout * sc.stride, Wout * sc.stride, sc.C, sc.stride);
+        if (rc) return rc;
+        p.seg[s].taps = sc.taps;
+        p.seg[s].cblocks = (sc.C + kBlockK - 1) / kBlockK;
+        p.seg[s].stride = sc.stride;
+        p.seg[s].C = sc.C;
+        kblocks += sc.taps * p.seg[s].cblocks;
+    }
+    if (kblocks * kBlockK != Ktot)
+        return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kblocks * kBlockK);
+    int BN;
+    if (out_f32) {
+        if (Cout > 16) return fail(S2S_ERR_INVALID, "conv_fwd: fp32 NCHW output supports Cout <= 16 (got %d)", Cout);
+        BN = 16;
+        p.mode = kModeF32Nchw;
+    } else {
+        if (Cout % 64) return fail(S2S_ERR_INVALID, "conv_fwd: bf16 output needs Cout %% 64 == 0 (got %d)", Cout);
+        BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+        p.mode = kModeBf16Nhwc;
+        if (axpy_x) return fail(S2S_ERR_INVALID, "conv_fwd: axpy needs the fp32 output mode");
+    }
+    const int npad = (Cout + BN - 1) / BN * BN;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)npad};
+        cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+        cuuint32_t box[2] = {kBlockK, (cuuint32_t)BN};
+        int rc = make_tmap(&p.tmW, w_packed, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    if (out_bf16) {
+        int rc = make_act_tmap(&p.tmOut, out_bf16, B, Hout, Wout, Cout, 1);
+        if (rc) return rc;
+    }
+    p.B = B; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout;
+    p.tiles_x = (Wout + kTileW - 1) / kTileW;
+    p.tiles_y = (Hout + kTileH - 1) / kTileH;
+    p.n_tiles_n = npad / BN;
+    p.total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles_n;
+    p.BN = BN;
+    p.kblocks = kblocks;
+    p.tmem_cols = pow2_cols(2 * BN);
+    p.bias = bias;
+    p.residual = (const __nv_bfloat16*)residual;
+    p.out_f32 = out_f32;
+    p.axpy_x = axpy_x;
+    p.axpy_a = axpy_a;
+    const size_t b_bytes = (size_t)(BN < 64 ? 64 : BN) * kBlockK * 2;
+    const size_t stage_bytes = kABytes + b_bytes;
+    const size_t fixed = 2 * kOutStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
+    int stages = (int)((kSmemBudget - fixed) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(S2S_ERR_INVALID, "conv_fwd: tile does not fit in shared memory");
+    p.num_stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    int rc = set_smem(conv_igemm_kernel, smem);
+    if (rc) return rc;
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_igemm_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(p);
+    LAUNCH_CHECK("conv_igemm_kernel");
+    return S2S_OK;
+}
+
+int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int stride, int B, int Hout, int Wout,
+                   float* dw, int ldn, int n_off, void* stream) {
+    if (taps != 1 && taps != 9) return fail(S2S_ERR_INVALID, "conv_wgrad: taps = %d", taps);
+    if (Cq % 64) return fail(S2S_ERR_INVALID, "conv_wgrad: input channels must be a multiple of 64 (got %d)", Cq);
+    if (ldn % 4 || n_off % 4) return fail(S2S_ERR_INVALID, "conv_wgrad: ldn / n_off must be multiples of 4");
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_act_tmap(&p.tmP, dy, B, Hout, Wout, Cm, 1);
+    if (rc) return rc;
+    rc = make_act_tmap(&p.tmQ, x, B, Hout * stride, Wout * stride, Cq, stride);
+    if (rc) return rc;
+    p.taps = taps; p.stride = stride; p.Cq = Cq; p.Mtot = Cm; p.Ntot = Cq;
+    p.BN = (Cq % 256 == 0) ? 256 : (Cq % 128 == 0 ? 128 : 64);
+    p.m_tiles = (Cm + 127) / 128;
+    p.n_tiles = Cq / p.BN;
+    p.tiles_x = (Wout + kTileW - 1) / kTileW;
+    p.tiles_y = (Hout + kTileH - 1) / kTileH;
+    p.pix_tiles = B * p.tiles_x * p.tiles_y;
+    const int mn = taps * p.m_tiles * p.n_tiles;
+    int splits = (2 * num_sms() + mn - 1) / mn;
+    if (splits > p.pix_tiles) splits = p.pix_tiles;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.tmem_cols = pow2_cols(p.BN);
+    p.dw = dw; p.ldn = ldn; p.n_off = n_off;
+    const size_t stage_bytes = 2 * kABytes + (size_t)(p.BN / 64) * kABytes;
+    const size_t fixed = 1024 + 512;
+    int stages = (int)((kSmemBudget - fixed) / stage_bytes);
+    if (stages > 6) stages = 6;
+    p.num_stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    rc = set_smem(conv_wgrad_kernel, smem);
+    if (rc) return rc;
+    conv_wgrad_kernel<<<mn * splits, kConvThreads, smem, (cudaStream_t)stream>>>(p);
+    LAUNCH_CHECK("conv_wgrad_kernel");
+    return S2S_OK;
+}
+
+int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad, int Cin_total,
+                     int n_begin, float beta, void* stream) {
+    const long long total = (long long)M * n_count * taps;
+    unpack_wgrad_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(dw, taps, M, ldn, n_off, n_count, grad,
+                                                                                  Cin_total, n_begin, beta);
+    LAUNCH_CHECK("unpack_wgrad_kernel");
+    return S2S_OK;
+}
+
+int s2s_patch27_pack(const float* x0, const float* x1, const float* t, int B, int H, int W, int sgn, void* dst,
+                     float* xt_out, void* stream) {
+    if (!x0 || !dst || (x1 && !t) || (sgn != 1 && sgn != -1)) return fail(S2S_ERR_INVALID, "patch27_pack: bad arguments");
+    const long long npix = (long long)B * H * W;
+    patch27_pack_kernel<<<ew_grid(npix, 128), 128, 0, (cudaStream_t)stream>>>(x0, x1, t, B, H, W, sgn,
+                                                                              (__nv_bfloat16*)dst, xt_out);
+    LAUNCH_CHECK("patch27_pack_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, int c_off, void* stream) {
+    int rc = check_vec_layout(C, "gn_stats");
+    if (rc) return rc;
+    const int ppc = pick_pix_per_cta(B, HW, C);
+    dim3 grid((HW + ppc - 1) / ppc, B);
+    gn_stats_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, HW, ppc, (float2*)stats,
+                                                                  Ctot, c_off);
+    LAUNCH_CHECK("gn_stats_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
+                int HW, float eps, float* coef, float* mean_rstd, void* stream) {
+    if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_coef: G = %d, C = %d unsupported", G, C);
+    gn_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)stats, gamma, beta, film, C, G, HW, eps,
+                                                        (float2*)coef, (float2*)mean_rstd);
+    LAUNCH_CHECK("gn_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
+                 int silu, float drop_p, uint64_t seed, void* stream) {
+    int rc = check_vec_layout(C, "gn_apply");
+    if (rc) return rc;
+    if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
+    const int ppc = pick_pix_per_cta(B, HW, C);
+    dim3 grid((HW + ppc - 1) / ppc, B);
+    if (silu)
+        gn_apply_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed);
+    else
+        gn_apply_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed);
+    LAUNCH_CHECK("gn_apply_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
+                      const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
+                      uint64_t seed, void* stream) {
+    int rc = check_vec_layout(C, "gn_bwd_reduce");
+    if (rc) return rc;
+    const int ppc = pick_pix_per_cta(B, HW, C);
+    dim3 grid((HW + ppc - 1) / ppc, B);
+    if (silu)
+        gn_bwd_reduce_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed);
+    else
+        gn_bwd_reduce_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed);
+    LAUNCH_CHECK("gn_bwd_reduce_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_bwd_coef(const float* red, const float* mean_rstd, const float* gamma, const float* beta, const float* film,
+                    int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta, float* dfilm, void* stream) {
+    if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_bwd_coef: G = %d, C = %d unsupported", G, C);
+    gn_bwd_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)red, (const float2*)mean_rstd, gamma, beta,
+                                                            film, C, G, HW, (float4*)pqr, dgamma, dbeta, dfilm);
+    LAUNCH_CHECK("gn_bwd_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef, const float* pqr,
+                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed,
+                     void* stream) {
+    int rc = check_vec_layout(C, "gn_bwd_apply");
+    if (rc) return rc;
+    const int ppc = pick_pix_per_cta(B, HW, C);
+    dim3 grid((HW + ppc - 1) / ppc, B);
+    if (silu)
+        gn_bwd_apply_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
+            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed);
+    else
+        gn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
+            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed);
+    LAUNCH_CHECK("gn_bwd_apply_kernel");
+    return S2S_OK;
+}
+
+int s2s_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "upsample2x: C %% 8 != 0");
+    const long long total = (long long)B * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LAUNCH_CHECK("upsample2x_kernel");
+    return S2S_OK;
+}
+int s2s_sumpool2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "sumpool2x: C %% 8 != 0");
+    const long long total = (long long)B * H * W * (C / 8);
+    sumpool2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LAUNCH_CHECK("sumpool2x_kernel");
+    return S2S_OK;
+}
+int s2s_zero_insert2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "zero_insert2x: C %% 8 != 0");
+    const long long total = (long long)B * 4 * H * W * (C / 8);
+    zero_insert2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LAUNCH_CHECK("zero_insert2x_kernel");
+    return S2S_OK;
+}
+
+int s2s_channel_sum(const void* x, long long npix, int C, float* out, void* stream) {
+    int rc = check_vec_layout(C, "channel_sum");
+    if (rc) return rc;
+    const int rows = kEwThreads / (C / 8);
+    long long ctas = (long long)num_sms() * 8;
+    long long ppc = (npix + ctas - 1) / ctas;
+    ppc = (ppc + rows - 1) / rows * rows;
+    if (ppc < rows * 8) ppc = rows * 8;
+    const int grid = (int)((npix + ppc - 1) / ppc);
+    channel_sum_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, npix, (int)ppc, out);
+    LAUNCH_CHECK("channel_sum_kernel");
+    return S2S_OK;
+}
+
+int s2s_fm_loss(const float* v, const float* x0, const float* x1, long long n, float* loss, float* dv, void* stream) {
+    int grid = ew_grid(n / 4 + 1);
+    fm_loss_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(v, x0, x1, n, 1.0f / (float)n, loss, dv);
+    LAUNCH_CHECK("fm_loss_kernel");
+    return S2S_OK;
+}
+
+int s2s_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int HW, void* stream) {
+    const long long total = (long long)B * C * HW;
+    nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, B, C, HW);
+    LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+    return S2S_OK;
+}
+int s2s_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, void* stream) {
+    const long long total = (long long)B * C * HW;
+    nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, B, C, HW);
+    LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+    return S2S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA, NHWC bf16 activations.
+//
+//   out[b, y, x, n] = bias[n] + residual[b, y, x, n]
+//                   + sum_{segment s} sum_{tap} sum_{c} A_s[b, y*stride + dy, x*stride + dx, c] * W[n, k(s, tap, c)]
+//
+// One GEMM row = one output pixel; an M tile is an 8 x 16 pixel patch (128 rows) of one sample, fetched per filter tap
+// as ONE 5-D TMA box {64 ch, 16 w, 1, 8 h, 1 b} whose out-of-bounds rows/columns are zero-filled by the TMA unit
+// (the conv padding is therefore free).  A box lands in shared memory as [128 pixels][64 ch] with the 128-byte
+// swizzle, i.e. exactly the canonical K-major UMMA operand.  Weights are pre-packed [N][K] (K-major) and fetched as
+// 2-D boxes {64 k, BN n}.  Several "segments" share one accumulator: the two halves of a channel concat, or a 3x3
+// conv plus the 1x1 skip-connection conv of a ResBlock (the residual add then costs nothing).
+//
+// Warp roles (256 threads, persistent over tiles, 1 CTA / SM):
+//   warp 0   : TMA producer (one lane)            smem ring: full[]/empty[] mbarriers
+//   warp 1   : tcgen05.mma issuer (one lane)      accumulators: 2 TMEM stages of BN fp32 columns, tfull[]/tempty[]
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue  TMEM -> registers -> (+bias, +residual) -> bf16 -> swizzled smem -> TMA store (NHWC)
+//              or fp32 NCHW direct stores for the narrow head conv (optionally fused with the Euler update).
+//
+// Stride-2 convs read the input through a parity view {2C, W/2, 2, H/2, B}: pixel (2y+dy-1, 2x+dx-1) is
+// (channel offset pw*C, column x + (dx==0 ? -1 : 0), parity ph, row y + (dy==0 ? -1 : 0)).
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+constexpr int kTileW = 16, kTileH = 8, kTileM = kTileW * kTileH;  // 128 output pixels per tile
+constexpr int kBlockK = 64;                                      // bf16 channels per k-block = one 128 B swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;                    // 16 KB
+constexpr int kOutStageBytes = kTileM * 64 * 2;                  // 16 KB staging per 64-channel output chunk
+constexpr int kMaxSeg = 3;
+constexpr int kConvThreads = 256;
+
+enum ConvMode : int { kModeBf16Nhwc = 0, kModeF32Nchw = 1 };
+
+struct ConvSeg {
+    int taps;     // 9 (3x3, pad 1) or 1 (1x1)
+    int cblocks;  // ceil(C / 64)
+    int stride;   // 1 or 2
+    int C;        // channels of this segment's tensor
+};
+
+struct ConvParams {
+    CUtensorMap tmA[kMaxSeg];
+    CUtensorMap tmW;
+    CUtensorMap tmOut;
+    ConvSeg seg[kMaxSeg];
+    int nseg;
+    int B, Hout, Wout, Cout;
+    int tiles_x, tiles_y, n_tiles_n, total_tiles;
+    int BN;          // 16, 64, 128 or 256
+    int kblocks;     // total k-blocks per tile
+    int num_stages;
+    uint32_t tmem_cols;
+    int mode;
+    const float* bias;               // [Cout] or nullptr
+    const __nv_bfloat16* residual;   // NHWC [B, Hout, Wout, Cout] or nullptr (bf16 mode only)
+    float* out_f32;                  // NCHW [B, Cout, Hout, Wout] (fp32 mode)
+    const float* axpy_x;             // fp32 mode, optional: out = axpy_x + axpy_a * (acc + bias)
+    float axpy_a;
+};
+
+__device__ __forceinline__ void conv_decode_tile(const ConvParams& p, int tile, int& b, int& ty, int& tx, int& nt) {
+    nt = tile % p.n_tiles_n;
+    int m = tile / p.n_tiles_n;
+    tx = m % p.tiles_x;
+    m /= p.tiles_x;
+    ty = m % p.tiles_y;
+    b = m / p.tiles_y;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024 B alignment is required by the 128 B swizzle atoms.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    const uint32_t b_bytes = (uint32_t)(BN < 64 ? 64 : BN) * kBlockK * 2;  // B region per stage (>= 8 KB keeps 1 KB alignment)
+    const uint32_t stage_bytes = kABytes + b_bytes;
+    const int S = p.num_stages;
+
+    uint8_t* ring = smem;
+    uint8_t* out_stage = smem + (size_t)S * stage_bytes;  // 2 x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 2 * kOutStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+        tma_prefetch_desc(&p.tmW);
+        if (p.mode == kModeBf16Nhwc) tma_prefetch_desc(&p.tmOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int b, ty, tx, nt;
+                conv_decode_tile(p, tile, b, ty, tx, nt);
+                const int x0 = tx * kTileW, y0 = ty * kTileH, n0 = nt * BN;
+                int kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    for (int tap = 0; tap < sg.taps; ++tap) {
+                        int cx, cy, cp = 0, coff = 0;
+                        if (sg.taps == 1) {
+                            cx = x0;
+                            cy = y0;
+                        } else if (sg.stride == 1) {
+                            cx = x0 + (tap % 3) - 1;
+                            cy = y0 + (tap / 3) - 1;
+                        } else {
+                            const int dx = tap % 3, dy = tap / 3;
+                            cx = x0 + (dx == 0 ? -1 : 0);
+                            cy = y0 + (dy == 0 ? -1 : 0);
+                            cp = (dy == 1) ? 0 : 1;
+                            coff = ((dx == 1) ? 0 : 1) * sg.C;
+                        }
+                        for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
+                            uint8_t* b_dst = a_dst + kABytes;
+                            mbar_arrive_expect_tx(&full[stage], kABytes + (uint32_t)BN * kBlockK * 2);
+                            tma_load_5d(a_dst, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp, cy, b);
+                            tma_load_2d(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                            if (++stage == S) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTileM, (uint32_t)BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);  // epilogue drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[as]);  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp & 3;           // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;    // GEMM row == pixel within the tile
+        const int et = threadIdx.x - 128; // 0..127
+        int it = 0;
+        int ob = 0;                       // output staging buffer toggle
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int b, ty, tx, nt;
+            conv_decode_tile(p, tile, b, ty, tx, nt);
+            const int x0 = tx * kTileW, y0 = ty * kTileH, n0 = nt * BN;
+            const int py = y0 + row / kTileW, px = x0 + row % kTileW;
+            const bool in_img = (py < p.Hout) && (px < p.Wout);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+
+            if (p.mode == kModeF32Nchw) {
+                uint32_t v[16];
+                tmem_ld_32x16(t_row, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+                if (in_img) {
+                    for (int c = 0; c < p.Cout; ++c) {
+                        float acc = __uint_as_float(v[c]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                        const size_t o = (((size_t)b * p.Cout + c) * p.Hout + py) * p.Wout + px;
+                        if (p.axpy_x) acc = __ldg(p.axpy_x + o) + p.axpy_a * acc;
+                        p.out_f32[o] = acc;
+                    }
+                }
+                continue;
+            }
+
+            const int nchunks = BN / 64;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(t_row + ch * 64, v0);
+                tmem_ld_32x32(t_row + ch * 64 + 32, v1);
+                tmem_ld_wait();
+                if (ch == nchunks - 1) {
+                    // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                const int nbase = n0 + ch * 64;
+                uint32_t packed[32];
+                const uint4* res = nullptr;
+                if (p.residual && in_img)
+                    res = reinterpret_cast<const uint4*>(p.residual + (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout +
+                                                         nbase);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = j * 8 + e;
+                        f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                        if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                    }
+                    if (res) {
+                        const uint4 r = __ldg(res + j);
+                        float2 t;
+                        t = unpack_bf16x2(r.x); f[0] += t.x; f[1] += t.y;
+                        t = unpack_bf16x2(r.y); f[2] += t.x; f[3] += t.y;
+                        t = unpack_bf16x2(r.z); f[4] += t.x; f[5] += t.y;
+                        t = unpack_bf16x2(r.w); f[6] += t.x; f[7] += t.y;
+                    }
+                    packed[j * 4 + 0] = pack_bf16x2(f[0], f[1]);
+                    packed[j * 4 + 1] = pack_bf16x2(f[2], f[3]);
+                    packed[j * 4 + 2] = pack_bf16x2(f[4], f[5]);
+                    packed[j * 4 + 3] = pack_bf16x2(f[6], f[7]);
+                }
+                // staging buffer `ob` was last read by the TMA store issued two chunks ago
+                if (et == 0) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+                uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
+                    *reinterpret_cast<uint4*>(dst + sw * 16) =
+                        make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0) {
+                    tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, y0, b);
+                    tma_store_commit();
+                }
+                ob ^= 1;
+            }
+        }
+        if (et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// ====================================================================================================== wgrad
+//   dW[tap][m][n] += sum_{pixels in this CTA's slice} P[pixel, m] * Q[pixel (+tap shift), n]
+// P = the tensor indexing the GEMM M dimension (dY for a conv weight gradient), Q = the tensor indexing N (the conv
+// input).  Both operands are "MN-major": a TMA box {64 ch, 16 w, 1, 8 h, 1} lands as [128 pixels][64 ch], 128 B
+// swizzled, which is the canonical MN-major UMMA atom layout with K = pixels (SBO = 1024 B per 8 pixels,
+// LBO = 16 KB to the next 64-channel atom).  Split-K over pixel tiles; partial sums leave through vectorised fp32
+// reductions (red.global.add.v4.f32) into a [tap][M][N] fp32 buffer.
+struct WgradParams {
+    CUtensorMap tmP;  // 5-D {Cm, W, 1, H, B}      (output-side tensor, never shifted)
+    CUtensorMap tmQ;  // 5-D parity view of the input-side tensor
+    int taps, stride, Cq;       // Cq = channels of Q (parity offset for stride 2)
+    int Mtot, Ntot;             // real extents (Cout, Cin of this segment)
+    int BN;                     // 64, 128 or 256
+    int m_tiles, n_tiles, splits;
+    int tiles_x, tiles_y, pix_tiles;  // pixel tiles of the OUTPUT-side geometry
+    int num_stages;
+    uint32_t tmem_cols;
+    float* dw;                  // [taps][Mtot][ldn] fp32, pre-zeroed or accumulating
+    int ldn, n_off;             // row length of dw and column offset of this segment
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    const uint32_t a_bytes = 2 * kABytes;                 // M = 128 -> two 64-channel atoms
+    const uint32_t b_bytes = (uint32_t)(BN / 64) * kABytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const int S = p.num_stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+    // work item decode
+    int w = blockIdx.x;
+    const int split = w % p.splits;  w /= p.splits;
+    const int nt = w % p.n_tiles;    w /= p.n_tiles;
+    const int mt = w % p.m_tiles;    w /= p.m_tiles;
+    const int tap = w;
+    const int per = (p.pix_tiles + p.splits - 1) / p.splits;
+    const int kbeg = split * per;
+    const int kend = min(p.pix_tiles, kbeg + per);
+    const int nk = max(0, kend - kbeg);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmP);
+        tma_prefetch_desc(&p.tmQ);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sx = 0, sy = 0, cp = 0, coff = 0;
+            if (p.taps == 9) {
+                const int dx = tap % 3, dy = tap / 3;
+                if (p.stride == 1) {
+                    sx = dx - 1;
+                    sy = dy - 1;
+                } else {
+                    sx = (dx == 0 ? -1 : 0);
+                    sy = (dy == 0 ? -1 : 0);
+                    cp = (dy == 1) ? 0 : 1;
+                    coff = ((dx == 1) ? 0 : 1) * p.Cq;
+                }
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = kbeg; k < kend; ++k) {
+                int m = k;
+                const int tx = m % p.tiles_x;  m /= p.tiles_x;
+                const int ty = m % p.tiles_y;
+                const int b = m / p.tiles_y;
+                const int x0 = tx * kTileW, y0 = ty * kTileH;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                uint8_t* b_dst = a_dst + a_bytes;
+                mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                tma_load_5d(a_dst, &p.tmP, &full[stage], mt * 128, x0, 0, y0, b);
+                tma_load_5d(a_dst + kABytes, &p.tmP, &full[stage], mt * 128 + 64, x0, 0, y0, b);
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_5d(b_dst + j * kABytes, &p.tmQ, &full[stage], coff + nt * BN + j * 64, x0 + sx, cp, y0 + sy, b);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nk > 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < nk; ++k) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int kk = 0; kk < kTileM / 16; ++kk) {  // 16 pixels per MMA
+                    const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
+                    const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(tfull);
+        }
+    } else if (warp >= 4 && nk > 0) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;  // m within the tile
+        const int m = mt * 128 + row;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* dst_row = p.dw + ((size_t)tap * p.Mtot + m) * p.ldn + p.n_off + nt * BN;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c0, v);
+            tmem_ld_wait();
+            if (m < p.Mtot) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = nt * BN + c0 + j;
+                    if (n + 3 < p.Ntot) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + j),
+                                     "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                     "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.Ntot) atomicAdd(dst_row + c0 + j + e, __uint_as_float(v[j + e]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+}  // namespace s2s

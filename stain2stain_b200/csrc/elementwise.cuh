@@ -1,0 +1,621 @@
+// Bandwidth-bound kernels of the flow-matching hot path: NHWC bf16 activations, 128-bit vector loads/stores,
+// fp32 statistics.  One CTA never straddles two samples, so per-(sample, channel) coefficients live in registers.
+//
+// Thread mapping shared by the GroupNorm kernels: a pixel row of C channels is C/8 16-byte vectors ("vpp", a power of
+// two <= 256).  Thread t owns vector slot (t % vpp) and walks pixels (t / vpp), (t / vpp) + 256 / vpp, ... of its
+// CTA's pixel chunk: a warp always touches whole contiguous pixel rows -> fully coalesced 512 B requests.
+#pragma once
+#include "common.cuh"
+
+namespace s2s {
+
+constexpr int kEwThreads = 256;
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Counter-based dropout mask: element i of a tensor draws from counter (i / 4), lane (i % 4).  The mask is a pure
+// function of (seed, element index), so backward regenerates it instead of storing it.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask bits for 8 consecutive elements starting at element index e8*8 (8 bits, bit j = keep element j)
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsigned long long e8, uint32_t thresh) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint4 a = philox4x32((uint32_t)(2 * e8), (uint32_t)((2 * e8) >> 32), k0, k1);
+    const uint4 b = philox4x32((uint32_t)(2 * e8 + 1), (uint32_t)((2 * e8 + 1) >> 32), k0, k1);
+    uint32_t m = 0;
+    m |= (a.x >= thresh) << 0; m |= (a.y >= thresh) << 1; m |= (a.z >= thresh) << 2; m |= (a.w >= thresh) << 3;
+    m |= (b.x >= thresh) << 4; m |= (b.y >= thresh) << 5; m |= (b.z >= thresh) << 6; m |= (b.w >= thresh) << 7;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// OIHW fp32 -> bf16 [rows_pad][ld_k] K-major operand of the implicit GEMM.
+//   forward : dst[co][k_off + tap*ci_count + (ci-ci_begin)]           = w[co][ci][tap]          rows = Cout
+//   dgrad   : dst[ci-ci_begin][k_off + tap*Cout + co]                 = w[co][ci][taps-1-tap]   rows = ci_count
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ci_begin,
+                                        int ci_count, __nv_bfloat16* __restrict__ dst, int ld_k, int k_off,
+                                        int transpose_flip) {
+    const long long total = (long long)Cout * ci_count * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // iterate in destination order so that writes are coalesced
+        int row, tap, inner;
+        if (!transpose_flip) {
+            inner = (int)(i % ci_count);
+            tap = (int)((i / ci_count) % taps);
+            row = (int)(i / ((long long)ci_count * taps));
+            const float v = w[((size_t)row * Cin + ci_begin + inner) * taps + tap];
+            dst[(size_t)row * ld_k + k_off + (size_t)tap * ci_count + inner] = __float2bfloat16(v);
+        } else {
+            inner = (int)(i % Cout);
+            tap = (int)((i / Cout) % taps);
+            row = (int)(i / ((long long)Cout * taps));
+            const float v = w[((size_t)inner * Cin + ci_begin + row) * taps + (taps - 1 - tap)];
+            dst[(size_t)row * ld_k + k_off + (size_t)tap * Cout + inner] = __float2bfloat16(v);
+        }
+    }
+}
+
+// [taps][M][ldn] fp32 wgrad buffer -> += into OIHW fp32 gradient.  dst[m][n_begin + n][tap] += src[tap][m][n_off + n]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, int taps, int M, int ldn, int n_off, int n_count,
+                                    float* __restrict__ grad, int Cin_total, int n_begin, float beta) {
+    const long long total = (long long)M * n_count * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % taps);
+        const int n = (int)((i / taps) % n_count);
+        const int m = (int)(i / ((long long)taps * n_count));
+        const float v = src[((size_t)tap * M + m) * ldn + n_off + n];
+        float* g = grad + ((size_t)m * Cin_total + n_begin + n) * taps + tap;
+        *g = beta * (*g) + v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 patch pack
+// fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64] with channel j = tap*3 + c holding src[b, c, y + sgn*(dy-1),
+// x + sgn*(dx-1)] (zero outside the image, zeros for j >= 27).  Turns the K=27 stem conv (sgn=+1) and the dgrad/wgrad
+// of the N=3 head conv (sgn=-1) into 64-wide GEMM operands.  Optional fused flow-matching interpolation:
+// src = (1 - t_b) * x0 + t_b * x1  (torchcfm sample_xt with sigma = 0).
+__global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                    const float* __restrict__ t, int B, int H, int W, int sgn,
+                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ xt_out) {
+    const long long npix = (long long)B * H * W;
+    for (long long pidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; pidx < npix;
+         pidx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(pidx % W);
+        const int y = (int)((pidx / W) % H);
+        const int b = (int)(pidx / ((long long)W * H));
+        const float tb = (x1 != nullptr) ? t[b] : 0.f;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + sgn * (tap / 3 - 1), xx = x + sgn * (tap % 3 - 1);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const size_t o = (((size_t)b * 3 + c) * H + yy) * W + xx;
+                    float s = __ldg(x0 + o);
+                    if (x1 != nullptr) s = (1.f - tb) * s + tb * __ldg(x1 + o);
+                    v[tap * 3 + c] = s;
+                    if (xt_out != nullptr && tap == 4) xt_out[o] = s;
+                }
+            }
+        }
+        uint4* d = reinterpret_cast<uint4*>(dst + (size_t)pidx * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = v[j * 8 + e];
+            d[j] = f32_to_bf16x8(f);
+        }
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 4; j < 8; ++j) d[j] = z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm stats
+// stats[b][c_off + c] = (sum, sumsq) over the sample's pixels; fp32 atomics across the pixel chunks of a sample.
+__global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
+                                                              int pix_per_cta, float2* __restrict__ stats, int Ctot,
+                                                              int c_off) {
+    __shared__ float red[kEwThreads][17];
+    const int vpp = C >> 3;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
+    float s[8], ss[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+    int p = p0 + prow;
+    for (; p + 3 * pstep < p1; p += 4 * pstep) {  // 4 independent 16 B loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float f[8];
+            bf16x8_to_f32(u[i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += f[e];
+                ss[e] += f[e] * f[e];
+            }
+        }
+    }
+    for (; p < p1; p += pstep) {
+        float f[8];
+        bf16x8_to_f32(ldg_stream(src + (size_t)p * vpp + slot), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s[e] += f[e];
+            ss[e] += f[e] * f[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[threadIdx.x][e] = s[e];
+        red[threadIdx.x][8 + e] = ss[e];
+    }
+    __syncthreads();
+    // thread (slot, e) for prow == 0..: reduce over pixel rows.  vpp*8 = C channels, up to 2048 -> loop
+    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+        const int sl = ci >> 3, e = ci & 7;
+        float a = 0.f, q = 0.f;
+        for (int r = 0; r < pstep; ++r) {
+            a += red[r * vpp + sl][e];
+            q += red[r * vpp + sl][8 + e];
+        }
+        float* dst = reinterpret_cast<float*>(stats + (size_t)b * Ctot + c_off + ci);
+        atomicAdd(dst, a);
+        atomicAdd(dst + 1, q);
+    }
+}
+
+// Per-(sample, channel) affine coefficients of the fused normalisation:
+//   y = silu?( x * A + Bc ),  A = rstd_g * gamma_c * (1 + scale_bc),  Bc = (beta_c - mean_g*rstd_g*gamma_c)*(1+scale_bc) + shift_bc
+// Also records (mean, rstd) per (sample, group) for backward.  film: [B][2C] fp32 (scale | shift) or nullptr.
+__global__ void gn_coef_kernel(const float2* __restrict__ stats, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ film, int C, int G, int HW,
+                               float eps, float2* __restrict__ coef, float2* __restrict__ mean_rstd) {
+    const int b = blockIdx.x;
+    const int cpg = C / G;
+    __shared__ float s_mean[64], s_rstd[64];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float2 st = stats[(size_t)b * C + c];
+            a += st.x;
+            q += st.y;
+        }
+        const float n = (float)cpg * (float)HW;
+        const float mean = a / n;
+        const float var = fmaxf(q / n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        s_mean[g] = mean;
+        s_rstd[g] = rstd;
+        mean_rstd[(size_t)b * G + g] = make_float2(mean, rstd);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float ga = gamma[c], be = beta[c];
+        float A = s_rstd[g] * ga;
+        float Bc = be - s_mean[g] * A;
+        if (film != nullptr) {
+            const float sc = 1.f + film[(size_t)b * 2 * C + c];
+            const float sh = film[(size_t)b * 2 * C + C + c];
+            A *= sc;
+            Bc = Bc * sc + sh;
+        }
+        coef[(size_t)b * C + c] = make_float2(A, Bc);
+    }
+}
+
+// y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), bf16 NHWC in / out (out row stride ld_out channels).
+template <bool kSilu>
+__global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
+                                                              int pix_per_cta, const float2* __restrict__ coef,
+                                                              int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
+                                                              int ld_out, float drop_p, unsigned long long seed) {
+    const int vpp = C >> 3;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    float A[8], Bc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float2 cf = coef[(size_t)b * Ctot + c_off + slot * 8 + e];
+        A[e] = cf.x;
+        Bc[e] = cf.y;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
+    __nv_bfloat16* dst = y + (size_t)b * HW * ld_out + c_off + slot * 8;
+    const bool drop = drop_p > 0.f;
+    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    auto body = [&](const uint4& u, int p) {
+        float f[8];
+        bf16x8_to_f32(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float z = fmaf(f[e], A[e], Bc[e]);
+            f[e] = kSilu ? silu_f(z) : z;
+        }
+        if (drop) {
+            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_out >> 3) +
+                                          (unsigned long long)((c_off >> 3) + slot);
+            const uint32_t m = dropout_keep8(seed, e8, thresh);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
+        }
+        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), f32_to_bf16x8(f));
+    };
+    int p = p0 + prow;
+    for (; p + 3 * pstep < p1; p += 4 * pstep) {
+        uint4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) body(u[i], p + i * pstep);
+    }
+    for (; p < p1; p += pstep) body(ldg_stream(src + (size_t)p * vpp + slot), p);
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm backward
+// Forward: z = x*A + Bc, a = dropout(silu(z)).  Given g = dL/da:  dz = g * mask/keep * silu'(z).
+// Pass 1 (this kernel): red[b][c] = (sum_p dz, sum_p dz * xhat) with xhat = (x - mean_g) * rstd_g.
+template <bool kSilu>
+__global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   const __nv_bfloat16* __restrict__ g, int ld_g,
+                                                                   int C, int HW, int pix_per_cta,
+                                                                   const float2* __restrict__ coef,
+                                                                   const float2* __restrict__ mean_rstd, int G,
+                                                                   int Ctot, int c_off, float2* __restrict__ red_out,
+                                                                   float drop_p, unsigned long long seed) {
+    __shared__ float red[kEwThreads][17];
+    const int vpp = C >> 3;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    const int cpg = Ctot / G;
+    float A[8], Bc[8], mu[8], rs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c_off + slot * 8 + e;
+        const float2 cf = coef[(size_t)b * Ctot + c];
+        A[e] = cf.x;
+        Bc[e] = cf.y;
+        const float2 mr = mean_rstd[(size_t)b * G + c / cpg];
+        mu[e] = mr.x;
+        rs[e] = mr.y;
+    }
+    const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
+    const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
+    const bool drop = drop_p > 0.f;
+    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        float xf[8], gf[8];
+        bf16x8_to_f32(ldg_stream(xs + (size_t)p * vpp + slot), xf);
+        bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gf);
+        uint32_t m = 0xffu;
+        if (drop) {
+            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
+                                          (unsigned long long)((c_off >> 3) + slot);
+            m = dropout_keep8(seed, e8, thresh);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float z = fmaf(xf[e], A[e], Bc[e]);
+            float dz = ((m >> e) & 1u) ? gf[e] * keep_scale : 0.f;
+            if (kSilu) dz *= silu_grad_f(z);
+            s1[e] += dz;
+            s2[e] += dz * (xf[e] - mu[e]) * rs[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[threadIdx.x][e] = s1[e];
+        red[threadIdx.x][8 + e] = s2[e];
+    }
+    __syncthreads();
+    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+        const int sl = ci >> 3, e = ci & 7;
+        float a = 0.f, q = 0.f;
+        for (int r = 0; r < pstep; ++r) {
+            a += red[r * vpp + sl][e];
+            q += red[r * vpp + sl][8 + e];
+        }
+        float* dst = reinterpret_cast<float*>(red_out + (size_t)b * Ctot + c_off + ci);
+        atomicAdd(dst, a);
+        atomicAdd(dst + 1, q);
+    }
+}
+
+// Pass 2 coefficients + parameter gradients.  One CTA per sample.
+//   dx = dz * P + x * Q + R,  P = rstd*gamma',  Q = -rstd^2 * m2,  R = -rstd*m1 + mean*rstd^2*m2
+//   m1 = sum_{c in g} gamma'_c S1_c / N,  m2 = sum_{c in g} gamma'_c S2_c / N,  gamma' = gamma * (1 + scale)
+//   dgamma_c += sum_b S2 (1+scale)   dbeta_c += sum_b S1 (1+scale)   dscale_bc = gamma S2 + beta S1   dshift_bc = S1
+__global__ void gn_bwd_coef_kernel(const float2* __restrict__ red, const float2* __restrict__ mean_rstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ film, int C, int G, int HW, float4* __restrict__ pqr,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm) {
+    const int b = blockIdx.x;
+    const int cpg = C / G;
+    __shared__ float s_m1[64], s_m2[64];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float sc = film ? 1.f + film[(size_t)b * 2 * C + c] : 1.f;
+            const float gp = gamma[c] * sc;
+            const float2 r = red[(size_t)b * C + c];
+            m1 += gp * r.x;
+            m2 += gp * r.y;
+        }
+        const float n = (float)cpg * (float)HW;
+        s_m1[g] = m1 / n;
+        s_m2[g] = m2 / n;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float2 mr = mean_rstd[(size_t)b * G + g];
+        const float sc = film ? 1.f + film[(size_t)b * 2 * C + c] : 1.f;
+        const float2 r = red[(size_t)b * C + c];
+        const float P = mr.y * gamma[c] * sc;
+        const float Q = -mr.y * mr.y * s_m2[g];
+        const float R = -mr.y * s_m1[g] + mr.x * mr.y * mr.y * s_m2[g];
+        pqr[(size_t)b * C + c] = make_float4(P, Q, R, 0.f);
+        atomicAdd(dgamma + c, r.y * sc);
+        atomicAdd(dbeta + c, r.x * sc);
+        if (dfilm != nullptr) {
+            dfilm[(size_t)b * 2 * C + c] = gamma[c] * r.y + beta[c] * r.x;
+            dfilm[(size_t)b * 2 * C + C + c] = r.x;
+        }
+    }
+}
+
+// Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; bf16 NHWC.
+template <bool kSilu>
+__global__ void __launch_bounds__(kEwThreads) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ g, int ld_g,
+                                                                  int C, int HW, int pix_per_cta,
+                                                                  const float2* __restrict__ coef,
+                                                                  const float4* __restrict__ pqr, int Ctot, int c_off,
+                                                                  const __nv_bfloat16* __restrict__ add,
+                                                                  __nv_bfloat16* __restrict__ dx, float drop_p,
+                                                                  unsigned long long seed) {
+    const int vpp = C >> 3;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    float A[8], Bc[8], P[8], Q[8], R[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c_off + slot * 8 + e;
+        const float2 cf = coef[(size_t)b * Ctot + c];
+        A[e] = cf.x;
+        Bc[e] = cf.y;
+        const float4 t = pqr[(size_t)b * Ctot + c];
+        P[e] = t.x;
+        Q[e] = t.y;
+        R[e] = t.z;
+    }
+    const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
+    const uint4* as = add ? reinterpret_cast<const uint4*>(add + (size_t)b * HW * C) : nullptr;
+    uint4* ds = reinterpret_cast<uint4*>(dx + (size_t)b * HW * C);
+    const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
+    const bool drop = drop_p > 0.f;
+    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
+    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        float xf[8], gf[8];
+        bf16x8_to_f32(ldg_stream(xs + (size_t)p * vpp + slot), xf);
+        bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gf);
+        uint32_t m = 0xffu;
+        if (drop) {
+            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
+                                          (unsigned long long)((c_off >> 3) + slot);
+            m = dropout_keep8(seed, e8, thresh);
+        }
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float z = fmaf(xf[e], A[e], Bc[e]);
+            float dz = ((m >> e) & 1u) ? gf[e] * keep_scale : 0.f;
+            if (kSilu) dz *= silu_grad_f(z);
+            o[e] = dz * P[e] + xf[e] * Q[e] + R[e];
+        }
+        if (as) {
+            float af[8];
+            bf16x8_to_f32(ldg_stream(as + (size_t)p * vpp + slot), af);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += af[e];
+        }
+        stg_stream(ds + (size_t)p * vpp + slot, f32_to_bf16x8(o));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ resampling
+// nearest x2 upsample, NHWC bf16: out[b, y, x, :] = in[b, y/2, x/2, :]
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp) {
+    const long long total = (long long)B * (2 * H) * (2 * W) * vpp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpp);
+        long long r = i / vpp;
+        const int x = (int)(r % (2 * W));  r /= (2 * W);
+        const int y = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        stg_stream(out + i, ldg_stream(in + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * vpp + v));
+    }
+}
+// backward of nearest x2: out[b, y, x, :] = sum of the 2x2 block of in (fp32 accumulate)
+__global__ void sumpool2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp) {
+    const long long total = (long long)B * H * W * vpp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpp);
+        long long r = i / vpp;
+        const int x = (int)(r % W);  r /= W;
+        const int y = (int)(r % H);
+        const int b = (int)(r / H);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                bf16x8_to_f32(ldg_stream(in + (((size_t)b * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * vpp + v), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
+        stg_stream(out + i, f32_to_bf16x8(acc));
+    }
+}
+// zero-insertion (transposed stride-2 conv as a stride-1 conv): out[b, 2y, 2x, :] = in[b, y, x, :], 0 elsewhere
+__global__ void zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp) {
+    const long long total = (long long)B * (2 * H) * (2 * W) * vpp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpp);
+        long long r = i / vpp;
+        const int x = (int)(r % (2 * W));  r /= (2 * W);
+        const int y = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (((x | y) & 1) == 0) val = ldg_stream(in + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * vpp + v);
+        stg_stream(out + i, val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ misc reductions
+// per-channel sum over all pixels of an NHWC bf16 tensor (bias gradients): out[c] += sum_{b,p} x[b,p,c]
+__global__ void __launch_bounds__(kEwThreads) channel_sum_kernel(const __nv_bfloat16* __restrict__ x, int C,
+                                                                 long long npix, int pix_per_cta,
+                                                                 float* __restrict__ out) {
+    __shared__ float red[kEwThreads][9];
+    const int vpp = C >> 3;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const long long p0 = (long long)blockIdx.x * pix_per_cta;
+    const long long p1 = min(npix, p0 + pix_per_cta);
+    const uint4* src = reinterpret_cast<const uint4*>(x);
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (long long p = p0 + prow; p < p1; p += pstep) {
+        float f[8];
+        bf16x8_to_f32(ldg_stream(src + p * vpp + slot), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
+    __syncthreads();
+    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+        const int sl = ci >> 3, e = ci & 7;
+        float a = 0.f;
+        for (int r = 0; r < pstep; ++r) a += red[r * vpp + sl][e];
+        atomicAdd(out + ci, a);
+    }
+}
+
+// Flow-matching loss: loss += sum (v - (x1 - x0))^2 * inv_n ; dv = 2 (v - (x1 - x0)) * inv_n * gscale.  fp32 NCHW.
+__global__ void __launch_bounds__(kEwThreads) fm_loss_kernel(const float* __restrict__ v, const float* __restrict__ x0,
+                                                             const float* __restrict__ x1, long long n, float inv_n,
+                                                             float* __restrict__ loss, float* __restrict__ dv) {
+    float acc = 0.f;
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(v)[i];
+        const float4 s = reinterpret_cast<const float4*>(x0)[i];
+        const float4 t = reinterpret_cast<const float4*>(x1)[i];
+        float4 d = make_float4(a.x - (t.x - s.x), a.y - (t.y - s.y), a.z - (t.z - s.z), a.w - (t.w - s.w));
+        acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        if (dv) reinterpret_cast<float4*>(dv)[i] = make_float4(2.f * inv_n * d.x, 2.f * inv_n * d.y, 2.f * inv_n * d.z, 2.f * inv_n * d.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long i = n4 << 2; i < n; ++i) {
+            const float d = v[i] - (x1[i] - x0[i]);
+            acc += d * d;
+            if (dv) dv[i] = 2.f * inv_n * d;
+        }
+    }
+    __shared__ float wsum[kEwThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < kEwThreads / 32 ? wsum[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(loss, t * inv_n);
+    }
+}
+
+// layout changes between the reference's fp32 NCHW tensors and the engine's bf16 NHWC tensors
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                             int C, int HW) {
+    const long long total = (long long)B * C * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        const int p = (int)(r % HW);
+        const int b = (int)(r / HW);
+        out[i] = __float2bfloat16(in[((size_t)b * C + c) * HW + p]);
+    }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B,
+                                             int C, int HW) {
+    const long long total = (long long)B * C * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const long long r = i / HW;
+        const int c = (int)(r % C);
+        const int b = (int)(r / C);
+        out[i] = __bfloat162float(in[((size_t)b * HW + p) * C + c]);
+    }
+}
+
+}  // namespace s2s
