@@ -9,7 +9,7 @@
  *
  * Conventions
  *   - all pointers are DEVICE pointers (caller-owned, no allocation inside), `stream` is a cudaStream_t passed as void*;
- *   - activations are bf16 NHWC, parameters/gradients fp32 in the reference's own layouts (OIHW conv weights),
+ *   - activations are 16-bit NHWC (fp16 forward / bf16 gradients, see S2S_FMT_*), parameters/gradients fp32 in the reference's own layouts (OIHW conv weights),
  *     image-space tensors (x0, x1, xt, v) fp32 NCHW exactly as the reference passes them;
  *   - every function is stream-ordered and re-entrant, returns 0 on success or a negative code; s2s_last_error()
  *     returns a thread-local message for the last failure.  Nothing falls back to the CPU.
@@ -28,6 +28,11 @@ extern "C" {
 #define S2S_ERR_CUDA (-2)    /* CUDA runtime / driver error                */
 #define S2S_ERR_TMAP (-3)    /* cuTensorMapEncodeTiled rejected a tensor   */
 
+/* 16-bit storage formats ("fmt" arguments).  Forward activations / forward weights default to fp16, gradients to
+ * bf16; both feed the same tcgen05 kind::f16 MMA (formats are set per operand in the instruction descriptor). */
+#define S2S_FMT_BF16 0
+#define S2S_FMT_F16 1
+
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
 int s2s_num_sms(void);
@@ -45,7 +50,7 @@ typedef struct {
  * transpose_flip = 1: dgrad operand    dst[ci - ci_begin][k_off + tap*Cout + co]       = w[co][ci][taps-1-tap]
  * Replaces: the implicit weight handling of F.conv2d / conv backward (torchcfm unet.py conv_nd). */
 int s2s_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst_bf16,
-                         int ld_k, int k_off, int transpose_flip, void* stream);
+                         int ld_k, int k_off, int transpose_flip, int fmt, void* stream);
 
 /* Fused implicit-GEMM convolution (tcgen05 + TMA).
  *   acc[b,y,x,n] = sum_s sum_tap sum_c srcs[s][b, y*stride+dy, x*stride+dx, c] * w[n][k]     (k = segment, tap, c order)
@@ -55,14 +60,15 @@ int s2s_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int c
  * the head conv + Euler update `x + dt * v` of torchdyn's fixed-step solver. */
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
-                 const float* axpy_x, float axpy_a, void* stream);
+                 const float* axpy_x, float axpy_a, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream);
 
 /* Weight gradient of one conv segment (tcgen05, split-K over pixels, fp32 reductions):
  *   dw[tap][m][n_off + n] += sum_{b,y,x} dy[b,y,x,m] * x[b, y*stride+dy, x*stride+dx, n]
- * dy: bf16 NHWC [B,Hout,Wout,Cm]; x: bf16 NHWC [B,Hout*stride,Wout*stride,Cq]; dw: fp32 [taps][Cm][ldn].
+ * dy: 16-bit NHWC [B,Hout,Wout,Cm]; x: 16-bit NHWC [B,Hout*stride,Wout*stride,Cq]; dw: fp32 [taps][Cm][ldn].
+ * dy_fmt must equal x_fmt (the MMA takes one operand format; mixed fp16 x bf16 is an illegal instruction on sm_100a).
  * Replaces: the weight half of conv2d backward (cudnn wgrad). */
 int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int stride, int B, int Hout, int Wout,
-                   float* dw, int ldn, int n_off, void* stream);
+                   float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream);
 
 /* dw fp32 [taps][M][ldn] -> grad_oihw[m][n_begin + n][tap] = beta * grad + dw[tap][m][n_off + n] */
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad_oihw,
@@ -73,13 +79,18 @@ int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n
  * xt = (1 - t_b) x0 + t_b x1 (torchcfm ConditionalFlowMatcher.sample_xt, sigma = 0), optionally also written to
  * xt_out (fp32 NCHW). */
 int s2s_patch27_pack(const float* x0, const float* x1, const float* t, int B, int H, int W, int sgn, void* dst_bf16,
-                     float* xt_out, void* stream);
+                     float* xt_out, int fmt, void* stream);
 
-/* GroupNorm(32, C) statistics of a bf16 NHWC tensor: stats[b][c_off + c] += (sum, sumsq). stats: fp32 [B][Ctot][2],
- * zeroed by the caller.  Replaces pass 1 of ATen native_group_norm. */
-int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, int c_off, void* stream);
+/* Number of pixel chunks the normalisation kernels cut one sample into (a function of B and HW only). */
+int s2s_gn_chunks(int B, int HW);
 
-/* Per-(sample, channel) coefficients: A = rstd*gamma*(1+scale), Bc = (beta - mean*rstd*gamma)*(1+scale) + shift.
+/* GroupNorm(32, C) statistics of a 16-bit NHWC tensor, deterministic two-stage reduction:
+ * stats[b][chunk][c_off + c] = (sum, sumsq) over the chunk's pixels.  stats: fp32 [B][s2s_gn_chunks][Ctot][2] (no
+ * zeroing needed; every source of a concat writes its own channel range).  Replaces pass 1 of ATen native_group_norm. */
+int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, int c_off, int x_fmt, void* stream);
+
+/* Folds the chunk partials, then per-(sample, channel) coefficients:
+ * A = rstd*gamma*(1+scale), Bc = (beta - mean*rstd*gamma)*(1+scale) + shift.
  * film: fp32 [B][2C] = ResBlock emb_layers output (scale | shift) or NULL.  coef: [B][C][2], mean_rstd: [B][G][2]. */
 int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
                 int HW, float eps, float* coef, float* mean_rstd, void* stream);
@@ -87,36 +98,41 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
 /* y[b,p,c_off+c] = dropout(silu?(x[b,p,c]*A + Bc)); y row stride ld_out channels (concat written in place).
  * Replaces: GroupNorm32 apply + `* (1 + scale) + shift` + SiLU + Dropout (+ torch.cat) of torchcfm ResBlock. */
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
-                 int silu, float drop_p, uint64_t seed, void* stream);
+                 int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream);
 
 /* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g).
- *   reduce: red[b][c_off+c] += (sum dz, sum dz*xhat)                     (red fp32 [B][Ctot][2], caller-zeroed)
- *   coef  : pqr[b][c] = (P,Q,R,0); dgamma/dbeta += ...; dfilm[b][2C] = (dscale | dshift)
+ *   reduce: red_part[b][chunk][c_off+c] = (sum dz, sum dz*xhat) over the chunk   (fp32 [B][s2s_gn_chunks][Ctot][2])
+ *   coef  : folds red_part into red[B][C][2]; pqr[b][c] = (P,Q,R,0); dgamma/dbeta += ...; dfilm[b][2C] = (dscale | dshift)
  *   apply : dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c])                      (bf16 NHWC [B,HW,C]) */
 int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
                       const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
-                      uint64_t seed, void* stream);
-int s2s_gn_bwd_coef(const float* red, const float* mean_rstd, const float* gamma, const float* beta, const float* film,
-                    int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta, float* dfilm, void* stream);
+                      uint64_t seed, int x_fmt, int g_fmt, void* stream);
+int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,
+                    const float* film, int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta,
+                    float* dfilm, void* stream);
 int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef, const float* pqr,
-                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed,
-                     void* stream);
+                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed, int x_fmt,
+                     int g_fmt, void* stream);
 
 /* nearest x2 upsample (F.interpolate(scale_factor=2, mode="nearest")), its adjoint, and zero insertion (the adjoint of
  * a stride-2 subsampling), all bf16 NHWC with C % 8 == 0.  H, W are the SMALL spatial dims. */
 int s2s_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream);
-int s2s_sumpool2x(const void* in, void* out, int B, int H, int W, int C, void* stream);
+int s2s_sumpool2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream);
 int s2s_zero_insert2x(const void* in, void* out, int B, int H, int W, int C, void* stream);
 
 /* out[c] += sum over pixels of bf16 NHWC x (conv bias gradient). */
-int s2s_channel_sum(const void* x, long long npix, int C, float* out, void* stream);
+int s2s_channel_sum(const void* x, long long npix, int C, float* out, int fmt, void* stream);
 
 /* loss += mean((v - (x1 - x0))^2); dv = 2 (v - (x1 - x0)) / n (may be NULL).  fp32 NCHW, n elements.
  * Replaces: `ut = x1 - x0`, `torch.mean((vt - ut) ** 2)` and its backward (conditional_flow_matching.py:66,72). */
 int s2s_fm_loss(const float* v, const float* x0, const float* x1, long long n, float* loss, float* dv, void* stream);
 
-int s2s_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int HW, void* stream);
-int s2s_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, void* stream);
+/* 16-bit storage format conversion of n elements (n % 8 == 0), e.g. fp16 saved activations -> bf16 wgrad operands
+ * (the two operands of one tcgen05 kind::f16 MMA must share a format). */
+int s2s_convert16(const void* in, void* out, long long n, int in_fmt, int out_fmt, void* stream);
+
+int s2s_nchw_f32_to_nhwc16(const float* in, void* out, int B, int C, int HW, int fmt, void* stream);
+int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int fmt, void* stream);
 
 #ifdef __cplusplus
 }

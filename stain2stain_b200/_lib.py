@@ -30,24 +30,26 @@ SIGNATURES = {
     "s2s_last_error": [],
     "s2s_abi_version": [],
     "s2s_num_sms": [],
-    "s2s_pack_conv_weight": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
-    "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp],
-    "s2s_conv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "s2s_pack_conv_weight": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
+    "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp],
+    "s2s_conv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
     "s2s_unpack_wgrad": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp],
-    "s2s_patch27_pack": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
-    "s2s_gn_stats": [_vp, _i, _i, _i, _vp, _i, _i, _vp],
+    "s2s_patch27_pack": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "s2s_gn_stats": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp],
     "s2s_gn_coef": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
-    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _f, _u64, _vp],
-    "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _vp],
-    "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _vp],
+    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _f, _u64, _i, _i, _vp],
+    "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _i, _i, _vp],
+    "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "s2s_gn_chunks": [_i, _i],
+    "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _i, _i, _vp],
     "s2s_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "s2s_sumpool2x": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_sumpool2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "s2s_zero_insert2x": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "s2s_channel_sum": [_vp, _ll, _i, _vp, _vp],
+    "s2s_channel_sum": [_vp, _ll, _i, _vp, _i, _vp],
     "s2s_fm_loss": [_vp, _vp, _vp, _ll, _vp, _vp, _vp],
-    "s2s_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i, _i, _i, _vp],
-    "s2s_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
+    "s2s_convert16": [_vp, _vp, _ll, _i, _i, _vp],
+    "s2s_nchw_f32_to_nhwc16": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
 }
 _RESTYPES = {"s2s_last_error": C.c_char_p}
 

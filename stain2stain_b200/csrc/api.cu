@@ -114,26 +114,28 @@ int ew_grid(long long work_items, int threads = kEwThreads) {
 }
 
 // pixels per CTA for the (chunk, sample) grids of the normalisation kernels: ~4 CTAs per SM-wave, >= 64 pixel rows
-int pick_pix_per_cta(int B, int HW, int C) {
-    const int vpp = C / 8;
-    const int rows = kEwThreads / vpp;  // pixels touched per block iteration
+// Depends on (B, HW) only, so that every source of a channel concat is cut into the same pixel chunks (the
+// per-chunk partial statistics of the sources then line up).
+int pick_pix_per_cta(int B, int HW, int /*C*/) {
     long long target_ctas = (long long)num_sms() * 8;
     long long chunks = (target_ctas + B - 1) / B;
     if (chunks < 1) chunks = 1;
     long long ppc = (HW + chunks - 1) / chunks;
-    const long long min_ppc = (long long)rows * 8;
-    if (ppc < min_ppc) ppc = min_ppc;
-    ppc = (ppc + rows - 1) / rows * rows;
+    if (ppc < 128) ppc = 128;
+    ppc = (ppc + 31) / 32 * 32;
     if (ppc > HW) ppc = HW;
     return (int)ppc;
 }
 
-bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
 int check_vec_layout(int C, const char* who) {
-    if (C % 8 || !is_pow2(C / 8) || C / 8 > kEwThreads)
-        return fail(S2S_ERR_INVALID, "%s: C = %d unsupported (need C/8 a power of two <= %d)", who, C, kEwThreads);
+    if (C <= 0 || C % 8 || C / 8 > kEwThreads)
+        return fail(S2S_ERR_INVALID, "%s: C = %d unsupported (need C %% 8 == 0 and C <= %d)", who, C, 8 * kEwThreads);
     return S2S_OK;
+}
+// block size of the (slot, pixel-row) mapping: vpp * floor(256 / vpp) threads
+int vec_threads(int C) {
+    const int vpp = C / 8;
+    return vpp * (kEwThreads / vpp);
 }
 
 }  // namespace
@@ -145,20 +147,23 @@ int s2s_abi_version(void) { return 1; }
 int s2s_num_sms(void) { return num_sms(); }
 
 int s2s_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst, int ld_k,
-                         int k_off, int transpose_flip, void* stream) {
+                         int k_off, int transpose_flip, int fmt, void* stream) {
     if (!w || !dst || Cout <= 0 || ci_count <= 0 || ci_begin < 0 || ci_begin + ci_count > Cin || (taps != 1 && taps != 9))
         return fail(S2S_ERR_INVALID, "pack_conv_weight: bad arguments");
     const long long total = (long long)Cout * ci_count * taps;
     pack_conv_weight_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(
-        w, Cout, Cin, taps, ci_begin, ci_count, (__nv_bfloat16*)dst, ld_k, k_off, transpose_flip);
+        w, Cout, Cin, taps, ci_begin, ci_count, (uint16_t*)dst, ld_k, k_off, transpose_flip, fmt);
     LAUNCH_CHECK("pack_conv_weight_kernel");
     return S2S_OK;
 }
 
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
-                 const float* axpy_x, float axpy_a, void* stream) {
+                 const float* axpy_x, float axpy_a, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream) {
     if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
+    if (a_fmt != w_fmt)
+        return fail(S2S_ERR_INVALID, "conv_fwd: activations and weights must share one 16-bit format (tcgen05 kind::f16 "
+                                     "rejects mixed fp16 x bf16 operands)");
     if ((out_bf16 != nullptr) == (out_f32 != nullptr))
         return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
     ConvParams p;
@@ -215,6 +220,7 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
     p.out_f32 = out_f32;
     p.axpy_x = axpy_x;
     p.axpy_a = axpy_a;
+    p.a_fmt = a_fmt; p.w_fmt = w_fmt; p.out_fmt = out_fmt; p.res_fmt = res_fmt;
     const size_t b_bytes = (size_t)(BN < 64 ? 64 : BN) * kBlockK * 2;
     const size_t stage_bytes = kABytes + b_bytes;
     const size_t fixed = 2 * kOutStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
@@ -232,8 +238,10 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
 }
 
 int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int stride, int B, int Hout, int Wout,
-                   float* dw, int ldn, int n_off, void* stream) {
+                   float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream) {
     if (taps != 1 && taps != 9) return fail(S2S_ERR_INVALID, "conv_wgrad: taps = %d", taps);
+    if (dy_fmt != x_fmt)
+        return fail(S2S_ERR_INVALID, "conv_wgrad: dy and x must share one 16-bit format (convert with s2s_convert16)");
     if (Cq % 64) return fail(S2S_ERR_INVALID, "conv_wgrad: input channels must be a multiple of 64 (got %d)", Cq);
     if (ldn % 4 || n_off % 4) return fail(S2S_ERR_INVALID, "conv_wgrad: ldn / n_off must be multiples of 4");
     WgradParams p;
@@ -256,6 +264,7 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     p.splits = splits;
     p.tmem_cols = pow2_cols(p.BN);
     p.dw = dw; p.ldn = ldn; p.n_off = n_off;
+    p.p_fmt = dy_fmt; p.q_fmt = x_fmt;
     const size_t stage_bytes = 2 * kABytes + (size_t)(p.BN / 64) * kABytes;
     const size_t fixed = 1024 + 512;
     int stages = (int)((kSmemBudget - fixed) / stage_bytes);
@@ -279,95 +288,104 @@ int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n
 }
 
 int s2s_patch27_pack(const float* x0, const float* x1, const float* t, int B, int H, int W, int sgn, void* dst,
-                     float* xt_out, void* stream) {
+                     float* xt_out, int fmt, void* stream) {
     if (!x0 || !dst || (x1 && !t) || (sgn != 1 && sgn != -1)) return fail(S2S_ERR_INVALID, "patch27_pack: bad arguments");
     const long long npix = (long long)B * H * W;
     patch27_pack_kernel<<<ew_grid(npix, 128), 128, 0, (cudaStream_t)stream>>>(x0, x1, t, B, H, W, sgn,
-                                                                              (__nv_bfloat16*)dst, xt_out);
+                                                                              (__nv_bfloat16*)dst, xt_out, fmt);
     LAUNCH_CHECK("patch27_pack_kernel");
     return S2S_OK;
 }
 
-int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, int c_off, void* stream) {
+int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, int c_off, int x_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_stats");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    gn_stats_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, HW, ppc, (float2*)stats,
-                                                                  Ctot, c_off);
+    gn_stats_kernel<<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, HW, ppc, (float2*)stats,
+                                                                  Ctot, c_off, x_fmt);
     LAUNCH_CHECK("gn_stats_kernel");
     return S2S_OK;
+}
+
+int s2s_gn_chunks(int B, int HW) {
+    const int ppc = pick_pix_per_cta(B, HW, 0);
+    return (HW + ppc - 1) / ppc;
 }
 
 int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
                 int HW, float eps, float* coef, float* mean_rstd, void* stream) {
     if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_coef: G = %d, C = %d unsupported", G, C);
-    gn_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)stats, gamma, beta, film, C, G, HW, eps,
-                                                        (float2*)coef, (float2*)mean_rstd);
+    gn_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)stats, s2s_gn_chunks(B, HW), gamma, beta, film,
+                                                        C, G, HW, eps, (float2*)coef, (float2*)mean_rstd);
     LAUNCH_CHECK("gn_coef_kernel");
     return S2S_OK;
 }
 
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
-                 int silu, float drop_p, uint64_t seed, void* stream) {
+                 int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_apply");
     if (rc) return rc;
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
     if (silu)
-        gn_apply_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed);
+        gn_apply_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed,
+            x_fmt, y_fmt);
     else
-        gn_apply_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed);
+        gn_apply_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed,
+            x_fmt, y_fmt);
     LAUNCH_CHECK("gn_apply_kernel");
     return S2S_OK;
 }
 
 int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
                       const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
-                      uint64_t seed, void* stream) {
+                      uint64_t seed, int x_fmt, int g_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_bwd_reduce");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
     if (silu)
-        gn_bwd_reduce_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+        gn_bwd_reduce_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed);
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, x_fmt, g_fmt);
     else
-        gn_bwd_reduce_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+        gn_bwd_reduce_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed);
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, x_fmt, g_fmt);
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
 }
 
-int s2s_gn_bwd_coef(const float* red, const float* mean_rstd, const float* gamma, const float* beta, const float* film,
-                    int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta, float* dfilm, void* stream) {
+int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,
+                    const float* film, int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta,
+                    float* dfilm, void* stream) {
     if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_bwd_coef: G = %d, C = %d unsupported", G, C);
-    gn_bwd_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)red, (const float2*)mean_rstd, gamma, beta,
-                                                            film, C, G, HW, (float4*)pqr, dgamma, dbeta, dfilm);
+    gn_bwd_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)red_part, s2s_gn_chunks(B, HW), (float2*)red,
+                                                            (const float2*)mean_rstd, gamma, beta, film, C, G, HW,
+                                                            (float4*)pqr, dgamma, dbeta, dfilm);
     LAUNCH_CHECK("gn_bwd_coef_kernel");
     return S2S_OK;
 }
 
 int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef, const float* pqr,
-                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed,
-                     void* stream) {
+                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed, int x_fmt,
+                     int g_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_bwd_apply");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
     if (silu)
-        gn_bwd_apply_kernel<true><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+        gn_bwd_apply_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed);
+            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, x_fmt, g_fmt);
     else
-        gn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(
+        gn_bwd_apply_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed);
+            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, x_fmt, g_fmt);
     LAUNCH_CHECK("gn_bwd_apply_kernel");
     return S2S_OK;
 }
@@ -379,10 +397,10 @@ int s2s_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* 
     LAUNCH_CHECK("upsample2x_kernel");
     return S2S_OK;
 }
-int s2s_sumpool2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+int s2s_sumpool2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream) {
     if (C % 8) return fail(S2S_ERR_INVALID, "sumpool2x: C %% 8 != 0");
     const long long total = (long long)B * H * W * (C / 8);
-    sumpool2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    sumpool2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8, fmt);
     LAUNCH_CHECK("sumpool2x_kernel");
     return S2S_OK;
 }
@@ -394,7 +412,7 @@ int s2s_zero_insert2x(const void* in, void* out, int B, int H, int W, int C, voi
     return S2S_OK;
 }
 
-int s2s_channel_sum(const void* x, long long npix, int C, float* out, void* stream) {
+int s2s_channel_sum(const void* x, long long npix, int C, float* out, int fmt, void* stream) {
     int rc = check_vec_layout(C, "channel_sum");
     if (rc) return rc;
     const int rows = kEwThreads / (C / 8);
@@ -403,7 +421,7 @@ int s2s_channel_sum(const void* x, long long npix, int C, float* out, void* stre
     ppc = (ppc + rows - 1) / rows * rows;
     if (ppc < rows * 8) ppc = rows * 8;
     const int grid = (int)((npix + ppc - 1) / ppc);
-    channel_sum_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, npix, (int)ppc, out);
+    channel_sum_kernel<<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, npix, (int)ppc, out, fmt);
     LAUNCH_CHECK("channel_sum_kernel");
     return S2S_OK;
 }
@@ -415,15 +433,23 @@ int s2s_fm_loss(const float* v, const float* x0, const float* x1, long long n, f
     return S2S_OK;
 }
 
-int s2s_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int HW, void* stream) {
+int s2s_convert16(const void* in, void* out, long long n, int in_fmt, int out_fmt, void* stream) {
+    if (n % 8) return fail(S2S_ERR_INVALID, "convert16: n %% 8 != 0");
+    convert16_kernel<<<ew_grid(n / 8), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, n / 8,
+                                                                              in_fmt, out_fmt);
+    LAUNCH_CHECK("convert16_kernel");
+    return S2S_OK;
+}
+
+int s2s_nchw_f32_to_nhwc16(const float* in, void* out, int B, int C, int HW, int fmt, void* stream) {
     const long long total = (long long)B * C * HW;
-    nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, B, C, HW);
+    nchw_f32_to_nhwc_bf16_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(in, (uint16_t*)out, B, C, HW, fmt);
     LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
     return S2S_OK;
 }
-int s2s_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, void* stream) {
+int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int fmt, void* stream) {
     const long long total = (long long)B * C * HW;
-    nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, B, C, HW);
+    nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint16_t*)in, out, B, C, HW, fmt);
     LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
     return S2S_OK;
 }

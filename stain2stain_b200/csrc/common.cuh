@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -170,14 +171,21 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor for kind::f16, A/B = bf16, D = fp32, M x N tile.  major bits: 0 = K-major, 1 = MN-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
-                                                       uint32_t b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
-           ((M >> 4) << 24);
+// Instruction descriptor for kind::f16, A/B = fp16 or bf16 (independently), D = fp32, M x N tile.  major bits: 0 = K-major, 1 = MN-major.
+// a_fmt / b_fmt: Fmt of each operand (descriptor encoding: F16 = 0, BF16 = 1).
+__host__ __device__ constexpr uint32_t umma_idesc_16b(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                      int a_fmt, int b_fmt) {
+    return (1u << 4) | ((a_fmt == 1 ? 0u : 1u) << 7) | ((b_fmt == 1 ? 0u : 1u) << 10) | (a_mn_major << 15) |
+           (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ numerics
+// 16-bit storage formats of the engine.  Forward activations / forward weights default to fp16 (11-bit significand:
+// 8x less rounding noise than bf16 at the same tensor-core rate), gradients are bf16 (fp32's exponent range, no loss
+// scaling).  Both are operands of the same tcgen05 kind::f16 MMA; the A/B formats are set per launch in the
+// instruction descriptor.
+enum Fmt : int { kFmtBF16 = 0, kFmtF16 = 1 };
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -185,6 +193,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {  // saturating: never produces inf
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int fmt) {
+    return fmt == kFmtF16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
+    return fmt == kFmtF16 ? unpack_f16x2(u) : unpack_bf16x2(u);
+}
+__device__ __forceinline__ uint16_t pack1(float v, int fmt) {
+    if (fmt == kFmtF16) return (uint16_t)(pack_f16x2(v, 0.f) & 0xffffu);
+    __nv_bfloat16 b = __float2bfloat16(v);
+    return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float unpack1(uint16_t u, int fmt) {
+    if (fmt == kFmtF16) return __half2float(*reinterpret_cast<__half*>(&u));
+    return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
 }
 __device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad_f(float z) {

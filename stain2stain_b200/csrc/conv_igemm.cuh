@@ -54,10 +54,11 @@ struct ConvParams {
     uint32_t tmem_cols;
     int mode;
     const float* bias;               // [Cout] or nullptr
-    const __nv_bfloat16* residual;   // NHWC [B, Hout, Wout, Cout] or nullptr (bf16 mode only)
+    const __nv_bfloat16* residual;   // NHWC [B, Hout, Wout, Cout] (16-bit, res_fmt) or nullptr (NHWC mode only)
     float* out_f32;                  // NCHW [B, Cout, Hout, Wout] (fp32 mode)
     const float* axpy_x;             // fp32 mode, optional: out = axpy_x + axpy_a * (acc + bias)
     float axpy_a;
+    int a_fmt, w_fmt, out_fmt, res_fmt;  // Fmt of activations (A), weights (B), NHWC output and residual
 };
 
 __device__ __forceinline__ void conv_decode_tile(const ConvParams& p, int tile, int& b, int& ty, int& tx, int& nt) {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kTileM, (uint32_t)BN, 0, 0);
+            const uint32_t idesc = umma_idesc_16b(kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -257,15 +258,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     if (res) {
                         const uint4 r = __ldg(res + j);
                         float2 t;
-                        t = unpack_bf16x2(r.x); f[0] += t.x; f[1] += t.y;
-                        t = unpack_bf16x2(r.y); f[2] += t.x; f[3] += t.y;
-                        t = unpack_bf16x2(r.z); f[4] += t.x; f[5] += t.y;
-                        t = unpack_bf16x2(r.w); f[6] += t.x; f[7] += t.y;
+                        t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                        t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                        t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                        t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
                     }
-                    packed[j * 4 + 0] = pack_bf16x2(f[0], f[1]);
-                    packed[j * 4 + 1] = pack_bf16x2(f[2], f[3]);
-                    packed[j * 4 + 2] = pack_bf16x2(f[4], f[5]);
-                    packed[j * 4 + 3] = pack_bf16x2(f[6], f[7]);
+                    packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
+                    packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
+                    packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
+                    packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
                 }
                 // staging buffer `ob` was last read by the TMA store issued two chunks ago
                 if (et == 0) tma_store_wait_read<1>();
@@ -316,6 +317,7 @@ struct WgradParams {
     uint32_t tmem_cols;
     float* dw;                  // [taps][Mtot][ldn] fp32, pre-zeroed or accumulating
     int ldn, n_off;             // row length of dw and column offset of this segment
+    int p_fmt, q_fmt;           // Fmt of P (usually bf16 gradients) and Q (usually fp16 saved activations)
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
         }
     } else if (warp == 1) {
         if (lane == 0 && nk > 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)BN, 1, 1);
+            const uint32_t idesc = umma_idesc_16b(128, (uint32_t)BN, 1, 1, p.p_fmt, p.q_fmt);
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < nk; ++k) {

@@ -1,9 +1,10 @@
 // Bandwidth-bound kernels of the flow-matching hot path: NHWC bf16 activations, 128-bit vector loads/stores,
 // fp32 statistics.  One CTA never straddles two samples, so per-(sample, channel) coefficients live in registers.
 //
-// Thread mapping shared by the GroupNorm kernels: a pixel row of C channels is C/8 16-byte vectors ("vpp", a power of
-// two <= 256).  Thread t owns vector slot (t % vpp) and walks pixels (t / vpp), (t / vpp) + 256 / vpp, ... of its
-// CTA's pixel chunk: a warp always touches whole contiguous pixel rows -> fully coalesced 512 B requests.
+// Thread mapping shared by the GroupNorm kernels: a pixel row of C channels is C/8 16-byte vectors ("vpp" <= 256).
+// The block has vpp * floor(256 / vpp) threads; thread t owns vector slot (t % vpp) and walks pixels (t / vpp),
+// (t / vpp) + blockDim / vpp, ... of its CTA's pixel chunk: warps touch whole contiguous pixel rows (coalesced), and
+// the per-channel coefficients of the thread's 8 channels stay in registers for the whole chunk.
 #pragma once
 #include "common.cuh"
 
@@ -11,15 +12,15 @@ namespace s2s {
 
 constexpr int kEwThreads = 256;
 
-__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+__device__ __forceinline__ void cvt8_in(const uint4& u, int fmt, float (&f)[8]) {
     float2 t;
-    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+    t = unpack2(u.x, fmt); f[0] = t.x; f[1] = t.y;
+    t = unpack2(u.y, fmt); f[2] = t.x; f[3] = t.y;
+    t = unpack2(u.z, fmt); f[4] = t.x; f[5] = t.y;
+    t = unpack2(u.w, fmt); f[6] = t.x; f[7] = t.y;
 }
-__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
-    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+__device__ __forceinline__ uint4 cvt8_out(const float (&f)[8], int fmt) {
+    return make_uint4(pack2(f[0], f[1], fmt), pack2(f[2], f[3], fmt), pack2(f[4], f[5], fmt), pack2(f[6], f[7], fmt));
 }
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
@@ -66,8 +67,8 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsig
 //   forward : dst[co][k_off + tap*ci_count + (ci-ci_begin)]           = w[co][ci][tap]          rows = Cout
 //   dgrad   : dst[ci-ci_begin][k_off + tap*Cout + co]                 = w[co][ci][taps-1-tap]   rows = ci_count
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ci_begin,
-                                        int ci_count, __nv_bfloat16* __restrict__ dst, int ld_k, int k_off,
-                                        int transpose_flip) {
+                                        int ci_count, uint16_t* __restrict__ dst, int ld_k, int k_off,
+                                        int transpose_flip, int fmt) {
     const long long total = (long long)Cout * ci_count * taps;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         // iterate in destination order so that writes are coalesced
@@ -77,13 +78,13 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
             tap = (int)((i / ci_count) % taps);
             row = (int)(i / ((long long)ci_count * taps));
             const float v = w[((size_t)row * Cin + ci_begin + inner) * taps + tap];
-            dst[(size_t)row * ld_k + k_off + (size_t)tap * ci_count + inner] = __float2bfloat16(v);
+            dst[(size_t)row * ld_k + k_off + (size_t)tap * ci_count + inner] = pack1(v, fmt);
         } else {
             inner = (int)(i % Cout);
             tap = (int)((i / Cout) % taps);
             row = (int)(i / ((long long)Cout * taps));
             const float v = w[((size_t)inner * Cin + ci_begin + row) * taps + (taps - 1 - tap)];
-            dst[(size_t)row * ld_k + k_off + (size_t)tap * Cout + inner] = __float2bfloat16(v);
+            dst[(size_t)row * ld_k + k_off + (size_t)tap * Cout + inner] = pack1(v, fmt);
         }
     }
 }
@@ -109,7 +110,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int taps, int
 // src = (1 - t_b) * x0 + t_b * x1  (torchcfm sample_xt with sigma = 0).
 __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                     const float* __restrict__ t, int B, int H, int W, int sgn,
-                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ xt_out) {
+                                    __nv_bfloat16* __restrict__ dst, float* __restrict__ xt_out, int fmt) {
     const long long npix = (long long)B * H * W;
     for (long long pidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; pidx < npix;
          pidx += (long long)gridDim.x * blockDim.x) {
@@ -140,7 +141,7 @@ __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* _
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = v[j * 8 + e];
-            d[j] = f32_to_bf16x8(f);
+            d[j] = cvt8_out(f, fmt);
         }
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -149,13 +150,13 @@ __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
-// stats[b][c_off + c] = (sum, sumsq) over the sample's pixels; fp32 atomics across the pixel chunks of a sample.
+// stats[b][chunk][c_off + c] = (sum, sumsq) over the pixels of one chunk of the sample (no atomics: deterministic).
 __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
                                                               int pix_per_cta, float2* __restrict__ stats, int Ctot,
-                                                              int c_off) {
+                                                              int c_off, int xfmt) {
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
-    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float f[8];
-            bf16x8_to_f32(u[i], f);
+            cvt8_in(u[i], xfmt, f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 s[e] += f[e];
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
     }
     for (; p < p1; p += pstep) {
         float f[8];
-        bf16x8_to_f32(ldg_stream(src + (size_t)p * vpp + slot), f);
+        cvt8_in(ldg_stream(src + (size_t)p * vpp + slot), xfmt, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s[e] += f[e];
@@ -195,23 +196,22 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
     }
     __syncthreads();
     // thread (slot, e) for prow == 0..: reduce over pixel rows.  vpp*8 = C channels, up to 2048 -> loop
-    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+    for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
         const int sl = ci >> 3, e = ci & 7;
         float a = 0.f, q = 0.f;
         for (int r = 0; r < pstep; ++r) {
             a += red[r * vpp + sl][e];
             q += red[r * vpp + sl][8 + e];
         }
-        float* dst = reinterpret_cast<float*>(stats + (size_t)b * Ctot + c_off + ci);
-        atomicAdd(dst, a);
-        atomicAdd(dst + 1, q);
+        // deterministic: one partial per (sample, pixel chunk); gn_coef_kernel sums the chunks in order
+        stats[((size_t)b * gridDim.x + blockIdx.x) * Ctot + c_off + ci] = make_float2(a, q);
     }
 }
 
 // Per-(sample, channel) affine coefficients of the fused normalisation:
 //   y = silu?( x * A + Bc ),  A = rstd_g * gamma_c * (1 + scale_bc),  Bc = (beta_c - mean_g*rstd_g*gamma_c)*(1+scale_bc) + shift_bc
 // Also records (mean, rstd) per (sample, group) for backward.  film: [B][2C] fp32 (scale | shift) or nullptr.
-__global__ void gn_coef_kernel(const float2* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void gn_coef_kernel(const float2* __restrict__ stats, int nchunks, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ film, int C, int G, int HW,
                                float eps, float2* __restrict__ coef, float2* __restrict__ mean_rstd) {
     const int b = blockIdx.x;
@@ -219,11 +219,12 @@ __global__ void gn_coef_kernel(const float2* __restrict__ stats, const float* __
     __shared__ float s_mean[64], s_rstd[64];
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float a = 0.f, q = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            const float2 st = stats[(size_t)b * C + c];
-            a += st.x;
-            q += st.y;
-        }
+        for (int k = 0; k < nchunks; ++k)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float2 st = stats[((size_t)b * nchunks + k) * C + c];
+                a += st.x;
+                q += st.y;
+            }
         const float n = (float)cpg * (float)HW;
         const float mean = a / n;
         const float var = fmaxf(q / n - mean * mean, 0.f);
@@ -253,9 +254,10 @@ template <bool kSilu>
 __global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
                                                               int pix_per_cta, const float2* __restrict__ coef,
                                                               int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
-                                                              int ld_out, float drop_p, unsigned long long seed) {
+                                                              int ld_out, float drop_p, unsigned long long seed,
+                                                              int xfmt, int yfmt) {
     const int vpp = C >> 3;
-    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat1
     const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
     auto body = [&](const uint4& u, int p) {
         float f[8];
-        bf16x8_to_f32(u, f);
+        cvt8_in(u, xfmt, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float z = fmaf(f[e], A[e], Bc[e]);
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat1
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
         }
-        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), f32_to_bf16x8(f));
+        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), cvt8_out(f, yfmt));
     };
     int p = p0 + prow;
     for (; p + 3 * pstep < p1; p += 4 * pstep) {
@@ -309,10 +311,11 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
                                                                    const float2* __restrict__ coef,
                                                                    const float2* __restrict__ mean_rstd, int G,
                                                                    int Ctot, int c_off, float2* __restrict__ red_out,
-                                                                   float drop_p, unsigned long long seed) {
+                                                                   float drop_p, unsigned long long seed, int xfmt,
+                                                                   int gfmt) {
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
-    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
@@ -338,8 +341,8 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
     for (int p = p0 + prow; p < p1; p += pstep) {
         float xf[8], gf[8];
-        bf16x8_to_f32(ldg_stream(xs + (size_t)p * vpp + slot), xf);
-        bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gf);
+        cvt8_in(ldg_stream(xs + (size_t)p * vpp + slot), xfmt, xf);
+        cvt8_in(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gfmt, gf);
         uint32_t m = 0xffu;
         if (drop) {
             const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
@@ -361,16 +364,14 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
         red[threadIdx.x][8 + e] = s2[e];
     }
     __syncthreads();
-    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+    for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
         const int sl = ci >> 3, e = ci & 7;
         float a = 0.f, q = 0.f;
         for (int r = 0; r < pstep; ++r) {
             a += red[r * vpp + sl][e];
             q += red[r * vpp + sl][8 + e];
         }
-        float* dst = reinterpret_cast<float*>(red_out + (size_t)b * Ctot + c_off + ci);
-        atomicAdd(dst, a);
-        atomicAdd(dst + 1, q);
+        red_out[((size_t)b * gridDim.x + blockIdx.x) * Ctot + c_off + ci] = make_float2(a, q);
     }
 }
 
@@ -378,13 +379,25 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
 //   dx = dz * P + x * Q + R,  P = rstd*gamma',  Q = -rstd^2 * m2,  R = -rstd*m1 + mean*rstd^2*m2
 //   m1 = sum_{c in g} gamma'_c S1_c / N,  m2 = sum_{c in g} gamma'_c S2_c / N,  gamma' = gamma * (1 + scale)
 //   dgamma_c += sum_b S2 (1+scale)   dbeta_c += sum_b S1 (1+scale)   dscale_bc = gamma S2 + beta S1   dshift_bc = S1
-__global__ void gn_bwd_coef_kernel(const float2* __restrict__ red, const float2* __restrict__ mean_rstd,
+__global__ void gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchunks, float2* __restrict__ red,
+                                   const float2* __restrict__ mean_rstd,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ film, int C, int G, int HW, float4* __restrict__ pqr,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm) {
     const int b = blockIdx.x;
     const int cpg = C / G;
     __shared__ float s_m1[64], s_m2[64];
+    // fold the per-chunk partials (deterministic order) into red[b][c]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int k = 0; k < nchunks; ++k) {
+            const float2 r = red_part[((size_t)b * nchunks + k) * C + c];
+            a += r.x;
+            q += r.y;
+        }
+        red[(size_t)b * C + c] = make_float2(a, q);
+    }
+    __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float m1 = 0.f, m2 = 0.f;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -426,9 +439,9 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_apply_kernel(const __nv_bfl
                                                                   const float4* __restrict__ pqr, int Ctot, int c_off,
                                                                   const __nv_bfloat16* __restrict__ add,
                                                                   __nv_bfloat16* __restrict__ dx, float drop_p,
-                                                                  unsigned long long seed) {
+                                                                  unsigned long long seed, int xfmt, int gfmt) {
     const int vpp = C >> 3;
-    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
@@ -453,8 +466,8 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_apply_kernel(const __nv_bfl
     const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
     for (int p = p0 + prow; p < p1; p += pstep) {
         float xf[8], gf[8];
-        bf16x8_to_f32(ldg_stream(xs + (size_t)p * vpp + slot), xf);
-        bf16x8_to_f32(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gf);
+        cvt8_in(ldg_stream(xs + (size_t)p * vpp + slot), xfmt, xf);
+        cvt8_in(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gfmt, gf);
         uint32_t m = 0xffu;
         if (drop) {
             const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
@@ -471,11 +484,11 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_apply_kernel(const __nv_bfl
         }
         if (as) {
             float af[8];
-            bf16x8_to_f32(ldg_stream(as + (size_t)p * vpp + slot), af);
+            cvt8_in(ldg_stream(as + (size_t)p * vpp + slot), gfmt, af);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += af[e];
         }
-        stg_stream(ds + (size_t)p * vpp + slot, f32_to_bf16x8(o));
+        stg_stream(ds + (size_t)p * vpp + slot, cvt8_out(o, gfmt));
     }
 }
 
@@ -493,7 +506,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
     }
 }
 // backward of nearest x2: out[b, y, x, :] = sum of the 2x2 block of in (fp32 accumulate)
-__global__ void sumpool2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp) {
+__global__ void sumpool2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp,
+                                 int fmt) {
     const long long total = (long long)B * H * W * vpp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(i % vpp);
@@ -509,11 +523,11 @@ __global__ void sumpool2x_kernel(const uint4* __restrict__ in, uint4* __restrict
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
                 float f[8];
-                bf16x8_to_f32(ldg_stream(in + (((size_t)b * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * vpp + v), f);
+                cvt8_in(ldg_stream(in + (((size_t)b * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * vpp + v), fmt, f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[e] += f[e];
             }
-        stg_stream(out + i, f32_to_bf16x8(acc));
+        stg_stream(out + i, cvt8_out(acc, fmt));
     }
 }
 // zero-insertion (transposed stride-2 conv as a stride-1 conv): out[b, 2y, 2x, :] = in[b, y, x, :], 0 elsewhere
@@ -535,10 +549,10 @@ __global__ void zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __rest
 // per-channel sum over all pixels of an NHWC bf16 tensor (bias gradients): out[c] += sum_{b,p} x[b,p,c]
 __global__ void __launch_bounds__(kEwThreads) channel_sum_kernel(const __nv_bfloat16* __restrict__ x, int C,
                                                                  long long npix, int pix_per_cta,
-                                                                 float* __restrict__ out) {
+                                                                 float* __restrict__ out, int fmt) {
     __shared__ float red[kEwThreads][9];
     const int vpp = C >> 3;
-    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = kEwThreads / vpp;
+    const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const long long p0 = (long long)blockIdx.x * pix_per_cta;
     const long long p1 = min(npix, p0 + pix_per_cta);
     const uint4* src = reinterpret_cast<const uint4*>(x);
@@ -547,14 +561,14 @@ __global__ void __launch_bounds__(kEwThreads) channel_sum_kernel(const __nv_bflo
     for (int e = 0; e < 8; ++e) s[e] = 0.f;
     for (long long p = p0 + prow; p < p1; p += pstep) {
         float f[8];
-        bf16x8_to_f32(ldg_stream(src + p * vpp + slot), f);
+        cvt8_in(ldg_stream(src + p * vpp + slot), fmt, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] += f[e];
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
     __syncthreads();
-    for (int ci = threadIdx.x; ci < C; ci += kEwThreads) {
+    for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
         const int sl = ci >> 3, e = ci & 7;
         float a = 0.f;
         for (int r = 0; r < pstep; ++r) a += red[r * vpp + sl][e];
@@ -594,27 +608,37 @@ __global__ void __launch_bounds__(kEwThreads) fm_loss_kernel(const float* __rest
     }
 }
 
+// 16-bit format conversion (fp16 <-> bf16), n8 vectors of 8 elements
+__global__ void convert16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n8, int in_fmt,
+                                 int out_fmt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        cvt8_in(ldg_stream(in + i), in_fmt, f);
+        stg_stream(out + i, cvt8_out(f, out_fmt));
+    }
+}
+
 // layout changes between the reference's fp32 NCHW tensors and the engine's bf16 NHWC tensors
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
-                                             int C, int HW) {
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int B,
+                                             int C, int HW, int fmt) {
     const long long total = (long long)B * C * HW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const long long r = i / C;
         const int p = (int)(r % HW);
         const int b = (int)(r / HW);
-        out[i] = __float2bfloat16(in[((size_t)b * C + c) * HW + p]);
+        out[i] = pack1(in[((size_t)b * C + c) * HW + p], fmt);
     }
 }
-__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B,
-                                             int C, int HW) {
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int B,
+                                             int C, int HW, int fmt) {
     const long long total = (long long)B * C * HW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i % HW);
         const long long r = i / HW;
         const int c = (int)(r % C);
         const int b = (int)(r / C);
-        out[i] = __bfloat162float(in[((size_t)b * HW + p) * C + c]);
+        out[i] = unpack1(in[((size_t)b * HW + p) * C + c], fmt);
     }
 }
 

@@ -1,19 +1,31 @@
 """Thin functional wrappers: torch tensors in, C-ABI calls (stain2stain_b200/_lib.py) on the current CUDA stream.
 
-Layouts: activations bf16 NHWC `[B, H, W, C]` contiguous; parameters fp32 in the reference's layouts.
+Layouts: activations 16-bit NHWC `[B, H, W, C]` contiguous; parameters fp32 in the reference's layouts.
+Storage formats: forward activations and forward weight operands are fp16 (ACT), gradients and dgrad weight operands
+bf16 (GRAD); both are operands of the same tcgen05 `kind::f16` MMA.  To torch every 16-bit engine tensor is an opaque
+`torch.bfloat16` tensor (autograd insists that a gradient has its tensor's dtype; declaring one dtype for both keeps
+the engine from inserting casts) -- use `to_float` / `from_float` to look inside.  `S2S_ACT_DTYPE=bf16` switches the
+forward format to bf16 as well.
 No autograd here (see ops.py) and no CPU path: host tensors raise.
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+import os
+from typing import Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
 from ._lib import ConvSrc, check, ptr, stream_ptr
 
-BF16 = torch.bfloat16
+T16 = torch.bfloat16  # declared dtype of every 16-bit engine tensor (see module docstring)
+FMT_BF16, FMT_F16 = 0, 1
+ACT = FMT_BF16 if os.environ.get("S2S_ACT_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else FMT_F16
+GRAD = FMT_BF16
+
+
+def fmt_name(fmt: int) -> str:
+    return "fp16" if fmt == FMT_F16 else "bf16"
 
 
 def _L():
@@ -21,8 +33,8 @@ def _L():
 
 
 def _nhwc_check(x: torch.Tensor):
-    assert x.is_cuda and x.dtype == BF16 and x.dim() == 4 and x.is_contiguous(), \
-        f"expected contiguous CUDA bf16 NHWC, got {x.dtype} {tuple(x.shape)} contiguous={x.is_contiguous()}"
+    assert x.is_cuda and x.dtype == T16 and x.dim() == 4 and x.is_contiguous(), \
+        f"expected contiguous CUDA 16-bit NHWC, got {x.dtype} {tuple(x.shape)} contiguous={x.is_contiguous()}"
 
 
 def padded_rows(cout: int) -> int:
@@ -32,21 +44,31 @@ def padded_rows(cout: int) -> int:
     return cout
 
 
+def from_float(x: torch.Tensor, fmt: int) -> torch.Tensor:
+    """fp32 tensor (any shape) -> opaque 16-bit tensor holding `fmt` bits."""
+    return x.to(torch.float16).view(T16) if fmt == FMT_F16 else x.to(torch.bfloat16)
+
+
+def to_float(x: torch.Tensor, fmt: int) -> torch.Tensor:
+    return x.view(torch.float16).float() if fmt == FMT_F16 else x.float()
+
+
 def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begin: int = 0,
-                     ci_count: Optional[int] = None, transpose_flip: bool = False):
-    """w: fp32 [Cout, Cin, kh, kw] (or [Cout, Cin(,1)] for linear / Conv1d) -> rows of dst (bf16 [rows, ld_k])."""
+                     ci_count: Optional[int] = None, transpose_flip: bool = False, fmt: int = ACT):
+    """w: fp32 [Cout, Cin, kh, kw] (or [Cout, Cin(,1)] for linear / Conv1d) -> rows of dst (16-bit [rows, ld_k])."""
     cout, cin = w.shape[0], w.shape[1]
     taps = w[0, 0].numel() if w.dim() > 2 else 1
     ci_count = cin - ci_begin if ci_count is None else ci_count
-    assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == BF16 and dst.is_contiguous()
+    assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == T16 and dst.is_contiguous()
     check(_L().s2s_pack_conv_weight(ptr(w), cout, cin, taps, ci_begin, ci_count, ptr(dst), dst.shape[1], k_off,
-                                    int(transpose_flip), stream_ptr()), "pack_conv_weight")
+                                    int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
 
 
 def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tensor, cout: int, hout: int, wout: int,
              bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out_f32: bool = False,
-             axpy_x: Optional[torch.Tensor] = None, axpy_a: float = 0.0, out: Optional[torch.Tensor] = None):
-    """srcs: [(x NHWC bf16, taps, stride)].  Returns bf16 NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32."""
+             axpy_x: Optional[torch.Tensor] = None, axpy_a: float = 0.0, out: Optional[torch.Tensor] = None,
+             a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT):
+    """srcs: [(x NHWC 16-bit, taps, stride)].  Returns 16-bit NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32."""
     arr = (ConvSrc * len(srcs))()
     B = srcs[0][0].shape[0]
     for i, (x, taps, stride) in enumerate(srcs):
@@ -58,31 +80,35 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     if out_f32:
         if out is None:
             out = torch.empty((B, cout, hout, wout), dtype=torch.float32, device=dev)
-        o_bf, o_f = None, ptr(out)
+        o16, o32 = None, ptr(out)
     else:
         if out is None:
-            out = torch.empty((B, hout, wout, cout), dtype=BF16, device=dev)
-        o_bf, o_f = ptr(out), None
+            out = torch.empty((B, hout, wout, cout), dtype=T16, device=dev)
+        o16, o32 = ptr(out), None
     if residual is not None:
         _nhwc_check(residual)
         assert tuple(residual.shape) == (B, hout, wout, cout)
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == cout
-    assert w_packed.dtype == BF16 and w_packed.is_contiguous() and w_packed.shape[0] >= padded_rows(cout)
+        assert bias.dtype == torch.float32 and bias.numel() == cout and bias.is_contiguous()
+    assert w_packed.dtype == T16 and w_packed.is_contiguous() and w_packed.shape[0] >= padded_rows(cout)
     check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
-                            ptr(residual), o_bf, o_f, ptr(axpy_x), float(axpy_a), stream_ptr()), "conv_fwd")
+                            ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), a_fmt, w_fmt, out_fmt, res_fmt,
+                            stream_ptr()), "conv_fwd")
     return out
 
 
-def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: torch.Tensor, n_off: int = 0):
-    """dw[tap][m][n_off+n] += sum dy[..., m] * x[shifted, n].  dw: fp32 [taps, Cm, ldn]."""
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: torch.Tensor, n_off: int = 0,
+               fmt: int = GRAD):
+    """dw[tap][m][n_off+n] += sum dy[..., m] * x[shifted, n].  dw: fp32 [taps, Cm, ldn].
+    Both operands must be stored in `fmt` (one MMA, one operand format: mixed fp16 x bf16 is an illegal instruction)."""
+    dy_fmt = x_fmt = fmt
     _nhwc_check(dy)
     _nhwc_check(x)
     B, ho, wo, cm = dy.shape
     assert x.shape[1] == ho * stride and x.shape[2] == wo * stride
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == taps and dw.shape[1] == cm
     check(_L().s2s_conv_wgrad(ptr(dy), cm, ptr(x), x.shape[3], taps, stride, B, ho, wo, ptr(dw), dw.shape[2], n_off,
-                              stream_ptr()), "conv_wgrad")
+                              dy_fmt, x_fmt, stream_ptr()), "conv_wgrad")
 
 
 def unpack_wgrad(dw: torch.Tensor, grad: torch.Tensor, n_off: int, n_count: int, n_begin: int, beta: float):
@@ -94,26 +120,38 @@ def unpack_wgrad(dw: torch.Tensor, grad: torch.Tensor, n_off: int, n_count: int,
 
 
 def patch27_pack(x0: torch.Tensor, sgn: int = 1, x1: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None,
-                 want_xt: bool = False):
-    """fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64] 3x3 patches (optionally of the FM interpolant)."""
+                 want_xt: bool = False, fmt: int = ACT):
+    """fp32 NCHW [B,3,H,W] -> 16-bit NHWC [B,H,W,64] 3x3 patches (optionally of the FM interpolant)."""
     assert x0.dtype == torch.float32 and x0.is_contiguous() and x0.shape[1] == 3
     B, _, H, W = x0.shape
-    dst = torch.empty((B, H, W, 64), dtype=BF16, device=x0.device)
+    dst = torch.empty((B, H, W, 64), dtype=T16, device=x0.device)
     xt = torch.empty_like(x0) if want_xt else None
     if x1 is not None:
-        assert x1.shape == x0.shape and x1.is_contiguous() and t.dtype == torch.float32 and t.numel() == B
-    check(_L().s2s_patch27_pack(ptr(x0), ptr(x1), ptr(t), B, H, W, sgn, ptr(dst), ptr(xt), stream_ptr()), "patch27_pack")
+        assert x1.shape == x0.shape and x1.is_contiguous() and x1.dtype == torch.float32
+        assert t.dtype == torch.float32 and t.numel() == B and t.is_contiguous()
+    check(_L().s2s_patch27_pack(ptr(x0), ptr(x1), ptr(t), B, H, W, sgn, ptr(dst), ptr(xt), fmt, stream_ptr()),
+          "patch27_pack")
     return (dst, xt) if want_xt else dst
 
 
-def gn_stats(x: torch.Tensor, stats: torch.Tensor, c_off: int = 0):
+def gn_chunks(B: int, HW: int) -> int:
+    return int(_L().s2s_gn_chunks(B, HW))
+
+
+def gn_partial_buffer(B: int, HW: int, ctot: int, device) -> torch.Tensor:
+    """fp32 [B, chunks, Ctot, 2] buffer for the deterministic two-stage reductions (fully overwritten, no zeroing)."""
+    return torch.empty((B, gn_chunks(B, HW), ctot, 2), dtype=torch.float32, device=device)
+
+
+def gn_stats(x: torch.Tensor, stats: torch.Tensor, c_off: int = 0, x_fmt: int = ACT):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    check(_L().s2s_gn_stats(ptr(x), B, H * W, Cc, ptr(stats), stats.shape[1], c_off, stream_ptr()), "gn_stats")
+    assert stats.dim() == 4 and stats.shape[1] == gn_chunks(B, H * W)
+    check(_L().s2s_gn_stats(ptr(x), B, H * W, Cc, ptr(stats), stats.shape[2], c_off, x_fmt, stream_ptr()), "gn_stats")
 
 
 def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
-    B, Cc, _ = stats.shape
+    B, _, Cc, _ = stats.shape
     coef = torch.empty((B, Cc, 2), dtype=torch.float32, device=stats.device)
     mr = torch.empty((B, G, 2), dtype=torch.float32, device=stats.device)
     check(_L().s2s_gn_coef(ptr(stats), ptr(gamma), ptr(beta), ptr(film), B, Cc, G, HW, eps, ptr(coef), ptr(mr),
@@ -121,63 +159,68 @@ def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
     return coef, mr
 
 
-def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0):
+def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
+             y_fmt: int = ACT):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), y.shape[3], int(silu),
-                            float(drop_p), int(seed), stream_ptr()), "gn_apply")
+                            float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
 
 
-def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0):
+def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
+                  g_fmt: int = GRAD):
     B, H, W, Cc = x.shape
     check(_L().s2s_gn_bwd_reduce(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
-                                 coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), stream_ptr()),
-          "gn_bwd_reduce")
+                                 coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), x_fmt, g_fmt,
+                                 stream_ptr()), "gn_bwd_reduce")
 
 
-def gn_bwd_coef(red, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool):
-    B, Cc, _ = red.shape
-    pqr = torch.empty((B, Cc, 4), dtype=torch.float32, device=red.device)
-    dfilm = torch.empty((B, 2 * Cc), dtype=torch.float32, device=red.device) if want_dfilm else None
-    check(_L().s2s_gn_bwd_coef(ptr(red), ptr(mr), ptr(gamma), ptr(beta), ptr(film), B, Cc, mr.shape[1], HW, ptr(pqr),
-                               ptr(dgamma), ptr(dbeta), ptr(dfilm), stream_ptr()), "gn_bwd_coef")
+def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool):
+    B, _, Cc, _ = red_part.shape
+    red = torch.empty((B, Cc, 2), dtype=torch.float32, device=red_part.device)
+    pqr = torch.empty((B, Cc, 4), dtype=torch.float32, device=red_part.device)
+    dfilm = torch.empty((B, 2 * Cc), dtype=torch.float32, device=red_part.device) if want_dfilm else None
+    check(_L().s2s_gn_bwd_coef(ptr(red_part), ptr(red), ptr(mr), ptr(gamma), ptr(beta), ptr(film), B, Cc, mr.shape[1],
+                               HW, ptr(pqr), ptr(dgamma), ptr(dbeta), ptr(dfilm), stream_ptr()), "gn_bwd_coef")
     return pqr, dfilm
 
 
-def gn_bwd_apply(x, g, coef, pqr, c_off: int, add, dx, silu: bool, drop_p: float = 0.0, seed: int = 0):
+def gn_bwd_apply(x, g, coef, pqr, c_off: int, add, dx, silu: bool, drop_p: float = 0.0, seed: int = 0,
+                 x_fmt: int = ACT, g_fmt: int = GRAD):
     B, H, W, Cc = x.shape
     check(_L().s2s_gn_bwd_apply(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(pqr), coef.shape[1], c_off,
-                                ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), stream_ptr()), "gn_bwd_apply")
+                                ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), x_fmt, g_fmt, stream_ptr()),
+          "gn_bwd_apply")
 
 
 def upsample2x(x):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=T16, device=x.device)
     check(_L().s2s_upsample2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "upsample2x")
     return out
 
 
-def sumpool2x(x):
+def sumpool2x(x, fmt: int = GRAD):
     _nhwc_check(x)
     B, H2, W2, Cc = x.shape
-    out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=BF16, device=x.device)
-    check(_L().s2s_sumpool2x(ptr(x), ptr(out), B, H2 // 2, W2 // 2, Cc, stream_ptr()), "sumpool2x")
+    out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=T16, device=x.device)
+    check(_L().s2s_sumpool2x(ptr(x), ptr(out), B, H2 // 2, W2 // 2, Cc, fmt, stream_ptr()), "sumpool2x")
     return out
 
 
 def zero_insert2x(x):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=T16, device=x.device)
     check(_L().s2s_zero_insert2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "zero_insert2x")
     return out
 
 
-def channel_sum(x, out):
+def channel_sum(x, out, fmt: int = GRAD):
     _nhwc_check(x)
     npix = x.shape[0] * x.shape[1] * x.shape[2]
-    check(_L().s2s_channel_sum(ptr(x), npix, x.shape[3], ptr(out), stream_ptr()), "channel_sum")
+    check(_L().s2s_channel_sum(ptr(x), npix, x.shape[3], ptr(out), fmt, stream_ptr()), "channel_sum")
 
 
 def fm_loss(v, x0, x1, want_grad: bool):
@@ -188,17 +231,27 @@ def fm_loss(v, x0, x1, want_grad: bool):
     return loss, dv
 
 
-def nchw_to_nhwc_bf16(x):
+def nchw_to_nhwc16(x, fmt: int = ACT):
     assert x.dtype == torch.float32 and x.is_contiguous()
     B, Cc, H, W = x.shape
-    out = torch.empty((B, H, W, Cc), dtype=BF16, device=x.device)
-    check(_L().s2s_nchw_f32_to_nhwc_bf16(ptr(x), ptr(out), B, Cc, H * W, stream_ptr()), "nchw_to_nhwc")
+    out = torch.empty((B, H, W, Cc), dtype=T16, device=x.device)
+    check(_L().s2s_nchw_f32_to_nhwc16(ptr(x), ptr(out), B, Cc, H * W, fmt, stream_ptr()), "nchw_to_nhwc16")
     return out
 
 
-def nhwc_to_nchw_f32(x):
+def nhwc16_to_nchw(x, fmt: int = ACT):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
-    check(_L().s2s_nhwc_bf16_to_nchw_f32(ptr(x), ptr(out), B, Cc, H * W, stream_ptr()), "nhwc_to_nchw")
+    check(_L().s2s_nhwc16_to_nchw_f32(ptr(x), ptr(out), B, Cc, H * W, fmt, stream_ptr()), "nhwc16_to_nchw")
+    return out
+
+
+def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
+    """Storage-format conversion of an opaque 16-bit tensor (no-op when the formats agree)."""
+    if in_fmt == out_fmt:
+        return x
+    assert x.is_cuda and x.dtype == T16 and x.is_contiguous()
+    out = torch.empty_like(x)
+    check(_L().s2s_convert16(ptr(x), ptr(out), x.numel(), in_fmt, out_fmt, stream_ptr()), "convert16")
     return out

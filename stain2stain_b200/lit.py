@@ -1,0 +1,214 @@
+"""LightningModule mirrors of the reference's flow-matching modules (same class names, constructor kwargs, methods,
+`state_dict` keys `net.*`, error behaviour), with the numerics routed to the B200 engine:
+
+  ConditionalFlowMatchingLitModule        <- src/models/conditional_flow_matching.py:9-170
+  ClassConditionalFlowMatchingLitModule   <- src/models/class_conditional_flow_matching.py:8-190
+
+`model_step` = FM sample -> net -> MSE (reference :53-74).  When `net` is this package's UNet and sigma == 0 the
+interpolation `xt = (1-t) x0 + t x1` is fused into the stem's operand packing and `ut = x1 - x0`, the MSE and its
+gradient into one loss kernel; otherwise the generic (reference-shaped) path runs on whatever `net` was given.
+`generate` integrates with `NeuralODE` exactly as the reference does (solver/atol/rtol taken from `self.solver` with
+the same `hasattr` fallbacks, :157-163); `solver="euler"` selects the CUDA-graph fused Euler sampler.
+
+If `lightning` is importable the classes derive from `lightning.LightningModule`; otherwise from a small stand-in
+with the same surface (`save_hyperparameters`, `log`, `hparams`, `device`), so entry points run without it.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .flow_matching import ConditionalFlowMatcher
+from .neural_ode import NeuralODE
+from .unet import RawUNetModel
+
+try:  # pragma: no cover - not installed in the build image
+    from lightning import LightningModule as _Base
+    HAVE_LIGHTNING = True
+except Exception:  # noqa: BLE001
+    HAVE_LIGHTNING = False
+
+    class _HParams(dict):
+        __getattr__ = dict.get
+
+    class _Base(nn.Module):
+        """Minimal stand-in for lightning.LightningModule (only what the reference modules touch)."""
+
+        def __init__(self):
+            super().__init__()
+            self.hparams = _HParams()
+            self.logged: Dict[str, Any] = {}
+            self.trainer = None
+            self.current_epoch = 0
+
+        def save_hyperparameters(self, *args, logger: bool = True, **kwargs):
+            import inspect
+            frame = inspect.currentframe().f_back
+            init_args = {k: v for k, v in frame.f_locals.items() if k not in ("self", "__class__")}
+            self.hparams.update(init_args)
+
+        def log(self, name, value, **kwargs):
+            self.logged[name] = value.detach() if torch.is_tensor(value) else value
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+
+def _solver_attr(solver, name, default):
+    # reference: `self.solver.<name> if hasattr(self.solver, '<name>') else default` (conditional_flow_matching.py:159-162).
+    # A functools.partial has no such attribute, so with the shipped yaml the defaults always win (SURVEY finding 5);
+    # we additionally honour the partial's keywords so that `solver: euler` in the yaml selects the fused sampler.
+    if hasattr(solver, name):
+        return getattr(solver, name)
+    if isinstance(solver, functools.partial) and name in solver.keywords and solver.keywords.get("_honour_partial", True):
+        return solver.keywords[name]
+    return default
+
+
+class ConditionalFlowMatchingLitModule(_Base):
+    def __init__(self, net: torch.nn.Module, flow_matcher: ConditionalFlowMatcher, solver: Optional[Any] = None,
+                 optimizer: Any = None, scheduler: Any = None, compile: bool = False, log_images: bool = True,
+                 n_images_log: int = 5, reference_solver_defaults: bool = False) -> None:
+        super().__init__()
+        self.save_hyperparameters(logger=False)
+        self.net = net
+        self.flow_matcher = flow_matcher
+        self.solver = solver
+        self.optimizer = optimizer
+        self.scheduler = scheduler
+        self.log_images = log_images
+        self.n_images_log = n_images_log
+        self.reference_solver_defaults = reference_solver_defaults
+        # `compile` is accepted and ignored: the engine is hand-written kernels, there is nothing to trace.
+
+    # ------------------------------------------------------------------ forward / step
+    def forward(self, t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        return self.net(t, x)
+
+    def _fused_ok(self) -> bool:
+        return isinstance(self.net, RawUNetModel) and float(getattr(self.flow_matcher, "sigma", 1.0)) == 0.0 \
+            and hasattr(self.flow_matcher, "sample_time")
+
+    def model_step(self, batch: Tuple[torch.Tensor, ...], t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        source_img, target_img = batch[:2]
+        x0, x1 = source_img, target_img
+        if self._fused_ok() and x0.is_cuda:
+            if t is None:
+                t = self.flow_matcher.sample_time(x0)
+            vt = self.net.velocity_of_interpolant(t, x0, x1)
+            return ops.fm_loss(vt.float(), x0.float(), x1.float())
+        t, xt, ut = self.flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
+        vt = self.forward(t, xt)
+        return torch.mean((vt - ut) ** 2)
+
+    def training_step(self, batch, batch_idx: int) -> torch.Tensor:
+        loss = self.model_step(batch)
+        self.log("train/loss", loss, on_step=True, on_epoch=True, prog_bar=True, sync_dist=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx: int) -> None:
+        loss = self.model_step(batch)
+        self.log("val/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+
+    def test_step(self, batch, batch_idx: int) -> None:
+        loss = self.model_step(batch)
+        self.log("test/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+
+    def configure_optimizers(self) -> Dict[str, Any]:
+        optimizer = self.optimizer(params=self.parameters())
+        if self.scheduler is not None:
+            scheduler = self.scheduler(optimizer=optimizer)
+            return {"optimizer": optimizer,
+                    "lr_scheduler": {"scheduler": scheduler, "monitor": "val/loss", "interval": "epoch", "frequency": 1}}
+        return {"optimizer": optimizer}
+
+    # ------------------------------------------------------------------ sampling
+    def _make_node(self, vf) -> NeuralODE:
+        if self.reference_solver_defaults:  # literal reference behaviour: the partial's settings are ignored
+            get = lambda n, d: getattr(self.solver, n) if hasattr(self.solver, n) else d  # noqa: E731
+        else:
+            get = lambda n, d: _solver_attr(self.solver, n, d)  # noqa: E731
+        return NeuralODE(vf, solver=get("solver", "dopri5"), sensitivity=get("sensitivity", "adjoint"),
+                         atol=get("atol", 1e-4), rtol=get("rtol", 1e-4))
+
+    @torch.no_grad()
+    def generate(self, source_img: torch.Tensor, num_steps: int = 100) -> torch.Tensor:
+        if self.solver is None:
+            raise ValueError("Solver is not initialized. Cannot perform inference.")
+        self.eval()
+        if source_img.dim() == 3:
+            source_img = source_img.unsqueeze(0)
+        device = source_img.device
+        node = self._make_node(self.net)
+        t_span = torch.linspace(0, 1, num_steps, device=device)
+        return node.final_state(source_img, t_span)
+
+    # image logging hooks of the reference (conditional_flow_matching.py:172-329) need wandb + a dataloader; the
+    # numerics they exercise are `generate`, so they are no-ops here unless lightning drives the module.
+    def on_train_epoch_end(self) -> None:
+        return None
+
+    def on_validation_epoch_end(self) -> None:
+        return None
+
+
+class ConditionalWrapper(nn.Module):
+    """src/models/class_conditional_flow_matching.py:163-174: closes over the target label for the ODE solver."""
+
+    def __init__(self, model, y):
+        super().__init__()
+        self.model = model
+        self.y = y
+
+    def forward(self, t, x, **kwargs):
+        return self.model(t, x, y=self.y)
+
+
+class ClassConditionalFlowMatchingLitModule(ConditionalFlowMatchingLitModule):
+    def __init__(self, net: torch.nn.Module, flow_matcher: ConditionalFlowMatcher, solver: Optional[Any] = None,
+                 optimizer: Any = None, scheduler: Any = None, compile: bool = False,
+                 reference_solver_defaults: bool = False) -> None:
+        super().__init__(net, flow_matcher, solver, optimizer, scheduler, compile, log_images=False, n_images_log=0,
+                         reference_solver_defaults=reference_solver_defaults)
+
+    def forward(self, t: torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        return self.net(t, x, y=y)
+
+    def model_step(self, batch, t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        source_img, target_img, target_label = batch
+        x0, x1 = source_img, target_img
+        y = target_label.long()
+        if self._fused_ok() and x0.is_cuda:
+            if t is None:
+                t = self.flow_matcher.sample_time(x0)
+            vt = self.net.velocity_of_interpolant(t, x0, x1, y=y)
+            return ops.fm_loss(vt.float(), x0.float(), x1.float())
+        t, xt, ut = self.flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
+        vt = self.forward(t, xt, y)
+        return torch.mean((vt - ut) ** 2)
+
+    @torch.no_grad()
+    def generate(self, source_img: torch.Tensor, target_class, num_steps: int = 100) -> torch.Tensor:  # type: ignore[override]
+        if self.solver is None:
+            raise ValueError("Solver is not initialized. Cannot perform inference.")
+        self.eval()
+        if source_img.dim() == 3:
+            source_img = source_img.unsqueeze(0)
+        batch_size, device = source_img.shape[0], source_img.device
+        if isinstance(target_class, int):
+            y = torch.full((batch_size,), target_class, dtype=torch.long, device=device)
+        else:
+            y = target_class.to(device).long()
+            if y.dim() == 0:
+                y = y.unsqueeze(0).expand(batch_size)
+        node = self._make_node(ConditionalWrapper(self.net, y))
+        t_span = torch.linspace(0, 1, num_steps, device=device)
+        return node.final_state(source_img, t_span)

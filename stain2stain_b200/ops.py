@@ -1,0 +1,363 @@
+"""Autograd operators of the hot path, each a fused forward/backward over the C-ABI kernels (kernels.py).
+
+Activations between operators are bf16 NHWC CUDA tensors; parameters stay fp32 `nn.Parameter`s in the reference's
+layouts (so Lightning checkpoints, torch optimizers and DDP see exactly what they see in the reference) and are packed
+to bf16 GEMM operands on the fly (cached while the parameter is unchanged).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import kernels as K
+
+T16 = K.T16
+
+
+# --------------------------------------------------------------------------------------------- packed-weight cache
+class _PackCache:
+    """bf16 GEMM operands derived from fp32 parameters, keyed by (purpose, parameter identity and version)."""
+
+    def __init__(self):
+        self._store: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
+
+    @staticmethod
+    def _sig(ws: Sequence[torch.Tensor]):
+        return tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws)
+
+    def get(self, key: tuple, ws: Sequence[torch.Tensor], make):
+        sig = self._sig(ws)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = make()
+        self._store[key] = (sig, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+PACK_CACHE = _PackCache()
+
+
+@dataclass(frozen=True)
+class Seg:
+    """One GEMM segment of a fused conv: source index, weight index, input-channel slice, filter taps, stride."""
+    src: int
+    weight: int
+    ci_begin: int
+    ci_count: int
+    taps: int
+    stride: int = 1
+
+
+@dataclass
+class ConvPlan:
+    segs: Tuple[Seg, ...]
+    cout: int
+    uid: int = field(default_factory=lambda: ConvPlan._next_uid())
+    _counter = [0]
+
+    @staticmethod
+    def _next_uid():
+        ConvPlan._counter[0] += 1
+        return ConvPlan._counter[0]
+
+    def ktot(self):
+        return sum(s.taps * ((s.ci_count + 63) // 64 * 64) for s in self.segs)
+
+    def packed_fwd(self, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+        def make():
+            wp = torch.zeros((K.padded_rows(self.cout), self.ktot()), dtype=T16, device=weights[0].device)
+            off = 0
+            for s in self.segs:
+                K.pack_conv_weight(weights[s.weight].detach(), wp, k_off=off, ci_begin=s.ci_begin, ci_count=s.ci_count)
+                off += s.taps * ((s.ci_count + 63) // 64 * 64)
+            return wp
+        return PACK_CACHE.get(("fwd", self.uid), weights, make)
+
+    def packed_dgrad(self, si: int, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+        s = self.segs[si]
+        w = weights[s.weight]
+
+        def make():
+            wd = torch.zeros((s.ci_count, s.taps * self.cout), dtype=T16, device=w.device)
+            K.pack_conv_weight(w.detach(), wd, ci_begin=s.ci_begin, ci_count=s.ci_count, transpose_flip=True,
+                               fmt=K.GRAD)
+            return wd
+        return PACK_CACHE.get(("dgrad", self.uid, si), [w], make)
+
+
+# --------------------------------------------------------------------------------------------- fused convolution
+class _FusedConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: ConvPlan, n_src: int, n_w: int, residual, *tensors):
+        srcs = tensors[:n_src]
+        weights = tensors[n_src:n_src + n_w]
+        biases = [b for b in tensors[n_src + n_w:] if b is not None]
+        B = srcs[0].shape[0]
+        s0 = plan.segs[0]
+        hout, wout = srcs[s0.src].shape[1] // s0.stride, srcs[s0.src].shape[2] // s0.stride
+        wp = plan.packed_fwd(weights)
+        bias = None
+        if biases:
+            bias = biases[0].detach().float()
+            for b in biases[1:]:
+                bias = bias + b.detach()
+            bias = bias.contiguous()
+        out = K.conv_fwd([(srcs[s.src], s.taps, s.stride) for s in plan.segs], wp, plan.cout, hout, wout, bias=bias,
+                         residual=residual)
+        ctx.plan, ctx.n_src, ctx.n_w = plan, n_src, n_w
+        ctx.has_res = residual is not None
+        ctx.bias_present = [b is not None for b in tensors[n_src + n_w:]]
+        ctx.save_for_backward(*srcs, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        plan, n_src, n_w = ctx.plan, ctx.n_src, ctx.n_w
+        saved = ctx.saved_tensors
+        srcs, weights = saved[:n_src], saved[n_src:]
+        d_out = d_out.contiguous()
+        B, hout, wout, cout = d_out.shape
+        need = ctx.needs_input_grad  # (plan, n_src, n_w, residual, *tensors)
+        d_res = d_out if (ctx.has_res and need[3]) else None
+        d_srcs: List[Optional[torch.Tensor]] = [None] * n_src
+        d_ws: List[Optional[torch.Tensor]] = [None] * n_w
+        # bias gradient (shared by every bias folded into this accumulator)
+        d_bias = None
+        if any(ctx.bias_present) and any(need[4 + n_src + n_w:]):
+            d_bias = torch.zeros(cout, dtype=torch.float32, device=d_out.device)
+            K.channel_sum(d_out, d_bias)
+        for si, s in enumerate(plan.segs):
+            x = srcs[s.src]
+            w = weights[s.weight]
+            if need[4 + n_src + s.weight]:
+                if d_ws[s.weight] is None:
+                    d_ws[s.weight] = torch.empty_like(w, dtype=torch.float32)
+                    if sum(t.ci_count for t in plan.segs if t.weight == s.weight) != w.shape[1]:
+                        d_ws[s.weight].zero_()
+                dw = torch.zeros((s.taps, cout, x.shape[3]), dtype=torch.float32, device=d_out.device)
+                K.conv_wgrad(d_out, K.convert16(x, K.ACT, K.GRAD), s.taps, s.stride, dw)
+                K.unpack_wgrad(dw, d_ws[s.weight].view(cout, w.shape[1], -1), 0, s.ci_count, s.ci_begin, 0.0)
+            if need[4 + s.src]:
+                wd = plan.packed_dgrad(si, weights)
+                g = d_out if s.stride == 1 else K.zero_insert2x(d_out)
+                dx = K.conv_fwd([(g, s.taps, 1)], wd, s.ci_count, g.shape[1], g.shape[2], a_fmt=K.GRAD, w_fmt=K.GRAD,
+                                out_fmt=K.GRAD)
+                d_srcs[s.src] = dx if d_srcs[s.src] is None else d_srcs[s.src] + dx
+        d_biases = [d_bias if (present and n) else None
+                    for present, n in zip(ctx.bias_present, need[4 + n_src + n_w:])]
+        return (None, None, None, d_res, *d_srcs, *d_ws, *d_biases)
+
+
+def fused_conv(plan: ConvPlan, srcs: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+               biases: Sequence[Optional[torch.Tensor]], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _FusedConv.apply(plan, len(srcs), len(weights), residual, *srcs, *weights, *biases)
+
+
+# --------------------------------------------------------------------------------------------- GroupNorm (+FiLM+SiLU+dropout, +concat)
+class _GroupNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, n_src: int, groups: int, eps: float, silu: bool, drop_p: float, seed: int, gamma, beta, film, *srcs):
+        B, H, W, _ = srcs[0].shape
+        ctot = sum(s.shape[3] for s in srcs)
+        dev = srcs[0].device
+        stats = K.gn_partial_buffer(B, H * W, ctot, dev)
+        off = 0
+        for s in srcs:
+            K.gn_stats(s, stats, off)
+            off += s.shape[3]
+        film_c = film.detach().float().contiguous() if film is not None else None
+        coef, mr = K.gn_coef(stats, gamma.detach(), beta.detach(), film_c, H * W, groups, eps)
+        y = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
+        off = 0
+        for s in srcs:
+            K.gn_apply(s, coef, y, off, silu, drop_p, seed)
+            off += s.shape[3]
+        ctx.cfg = (n_src, groups, silu, drop_p, seed, film is not None)
+        ctx.save_for_backward(coef, mr, gamma, beta, film_c, *srcs)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        n_src, groups, silu, drop_p, seed, has_film = ctx.cfg
+        coef, mr, gamma, beta, film_c, *srcs = ctx.saved_tensors
+        g = g.contiguous()
+        B, H, W, ctot = g.shape
+        dev = g.device
+        red = K.gn_partial_buffer(B, H * W, ctot, dev)
+        off = 0
+        for s in srcs:
+            K.gn_bwd_reduce(s, g, coef, mr, red, off, silu, drop_p, seed)
+            off += s.shape[3]
+        dgamma = torch.zeros(ctot, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(ctot, dtype=torch.float32, device=dev)
+        pqr, dfilm = K.gn_bwd_coef(red, mr, gamma.detach(), beta.detach(), film_c, H * W, dgamma, dbeta, has_film)
+        dxs = []
+        off = 0
+        for i, s in enumerate(srcs):
+            if ctx.needs_input_grad[9 + i]:
+                dx = torch.empty_like(s)
+                K.gn_bwd_apply(s, g, coef, pqr, off, None, dx, silu, drop_p, seed)
+                dxs.append(dx)
+            else:
+                dxs.append(None)
+            off += s.shape[3]
+        return (None, None, None, None, None, None, dgamma, dbeta, dfilm, *dxs)
+
+
+def group_norm_act(srcs: Sequence[torch.Tensor], gamma, beta, film=None, silu=True, drop_p=0.0, seed=0, groups=32,
+                   eps=1e-5) -> torch.Tensor:
+    """GroupNorm over the channel-concatenation of `srcs`, optional FiLM `(1+scale), shift`, SiLU and dropout."""
+    return _GroupNormAct.apply(len(srcs), groups, eps, bool(silu), float(drop_p), int(seed), gamma, beta, film, *srcs)
+
+
+# --------------------------------------------------------------------------------------------- resampling
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.upsample2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.sumpool2x(g.contiguous())
+
+
+def upsample2x(x):
+    return _Upsample2x.apply(x)
+
+
+# --------------------------------------------------------------------------------------------- stem / head (3-channel ends)
+class _Stem(torch.autograd.Function):
+    """3x3 conv on the fp32 NCHW image (optionally the FM interpolant of x0, x1 at t) -> bf16 NHWC features."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, t, w, b):
+        patches = K.patch27_pack(x0.contiguous(), 1, None if x1 is None else x1.contiguous(),
+                                 None if t is None else t.float().contiguous())
+        cout = w.shape[0]
+
+        def make():
+            wp = torch.zeros((cout, 64), dtype=T16, device=w.device)
+            K.pack_conv_weight(w.detach(), wp)
+            return wp
+        wp = PACK_CACHE.get(("stem", id(w)), [w], make)
+        B, _, H, W = x0.shape
+        out = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach())
+        ctx.save_for_backward(patches)
+        ctx.wshape = tuple(w.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (patches,) = ctx.saved_tensors
+        g = g.contiguous()
+        cout = g.shape[3]
+        dw = torch.zeros((1, cout, 64), dtype=torch.float32, device=g.device)
+        K.conv_wgrad(g, K.convert16(patches, K.ACT, K.GRAD), 1, 1, dw)
+        d_w = dw[0, :, :27].reshape(cout, 9, 3).permute(0, 2, 1).reshape(ctx.wshape).contiguous()
+        d_b = torch.zeros(cout, dtype=torch.float32, device=g.device)
+        K.channel_sum(g, d_b)
+        return None, None, None, d_w, d_b
+
+
+def stem_conv(x0, w, b, x1=None, t=None):
+    assert w.shape[1] == 3 and tuple(w.shape[2:]) == (3, 3), "stem expects a 3-channel 3x3 conv"
+    return _Stem.apply(x0, x1, t, w, b)
+
+
+class _HeadConv(torch.autograd.Function):
+    """3x3 conv to <= 3 channels, fp32 NCHW output; optional fused `axpy_x + a * v` (Euler update, inference only)."""
+
+    @staticmethod
+    def forward(ctx, a, w, b, axpy_x, axpy_a):
+        cout, cin = w.shape[0], w.shape[1]
+
+        def make():
+            wp = torch.zeros((16, 9 * cin), dtype=T16, device=w.device)
+            K.pack_conv_weight(w.detach(), wp)
+            return wp
+        wp = PACK_CACHE.get(("head", id(w)), [w], make)
+        B, H, W, _ = a.shape
+        out = K.conv_fwd([(a, 9, 1)], wp, cout, H, W, bias=b.detach(), out_f32=True, axpy_x=axpy_x, axpy_a=axpy_a,
+                         out=axpy_x if axpy_x is not None else None)
+        ctx.save_for_backward(a, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dv):
+        a, w = ctx.saved_tensors
+        cout, cin = w.shape[0], w.shape[1]
+        assert cout == 3
+        dv = dv.contiguous().float()
+        dcol = K.patch27_pack(dv, -1, fmt=K.GRAD)  # [B,H,W,64], column tap*3 + co = dv[q - tap_off][co]
+        # dgrad: da[q][ci] = sum_j dcol[q][j] * Wd[ci][j], Wd[ci][tap*3+co] = w[co][ci][tap]
+        wd = torch.zeros((cin, 64), dtype=torch.bfloat16, device=w.device)
+        wd[:, :27] = w.detach().permute(1, 2, 3, 0).reshape(cin, 27).to(torch.bfloat16)
+        B, H, W, _ = a.shape
+        da = K.conv_fwd([(dcol, 1, 1)], wd, cin, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD)
+        # wgrad: D[ci][tap*3+co] = sum_q a[q][ci] * dcol[q][tap*3+co]
+        dw = torch.zeros((1, cin, 64), dtype=torch.float32, device=w.device)
+        K.conv_wgrad(K.convert16(a, K.ACT, K.GRAD), dcol, 1, 1, dw)
+        d_w = dw[0, :, :27].reshape(cin, 9, 3).permute(2, 0, 1).reshape(cout, cin, 3, 3).contiguous()
+        d_b = dv.sum(dim=(0, 2, 3))
+        return da, d_w, d_b, None, None
+
+
+def head_conv(a, w, b, axpy_x=None, axpy_a=0.0):
+    return _HeadConv.apply(a, w, b, axpy_x, axpy_a)
+
+
+# --------------------------------------------------------------------------------------------- loss
+class _FMLoss(torch.autograd.Function):
+    """mean((v - (x1 - x0))^2) with the gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, v, x0, x1):
+        loss, dv = K.fm_loss(v.contiguous(), x0.contiguous(), x1.contiguous(), True)
+        ctx.save_for_backward(dv)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dv,) = ctx.saved_tensors
+        return dv * g, None, None
+
+
+def fm_loss(v, x0, x1):
+    return _FMLoss.apply(v, x0, x1)
+
+
+# --------------------------------------------------------------------------------------------- opaque <-> real dtype glue
+class _ActToBF16(torch.autograd.Function):
+    """Opaque forward-format activations -> a real torch.bfloat16 tensor (for library ops such as SDPA)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x if K.ACT == K.FMT_BF16 else x.view(torch.float16).to(torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g  # gradients are bf16 on both sides
+
+
+class _BF16ToAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x if K.ACT == K.FMT_BF16 else x.to(torch.float16).view(T16)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def act_to_bf16(x):
+    return _ActToBF16.apply(x)
+
+
+def bf16_to_act(x):
+    return _BF16ToAct.apply(x)

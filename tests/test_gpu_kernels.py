@@ -19,16 +19,22 @@ def K():
     return kernels
 
 
-def rb(x):  # round to bf16 and back
-    return x.to(torch.bfloat16).float()
+def _fmt(kind):
+    k = K()
+    return k.ACT if kind == "act" else k.GRAD
 
 
-def nhwc(x):  # fp32 NCHW -> bf16 NHWC
-    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+def rb(x, kind="act"):  # round to the storage format and back
+    k = K()
+    return k.to_float(k.from_float(x, _fmt(kind)), _fmt(kind))
 
 
-def nchw(x):  # bf16 NHWC -> fp32 NCHW
-    return x.float().permute(0, 3, 1, 2).contiguous()
+def nhwc(x, kind="act"):  # fp32 NCHW -> opaque 16-bit NHWC
+    return K().nchw_to_nhwc16(x.contiguous(), _fmt(kind))
+
+
+def nchw(x, kind="act"):  # opaque 16-bit NHWC -> fp32 NCHW
+    return K().nhwc16_to_nchw(x, _fmt(kind))
 
 
 def rel_l2(a, b):
@@ -42,10 +48,20 @@ def assert_close_bf16(got, ref, what):
     assert err <= scale * 2 ** -6 and r < 6e-3, f"{what}: max err {err:.4g} (scale {scale:.4g}) rel-L2 {r:.3g}"
 
 
+def assert_close_act(got, ref, what):
+    """forward-format outputs: fp16 by default (2^-11 relative rounding), bf16 when S2S_ACT_DTYPE=bf16"""
+    if K().ACT == K().FMT_BF16:
+        return assert_close_bf16(got, ref, what)
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max())
+    r = rel_l2(got, ref)
+    assert err <= scale * 2 ** -9 and r < 8e-4, f"{what}: max err {err:.4g} (scale {scale:.4g}) rel-L2 {r:.3g}"
+
+
 def pack_fwd(k, weights, cout):
     """weights: list of (w fp32 OIHW, ci_begin, ci_count) sharing one accumulator."""
     ktot = sum(w[0, 0].numel() * ((cnt + 63) // 64 * 64) for w, _, cnt in weights)
-    wp = torch.zeros((k.padded_rows(cout), ktot), dtype=torch.bfloat16, device=DEV)
+    wp = torch.zeros((k.padded_rows(cout), ktot), dtype=k.T16, device=DEV)
     off = 0
     for w, beg, cnt in weights:
         k.pack_conv_weight(w, wp, k_off=off, ci_begin=beg, ci_count=cnt)
@@ -65,7 +81,7 @@ def test_conv3x3_s1(B, H, W, Cin, Cout):
     ref = F.conv2d(x, w, b, padding=1) + r
     wp = pack_fwd(k, [(w, 0, Cin)], Cout)
     out = k.conv_fwd([(nhwc(x), 9, 1)], wp, Cout, H, W, bias=b, residual=nhwc(r))
-    assert_close_bf16(nchw(out), ref, "conv3x3 s1")
+    assert_close_act(nchw(out), ref, "conv3x3 s1")
 
 
 def test_conv1x1_and_multiseg():
@@ -81,12 +97,12 @@ def test_conv1x1_and_multiseg():
     ref = F.conv2d(xa, w3, b, padding=1) + F.conv2d(torch.cat([xs0, xs1], 1), w1)
     wp = pack_fwd(k, [(w3, 0, 128), (w1, 0, 128), (w1, 128, 64)], 128)
     out = k.conv_fwd([(nhwc(xa), 9, 1), (nhwc(xs0), 1, 1), (nhwc(xs1), 1, 1)], wp, 128, H, W, bias=b)
-    assert_close_bf16(nchw(out), ref, "3x3 + 1x1 skip over a concat")
+    assert_close_act(nchw(out), ref, "3x3 + 1x1 skip over a concat")
     # plain 1x1
     ref1 = F.conv2d(xs0, w1[:, :128].contiguous())
     wp1 = pack_fwd(k, [(w1, 0, 128)], 128)
     out1 = k.conv_fwd([(nhwc(xs0), 1, 1)], wp1, 128, H, W)
-    assert_close_bf16(nchw(out1), ref1, "1x1")
+    assert_close_act(nchw(out1), ref1, "1x1")
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 128), (1, 32, 64, 256)])
@@ -99,7 +115,7 @@ def test_conv3x3_s2(B, H, W, C):
     ref = F.conv2d(x, w, b, stride=2, padding=1)
     wp = pack_fwd(k, [(w, 0, C)], C)
     out = k.conv_fwd([(nhwc(x), 9, 2)], wp, C, H // 2, W // 2, bias=b)
-    assert_close_bf16(nchw(out), ref, "conv3x3 s2")
+    assert_close_act(nchw(out), ref, "conv3x3 s2")
 
 
 def test_conv_head_f32_axpy():
@@ -122,23 +138,24 @@ def test_conv_dgrad_via_flipped_pack():
     k = K()
     g = torch.Generator(device=DEV).manual_seed(5)
     B, H, W, Cin, Cout = 2, 32, 32, 128, 256
-    x = rb(torch.randn(B, Cin, H, W, device=DEV, generator=g)).requires_grad_(True)
-    w = rb(torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin))
-    dy = rb(torch.randn(B, Cout, H, W, device=DEV, generator=g))
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g).requires_grad_(True)
+    w = rb(torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin), "grad")
+    dy = rb(torch.randn(B, Cout, H, W, device=DEV, generator=g), "grad")
     F.conv2d(x, w, padding=1).backward(dy)
-    wd = torch.zeros((Cin, 9 * Cout), dtype=torch.bfloat16, device=DEV)
-    k.pack_conv_weight(w, wd, transpose_flip=True)
-    dx = k.conv_fwd([(nhwc(dy), 9, 1)], wd, Cin, H, W)
-    assert_close_bf16(nchw(dx), x.grad, "dgrad 3x3")
+    wd = torch.zeros((Cin, 9 * Cout), dtype=k.T16, device=DEV)
+    k.pack_conv_weight(w, wd, transpose_flip=True, fmt=k.GRAD)
+    dx = k.conv_fwd([(nhwc(dy, "grad"), 9, 1)], wd, Cin, H, W, a_fmt=k.GRAD, w_fmt=k.GRAD, out_fmt=k.GRAD)
+    assert_close_bf16(nchw(dx, "grad"), x.grad, "dgrad 3x3")
     # stride-2 dgrad = zero insertion + stride-1 conv with the flipped weights
-    x2 = rb(torch.randn(B, Cin, H, W, device=DEV, generator=g)).requires_grad_(True)
-    w2 = rb(torch.randn(Cin, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin))
-    dy2 = rb(torch.randn(B, Cin, H // 2, W // 2, device=DEV, generator=g))
+    x2 = torch.randn(B, Cin, H, W, device=DEV, generator=g).requires_grad_(True)
+    w2 = rb(torch.randn(Cin, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin), "grad")
+    dy2 = rb(torch.randn(B, Cin, H // 2, W // 2, device=DEV, generator=g), "grad")
     F.conv2d(x2, w2, stride=2, padding=1).backward(dy2)
-    wd2 = torch.zeros((Cin, 9 * Cin), dtype=torch.bfloat16, device=DEV)
-    k.pack_conv_weight(w2, wd2, transpose_flip=True)
-    dx2 = k.conv_fwd([(k.zero_insert2x(nhwc(dy2)), 9, 1)], wd2, Cin, H, W)
-    assert_close_bf16(nchw(dx2), x2.grad, "dgrad 3x3 s2")
+    wd2 = torch.zeros((Cin, 9 * Cin), dtype=k.T16, device=DEV)
+    k.pack_conv_weight(w2, wd2, transpose_flip=True, fmt=k.GRAD)
+    dx2 = k.conv_fwd([(k.zero_insert2x(nhwc(dy2, "grad")), 9, 1)], wd2, Cin, H, W, a_fmt=k.GRAD, w_fmt=k.GRAD,
+                     out_fmt=k.GRAD)
+    assert_close_bf16(nchw(dx2, "grad"), x2.grad, "dgrad 3x3 s2")
 
 
 @pytest.mark.parametrize("taps,stride,Cin,Cout,B,H,W", [(9, 1, 128, 128, 2, 32, 32), (9, 1, 64, 256, 1, 16, 48),
@@ -148,12 +165,12 @@ def test_conv_wgrad(taps, stride, Cin, Cout, B, H, W):
     k = K()
     g = torch.Generator(device=DEV).manual_seed(6)
     ks = 3 if taps == 9 else 1
-    x = rb(torch.randn(B, Cin, H * stride, W * stride, device=DEV, generator=g))
+    x = rb(torch.randn(B, Cin, H * stride, W * stride, device=DEV, generator=g), "grad")
     w = torch.zeros(Cout, Cin, ks, ks, device=DEV, requires_grad=True)
-    dy = rb(torch.randn(B, Cout, H, W, device=DEV, generator=g))
+    dy = rb(torch.randn(B, Cout, H, W, device=DEV, generator=g), "grad")
     F.conv2d(x, w, stride=stride, padding=ks // 2).backward(dy)
     dw = torch.zeros((taps, Cout, Cin), dtype=torch.float32, device=DEV)
-    k.conv_wgrad(nhwc(dy), nhwc(x), taps, stride, dw)
+    k.conv_wgrad(nhwc(dy, "grad"), nhwc(x, "grad"), taps, stride, dw)
     grad = torch.zeros_like(w)
     k.unpack_wgrad(dw, grad, 0, Cin, 0, 0.0)
     r = rel_l2(grad, w.grad)
@@ -173,11 +190,11 @@ def test_patch27_and_stem():
     patches, xt = k.patch27_pack(x0, 1, x1, t, want_xt=True)
     assert rel_l2(xt, xt_ref) < 1e-6
     # stem conv as a 1x1 GEMM over the patches: weight [128][64] with column tap*3 + c
-    wp = torch.zeros((128, 64), dtype=torch.bfloat16, device=DEV)
-    wp[:, :27] = w.permute(0, 2, 3, 1).reshape(128, 27).to(torch.bfloat16)
+    wp = torch.zeros((128, 64), dtype=k.T16, device=DEV)
+    k.pack_conv_weight(w, wp)
     out = k.conv_fwd([(patches, 1, 1)], wp, 128, H, W, bias=b)
     ref = F.conv2d(rb(xt_ref), w, b, padding=1)
-    assert_close_bf16(nchw(out), ref, "stem via patches")
+    assert_close_act(nchw(out), ref, "stem via patches")
     # sgn = -1: adjoint patches, check against unfold of the flipped image
     xp = F.pad(x0, (1, 1, 1, 1))
     for sgn in (1, -1):
@@ -187,8 +204,9 @@ def test_patch27_and_stem():
             oy, ox = 1 + sgn * (tap // 3 - 1), 1 + sgn * (tap % 3 - 1)
             cols.append(xp[:, :, oy:oy + H, ox:ox + W])
         ref_m = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(B, H, W, 27)
-        assert rel_l2(pm[..., :27].float(), rb(ref_m)) < 1e-6, sgn
-        assert float(pm[..., 27:].abs().max()) == 0.0
+        pmf = k.to_float(pm, k.ACT)
+        assert rel_l2(pmf[..., :27], rb(ref_m)) < 1e-6, sgn
+        assert float(pmf[..., 27:].abs().max()) == 0.0
 
 
 def _gn_ref(x, gamma, beta, film, silu, G=32):
@@ -200,7 +218,7 @@ def _gn_ref(x, gamma, beta, film, silu, G=32):
 
 
 @pytest.mark.parametrize("C0,C1,film,silu", [(128, 0, False, True), (256, 128, False, True), (512, 256, True, True),
-                                             (64, 0, True, False), (1024, 0, False, True)])
+                                             (64, 0, True, False), (1024, 0, False, True), (384, 0, True, True)])
 def test_groupnorm_fwd_bwd(C0, C1, film, silu):
     k = K()
     g = torch.Generator(device=DEV).manual_seed(8)
@@ -212,25 +230,25 @@ def test_groupnorm_fwd_bwd(C0, C1, film, silu):
     fl = (0.3 * torch.randn(B, 2 * Ct, device=DEV, generator=g)).requires_grad_(True) if film else None
     xcat = torch.cat(xs, 1).requires_grad_(True)
     ref = _gn_ref(xcat, gamma, beta, fl, silu)
-    gy = rb(torch.randn(B, Ct, H, W, device=DEV, generator=g))
+    gy = rb(torch.randn(B, Ct, H, W, device=DEV, generator=g), "grad")
     ref.backward(gy)
 
-    stats = torch.zeros((B, Ct, 2), dtype=torch.float32, device=DEV)
+    stats = k.gn_partial_buffer(B, H * W, Ct, DEV)
     xh = [nhwc(x) for x in xs]
     off = 0
     for x in xh:
         k.gn_stats(x, stats, off)
         off += x.shape[3]
     coef, mr = k.gn_coef(stats, gamma.detach(), beta.detach(), fl.detach() if film else None, H * W)
-    y = torch.empty((B, H, W, Ct), dtype=torch.bfloat16, device=DEV)
+    y = torch.empty((B, H, W, Ct), dtype=k.T16, device=DEV)
     off = 0
     for x in xh:
         k.gn_apply(x, coef, y, off, silu)
         off += x.shape[3]
-    assert_close_bf16(nchw(y), ref.detach(), "gn fwd")
+    assert_close_act(nchw(y), ref.detach(), "gn fwd")
 
-    red = torch.zeros((B, Ct, 2), dtype=torch.float32, device=DEV)
-    gh = nhwc(gy)
+    red = k.gn_partial_buffer(B, H * W, Ct, DEV)
+    gh = nhwc(gy, "grad")
     off = 0
     for x in xh:
         k.gn_bwd_reduce(x, gh, coef, mr, red, off, silu)
@@ -244,7 +262,7 @@ def test_groupnorm_fwd_bwd(C0, C1, film, silu):
     for x in xh:
         dx = torch.empty_like(x)
         k.gn_bwd_apply(x, gh, coef, pqr, off, None, dx, silu)
-        dxs.append(nchw(dx))
+        dxs.append(nchw(dx, "grad"))
         off += x.shape[3]
     dx = torch.cat(dxs, 1)
     assert rel_l2(dx, xcat.grad) < 1e-2, f"gn dx rel-L2 {rel_l2(dx, xcat.grad)}"
@@ -257,7 +275,7 @@ def test_groupnorm_fwd_bwd(C0, C1, film, silu):
 def test_dropout_statistics_and_replay():
     k = K()
     B, H, W, Cc = 2, 32, 32, 128
-    x = torch.ones((B, H, W, Cc), dtype=torch.bfloat16, device=DEV)
+    x = k.from_float(torch.ones((B, H, W, Cc), device=DEV), k.ACT)
     coef = torch.zeros((B, Cc, 2), device=DEV)
     coef[..., 0] = 1.0  # y = x
     y1 = torch.empty_like(x)
@@ -265,9 +283,10 @@ def test_dropout_statistics_and_replay():
     k.gn_apply(x, coef, y1, 0, False, 0.1, 1234)
     k.gn_apply(x, coef, y2, 0, False, 0.1, 1234)
     assert torch.equal(y1, y2)
-    keep = float((y1 != 0).float().mean())
+    y1f = k.to_float(y1, k.ACT)
+    keep = float((y1f != 0).float().mean())
     assert abs(keep - 0.9) < 0.005, keep
-    kept = y1[y1 != 0].float()
+    kept = y1f[y1f != 0]
     assert float((kept - 1 / 0.9).abs().max()) < 0.01
     y3 = torch.empty_like(x)
     k.gn_apply(x, coef, y3, 0, False, 0.1, 99)
@@ -280,16 +299,23 @@ def test_resample_and_sums():
     x = rb(torch.randn(2, 64, 16, 24, device=DEV, generator=g))
     up = k.upsample2x(nhwc(x))
     assert torch.equal(nchw(up), F.interpolate(x, scale_factor=2, mode="nearest"))
-    big = rb(torch.randn(2, 64, 32, 48, device=DEV, generator=g))
-    sp = k.sumpool2x(nhwc(big))
-    assert_close_bf16(nchw(sp), F.avg_pool2d(big, 2) * 4, "sumpool")
+    big = rb(torch.randn(2, 64, 32, 48, device=DEV, generator=g), "grad")
+    sp = k.sumpool2x(nhwc(big, "grad"))
+    assert_close_bf16(nchw(sp, "grad"), F.avg_pool2d(big, 2) * 4, "sumpool")
     zi = nchw(k.zero_insert2x(nhwc(x)))
-    assert torch.equal(zi[:, :, ::2, ::2], x) and float(zi.abs().sum() - x.abs().sum()) == 0.0
-    cs = torch.zeros(64, device=DEV)
-    k.channel_sum(nhwc(big), cs)
-    assert rel_l2(cs, big.sum(dim=(0, 2, 3))) < 1e-4
-    assert torch.equal(nchw(k.nchw_to_nhwc_bf16(x)), x)
-    assert torch.equal(k.nhwc_to_nchw_f32(nhwc(x)), x)
+    assert torch.equal(zi[:, :, ::2, ::2], x)
+    assert float(zi[:, :, 1::2, :].abs().max()) == 0.0 and float(zi[:, :, :, 1::2].abs().max()) == 0.0
+    xr = rb(x)
+    assert torch.equal(k.to_float(k.convert16(k.from_float(xr, k.FMT_F16), k.FMT_F16, k.FMT_BF16), k.FMT_BF16),
+                       xr.to(torch.bfloat16).float())
+    for C in (64, 384):
+        big = rb(torch.randn(2, C, 32, 48, device=DEV, generator=g), "grad")
+        cs = torch.zeros(C, device=DEV)
+        k.channel_sum(nhwc(big, "grad"), cs)
+        assert rel_l2(cs, big.sum(dim=(0, 2, 3))) < 1e-4
+    for kind in ("act", "grad"):
+        xr = rb(x, kind)
+        assert torch.equal(nchw(nhwc(xr, kind), kind), xr)
 
 
 def test_fm_loss():
