@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Headline benchmark: 256x256 tiles/s of the flow-matching hot path on 1/2/4/8 B200 (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's engine (train step, configs[1])
+    python bench.py --mode sample ...                              # 50-evaluation Euler sampling (configs[2])
+    python bench.py --impl reference ...                           # the reference's CPU path (fp32 oracle restatement)
+
+A "step" (train) = FM sample -> UNet forward -> MSE -> backward -> gradient all-reduce (N>1) -> Adam, on one batch of
+synthetic 3x256x256 tile pairs, batch 64 per GPU (config A of SURVEY.md).  A "step" (sample) = 50 Euler velocity
+evaluations + state updates of one micro-batch of tiles.  One JSON line is printed by rank 0; see the task contract for
+the keys.  `value` is timed with inputs resident in HBM; `e2e` includes the pinned-host -> device copy of each step's
+inputs and the device -> host read of its result through the public LitModule API.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+FLOP_FWD_PER_TILE = 814.4e9        # 407.21 GMAC per 256^2 tile (config A)
+FLOP_TRAIN_PER_TILE = 2443e9
+L2_BYTES = 126 * 1024 * 1024
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def _max_over_ranks(ms: float, world: int, dev) -> float:
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def build_lit(device, dropout=0.1):
+    import functools
+    from stain2stain_b200.flow_matching import ConditionalFlowMatcher
+    from stain2stain_b200.lit import ConditionalFlowMatchingLitModule
+    from stain2stain_b200.neural_ode import NeuralODE
+    from stain2stain_b200.optim import FusedAdam
+    from stain2stain_b200.unet import UNetModel
+    torch.manual_seed(1984)
+    net = UNetModel(dim=[3, 256, 256], num_channels=128, num_res_blocks=2, attention_resolutions="16,8",
+                    dropout=dropout, use_scale_shift_norm=True, num_heads=4, num_head_channels=32,
+                    channel_mult=[1, 2, 2, 4])
+    _dezero(net)
+    lit = ConditionalFlowMatchingLitModule(
+        net=net, flow_matcher=ConditionalFlowMatcher(sigma=0.0),
+        solver=functools.partial(NeuralODE, solver="euler", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+        optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=0.0), scheduler=None)
+    return lit.to(device)
+
+
+def _dezero(net, seed=1984):
+    """Zero-initialised convs re-drawn (SURVEY finding 7) so that every layer does real work with real values."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() >= 2 and float(p.abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g) / math.sqrt(p[0].numel()))
+
+
+class _StepModule(torch.nn.Module):
+    """What Lightning's DDP strategy does: DDP wraps a module whose forward is the LightningModule's training_step."""
+
+    def __init__(self, lit):
+        super().__init__()
+        self.lit = lit
+
+    def forward(self, x0, x1):
+        return self.lit.training_step((x0, x1), 0)
+
+
+def run_train(args, rank, world, local):
+    from stain2stain_b200 import kernels as K
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    lit = build_lit(dev)
+    lit.train()
+    step_mod = _StepModule(lit)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True)
+    opt = lit.configure_optimizers()["optimizer"]
+    g = torch.Generator(device=dev).manual_seed(1984 + rank)
+    # inputs larger than L2 (2 x 50 MB per step at B=64) and a fresh pair per step: no L2 reuse between steps
+    n_sets = 4
+    x0s = [torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
+    x1s = [torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
+    host0 = [x.cpu().pin_memory() for x in x0s[:2]]
+    host1 = [x.cpu().pin_memory() for x in x1s[:2]]
+
+    def step(x0, x1):
+        opt.zero_grad(set_to_none=True)
+        loss = step_mod(x0, x1)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(x0s[i % n_sets], x1s[i % n_sets])
+    _barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.LAUNCHES[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(x0s[i % n_sets], x1s[i % n_sets])
+    e1.record()
+    _barrier(world)
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = K.LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    last_loss = float(loss)
+
+    # ---- end to end through the public API: pinned host inputs -> device, loss back to the host, every step
+    _barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        x0 = host0[i % 2].to(dev, non_blocking=True)
+        x1 = host1[i % 2].to(dev, non_blocking=True)
+        loss_host = float(step(x0, x1))  # device -> host read of the step's result
+    e1.record()
+    _barrier(world)
+    ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, one instrumented step
+    roof = None
+    prof = {}
+    if rank == 0:
+        torch.cuda.synchronize()
+        K.PROFILE = []
+        step(x0s[0], x1s[0])
+        torch.cuda.synchronize()
+        prof = K.profile_summary(K.PROFILE)
+        K.PROFILE = None
+    _barrier(world)
+    tiles = B * world * args.steps
+    out = {
+        "metric": "256x256 tiles/s, conditional flow-matching train step (FM sample + UNet fwd + MSE + bwd + allreduce + Adam)",
+        "value": tiles / (ms / 1e3), "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 forward / bf16 backward operands, fp32 accumulate (tcgen05 kind::f16)" if K.ACT == K.FMT_F16
+                 else "bf16 operands, fp32 accumulate",
+        "data": "synthetic U(-1,1) 3x256x256 tile pairs, random-init (de-zeroed) config-A UNet, seed 1984",
+        "config": {"workload": "configs[1]: simple flow-matching UNet training, 256x256 tiles, batch 64/GPU, DDP",
+                   "per_gpu_batch": B, "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()),
+                   "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "Adam lr 1e-4 (fused, own kernel)",
+                   "l2": "inputs larger than L2 (2 x %.0f MB per step, 4 rotating sets)" % (B * 3 * 256 * 256 * 4 / 1e6)},
+        "loss": last_loss,
+        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": 2 * B * 3 * 256 * 256 * 4,
+                "d2h_bytes_per_step": 4, "loss": loss_host},
+        "gpu_launches": launches,
+    }
+    if rank == 0:
+        pk = _peaks()
+        step_ms = ms / args.steps
+        if "conv_igemm" in prof:
+            c = prof["conv_igemm"]
+            ach = c["flops"] / (c["ms"] / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (fwd + dgrad implicit GEMM)", "achieved": ach,
+                    "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+                    "peak_source": pk["src"] + " bf16_tflops_sustained", "launches_per_step": c["launches"],
+                    "kernel_ms_per_step": c["ms"], "share_of_step": c["ms"] / step_ms,
+                    "algorithmic_flops_per_step": c["flops"]}
+        out["roofline"] = roof
+        kern = {}
+        for name, d in prof.items():
+            e = {"launches": d["launches"], "ms": round(d["ms"], 3)}
+            if d["flops"]:
+                e["tflops"] = d["flops"] / (d["ms"] / 1e3) / 1e12
+                e["frac_tensor_peak"] = e["tflops"] / pk["tf"]
+            if d["bytes"]:
+                e["gbs"] = d["bytes"] / (d["ms"] / 1e3) / 1e9
+                e["frac_hbm_peak"] = e["gbs"] / pk["hbm"]
+            kern[name] = e
+        out["kernels"] = kern
+        out["model_flops_utilisation"] = (FLOP_TRAIN_PER_TILE * B / (step_ms / 1e3)) / 1e12 / pk["tf"]
+        out["clocks"] = clocks
+        out["cpu_baseline"] = cpu_baseline(sample_steps=1) if (world == 1 and not args.no_cpu) else None
+    return out
+
+
+def run_sample(args, rank, world, local):
+    from stain2stain_b200 import kernels as K
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    lit = build_lit(dev)
+    lit.eval()
+    g = torch.Generator(device=dev).manual_seed(1984 + rank)
+    n_sets = 3
+    xs = [torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
+    hosts = [x.cpu().pin_memory() for x in xs[:2]]
+    evals = 50
+
+    def step(x):
+        return lit.generate(x, num_steps=evals + 1)  # 51 grid points = 50 Euler evaluations, dt = 1/50
+
+    for i in range(max(args.warmup, 1)):
+        step(xs[i % n_sets])
+    _barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.LAUNCHES[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out_img = step(xs[i % n_sets])
+    e1.record()
+    _barrier(world)
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    _barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        res = step(hosts[i % 2].to(dev, non_blocking=True)).cpu()
+    e1.record()
+    _barrier(world)
+    ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    tiles = B * world * args.steps
+    pk = _peaks()
+    step_ms = ms / args.steps
+    ach = FLOP_FWD_PER_TILE * evals * B / (step_ms / 1e3) / 1e12
+    return {
+        "metric": "256x256 tiles/s, 50-evaluation Euler ODE sampling (CUDA-graph fused velocity eval + update)",
+        "value": tiles / (ms / 1e3), "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, fp32 accumulate, fp32 ODE state" if K.ACT == K.FMT_F16 else "bf16 operands, fp32 state",
+        "data": "synthetic U(-1,1) 3x256x256 tiles, random-init (de-zeroed) config-A UNet, seed 1984",
+        "config": {"workload": "configs[2]: 50-step Euler ODE sampling of synthetic 256x256 tiles, sharded by tile",
+                   "micro_batch": B, "evaluations": evals, "parallelism": f"replicas x{world} (no collective)",
+                   "l2": "activations of one evaluation (>1 GB) exceed L2"},
+        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+                "d2h_bytes_per_step": B * 3 * 256 * 256 * 4},
+        "gpu_launches": "CUDA graph replays: %d x %d-kernel graph" % (evals * args.steps, 0),
+        "roofline": {"bound": "tensor", "kernel": "whole velocity evaluation (conv_igemm dominated)", "achieved": ach,
+                     "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16_tflops_sustained"},
+        "clocks": clocks,
+        "cpu_baseline": None,
+    }
+
+
+# --------------------------------------------------------------------------------------------------- CPU reference arm
+def _oracle_step_fn(batch=4):
+    """configs[0]: `src/train.py trainer=cpu`-equivalent step on the fp32 oracle (the reference's packages are absent)."""
+    from oracle import flow as oflow
+    from oracle import unet as ounet
+    torch.manual_seed(1984)
+    net = ounet.UNetModel(**ounet.CONFIG_A)
+    ounet.dezero_(net)
+    net.train()
+    fm = oflow.ConditionalFlowMatcher(0.0)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(1984)
+    x0 = torch.rand(batch, 3, 256, 256, generator=g) * 2 - 1
+    x1 = torch.rand(batch, 3, 256, 256, generator=g) * 2 - 1
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = oflow.model_step(net, fm, (x0, x1))
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def cpu_baseline(sample_steps=1, batch=4):
+    step = _oracle_step_fn(batch)
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": batch * sample_steps / dt, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_steps} un-warmed train step(s) of configs[0] (config-A UNet, batch {batch}, fp32, "
+                      f"fwd+bwd+Adam) on the host CPU, {os.cpu_count()} logical cores"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    batch = 4
+    step = _oracle_step_fn(batch)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = min(args.steps, 3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = batch * steps / dt
+    sample = (f"{steps} train steps of batch {batch} (configs[0]) after {min(args.warmup, 1)} warm-up, fp32 oracle "
+              f"restatement of the torchcfm UNet (torchcfm/lightning are not installable here), "
+              f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores")
+    return {"impl": "reference",
+            "metric": "256x256 tiles/s, conditional flow-matching train step (FM sample + UNet fwd + MSE + bwd + allreduce + Adam)",
+            "value": v, "unit": "tiles/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic U(-1,1) 3x256x256 tile pairs, seed 1984",
+            "config": {"workload": "configs[1] model on the reference's CPU path, bounded sample: batch 4 per step"},
+            "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "sample"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 32)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.mode == "train" else 32
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
+    rank, world, local = _dist_setup(args.gpus)
+    out = run_train(args, rank, world, local) if args.mode == "train" else run_sample(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,26 @@ int s2s_convert16(const void* in, void* out, long long n, int in_fmt, int out_fm
 int s2s_nchw_f32_to_nhwc16(const float* in, void* out, int B, int C, int HW, int fmt, void* stream);
 int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int fmt, void* stream);
 
+/* One parameter tensor of the fused optimizer: fp32 param / grad / exp_avg / exp_avg_sq of n elements. */
+typedef struct {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long n;
+} s2s_adam_tensor;
+
+/* Elements of one (tensor, chunk) work item of s2s_adam_multi. */
+int s2s_adam_chunk(void);
+
+/* torch.optim.Adam step (L2 weight decay: g += wd * p; bias-corrected; eps outside the sqrt) over ALL tensors in one
+ * launch.  tensors_dev: device array of s2s_adam_tensor; work_dev: device array of n_work int pairs (tensor index,
+ * chunk index), one CTA each.  `step` is the 1-based step count, grad_scale multiplies every gradient first.
+ * Replaces: torch.optim.Adam / _multi_tensor_adam (configs/model/conditional_flow_matching.yaml:3-7,
+ * src/models/conditional_flow_matching.py:112-131). */
+int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ SIGNATURES = {
     "s2s_convert16": [_vp, _vp, _ll, _i, _i, _vp],
     "s2s_nchw_f32_to_nhwc16": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_adam_chunk": [],
+    "s2s_adam_multi": [_vp, _vp, _i, _f, _f, _f, _f, _f, _i, _f, _vp],
 }
 _RESTYPES = {"s2s_last_error": C.c_char_p}
 

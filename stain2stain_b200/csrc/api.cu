@@ -1,12 +1,14 @@
 // C-ABI entry points (include/s2s_b200.h): argument validation, TMA tensor-map construction and kernel launches.
 #include "../../include/s2s_b200.h"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
 
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
+#include "optim.cuh"
 
 using namespace s2s;
 
@@ -451,6 +453,26 @@ int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int
     const long long total = (long long)B * C * HW;
     nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint16_t*)in, out, B, C, HW, fmt);
     LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+    return S2S_OK;
+}
+
+int s2s_adam_chunk(void) { return kAdamChunk; }
+
+int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    static_assert(sizeof(s2s_adam_tensor) == sizeof(AdamTensor), "ABI struct drifted from the kernel's");
+    if (n_work <= 0) return S2S_OK;
+    if (!tensors_dev || !work_dev || step < 1) return fail(S2S_ERR_INVALID, "adam_multi: bad arguments");
+    AdamHyper h;
+    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+    h.omb1 = (float)(1.0 - (double)beta1);
+    h.omb2 = (float)(1.0 - (double)beta2);
+    h.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
+    h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)step)));
+    h.grad_scale = grad_scale;
+    adam_multi_kernel<<<n_work, kAdamThreads, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors_dev,
+                                                                          (const int2*)work_dev, h);
+    LAUNCH_CHECK("adam_multi_kernel");
     return S2S_OK;
 }
 

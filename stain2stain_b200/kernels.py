@@ -16,12 +16,55 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvSrc, check, ptr, stream_ptr
+from ._lib import ConvSrc, ptr, stream_ptr
+from ._lib import check as _check
 
 T16 = torch.bfloat16  # declared dtype of every 16-bit engine tensor (see module docstring)
 FMT_BF16, FMT_F16 = 0, 1
 ACT = FMT_BF16 if os.environ.get("S2S_ACT_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else FMT_F16
 GRAD = FMT_BF16
+
+
+# ---- instrumentation: launch counter + optional per-launch CUDA-event profile (bench.py roofline) ----------------
+LAUNCHES = [0]
+PROFILE = None  # when a list: (kernel name, start event, end event, algorithmic flops, algorithmic bytes) per launch
+
+
+def check(rc: int, what: str = ""):
+    LAUNCHES[0] += 1
+    _check(rc, what)
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.bytes, self.e0 = name, flops, nbytes, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.e0, e1, self.flops, self.bytes))
+        return False
+
+
+def profile_summary(records):
+    """-> {kernel: dict(launches, ms, flops, bytes)} (call after torch.cuda.synchronize())."""
+    out = {}
+    for name, e0, e1, fl, by in records:
+        d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
 
 
 def fmt_name(fmt: int) -> str:
@@ -91,9 +134,12 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout and bias.is_contiguous()
     assert w_packed.dtype == T16 and w_packed.is_contiguous() and w_packed.shape[0] >= padded_rows(cout)
-    check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
-                            ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), a_fmt, w_fmt, out_fmt, res_fmt,
-                            stream_ptr()), "conv_fwd")
+    # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted)
+    macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs)
+    with _Prof("conv_igemm", 2.0 * macs):
+        check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
+                                ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), a_fmt, w_fmt, out_fmt, res_fmt,
+                                stream_ptr()), "conv_fwd")
     return out
 
 
@@ -107,8 +153,9 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: to
     B, ho, wo, cm = dy.shape
     assert x.shape[1] == ho * stride and x.shape[2] == wo * stride
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == taps and dw.shape[1] == cm
-    check(_L().s2s_conv_wgrad(ptr(dy), cm, ptr(x), x.shape[3], taps, stride, B, ho, wo, ptr(dw), dw.shape[2], n_off,
-                              dy_fmt, x_fmt, stream_ptr()), "conv_wgrad")
+    with _Prof("conv_wgrad", 2.0 * B * ho * wo * cm * x.shape[3] * taps):
+        check(_L().s2s_conv_wgrad(ptr(dy), cm, ptr(x), x.shape[3], taps, stride, B, ho, wo, ptr(dw), dw.shape[2],
+                                  n_off, dy_fmt, x_fmt, stream_ptr()), "conv_wgrad")
 
 
 def unpack_wgrad(dw: torch.Tensor, grad: torch.Tensor, n_off: int, n_count: int, n_begin: int, beta: float):
@@ -147,7 +194,9 @@ def gn_stats(x: torch.Tensor, stats: torch.Tensor, c_off: int = 0, x_fmt: int = 
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     assert stats.dim() == 4 and stats.shape[1] == gn_chunks(B, H * W)
-    check(_L().s2s_gn_stats(ptr(x), B, H * W, Cc, ptr(stats), stats.shape[2], c_off, x_fmt, stream_ptr()), "gn_stats")
+    with _Prof("gn_stats", 0.0, 2.0 * x.numel()):
+        check(_L().s2s_gn_stats(ptr(x), B, H * W, Cc, ptr(stats), stats.shape[2], c_off, x_fmt, stream_ptr()),
+              "gn_stats")
 
 
 def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
@@ -163,16 +212,18 @@ def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int 
              y_fmt: int = ACT):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), y.shape[3], int(silu),
-                            float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
+    with _Prof("gn_apply", 0.0, 4.0 * x.numel()):  # 1 read + 1 write of 2-byte elements
+        check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), y.shape[3], int(silu),
+                                float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
 
 
 def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
                   g_fmt: int = GRAD):
     B, H, W, Cc = x.shape
-    check(_L().s2s_gn_bwd_reduce(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
-                                 coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), x_fmt, g_fmt,
-                                 stream_ptr()), "gn_bwd_reduce")
+    with _Prof("gn_bwd_reduce", 0.0, 4.0 * x.numel()):  # reads x and g
+        check(_L().s2s_gn_bwd_reduce(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
+                                     coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), x_fmt,
+                                     g_fmt, stream_ptr()), "gn_bwd_reduce")
 
 
 def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool):
@@ -188,9 +239,10 @@ def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_df
 def gn_bwd_apply(x, g, coef, pqr, c_off: int, add, dx, silu: bool, drop_p: float = 0.0, seed: int = 0,
                  x_fmt: int = ACT, g_fmt: int = GRAD):
     B, H, W, Cc = x.shape
-    check(_L().s2s_gn_bwd_apply(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(pqr), coef.shape[1], c_off,
-                                ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), x_fmt, g_fmt, stream_ptr()),
-          "gn_bwd_apply")
+    with _Prof("gn_bwd_apply", 0.0, (6.0 + (2.0 if add is not None else 0.0)) * x.numel()):  # x, g (+add) in, dx out
+        check(_L().s2s_gn_bwd_apply(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(pqr), coef.shape[1],
+                                    c_off, ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), x_fmt, g_fmt,
+                                    stream_ptr()), "gn_bwd_apply")
 
 
 def upsample2x(x):

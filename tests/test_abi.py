@@ -1,0 +1,71 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports exactly what include/s2s_b200.h declares
+(no compute calls here: there is no GPU in the CPU test tier)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "s2s_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2s_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_bound_symbols():
+    from stain2stain_b200 import _lib
+    assert _declared() == sorted(_lib.SIGNATURES)
+
+
+def test_library_builds_loads_and_exports_every_symbol():
+    from stain2stain_b200 import _build, _lib
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} is declared in include/s2s_b200.h but not exported"
+    loaded = _lib.load(build_if_missing=False)
+    assert loaded.s2s_abi_version() == 1
+    assert loaded.s2s_adam_chunk() > 0
+    assert ctypes.sizeof(_lib.ConvSrc) == 24  # {void*, int, int, int} + padding, as in the header
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA -> UTMALDG/UTMASTG (B200_PROFILING.md evidence table)."""
+    from stain2stain_b200 import _build
+    path = _build.build()
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, timeout=300).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not on PATH")
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "sm_100" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")  # no legacy mma.sync path
+
+
+def test_no_cpu_fallback():
+    import torch
+    from stain2stain_b200 import _lib, kernels
+    with pytest.raises(_lib.S2SError):
+        _lib.ptr(torch.zeros(4))
+    from stain2stain_b200.unet import UNetModel
+    net = UNetModel(dim=[3, 32, 32], num_channels=32, num_res_blocks=1, attention_resolutions="16",
+                    use_scale_shift_norm=True, num_head_channels=16, channel_mult=[1, 2])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.rand(1), torch.zeros(1, 3, 32, 32))
+    assert kernels.ACT in (kernels.FMT_BF16, kernels.FMT_F16)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "stain2stain_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f

@@ -329,3 +329,28 @@ def test_fm_loss():
     loss, dv = k.fm_loss(v.detach(), x0, x1, True)
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)) + 1e-7
     assert rel_l2(dv, v.grad) < 1e-6
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-5])
+def test_fused_adam_matches_torch_adam(wd):
+    """FusedAdam (one multi-tensor launch) vs torch.optim.Adam, same params / grads, 3 steps; state_dict layout equal."""
+    from stain2stain_b200.optim import FusedAdam
+    g = torch.Generator(device=DEV).manual_seed(3)
+    shapes = [(128, 64, 3, 3), (257,), (3, 5, 7), (40000,), (1,)]
+    pa = [torch.randn(s, device=DEV, generator=g).requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    oa = FusedAdam(pa, lr=1e-3, weight_decay=wd)
+    ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=wd)
+    for it in range(3):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device=DEV, generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step(), ob.step()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert set(sa["state"][k]) == set(sb["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 3.0
+        assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-8)

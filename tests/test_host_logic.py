@@ -1,0 +1,160 @@
+"""CPU tests of the host side that mirrors the reference's interfaces (no kernels run here):
+LitModule surface (src/models/conditional_flow_matching.py:9-170, class_conditional_flow_matching.py:8-190),
+the `torchdyn.core.NeuralODE` stand-in on arbitrary vector fields, the flow matcher, module tree / state_dict keys
+of the B200 UNet vs the oracle, and conv-plan bookkeeping."""
+import functools
+import pickle
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import flow as oflow
+from oracle import unet as ounet
+from stain2stain_b200.flow_matching import ConditionalFlowMatcher
+from stain2stain_b200.lit import (ClassConditionalFlowMatchingLitModule, ConditionalFlowMatchingLitModule,
+                                  ConditionalWrapper)
+from stain2stain_b200.neural_ode import NeuralODE
+from stain2stain_b200.ops import ConvPlan, Seg
+from stain2stain_b200.unet import RawUNetModel, UNetModel
+
+
+class TinyField(nn.Module):
+    """A stand-in `net(t, x, y=None)` so the generic (reference-shaped) LitModule path runs on CPU."""
+
+    def __init__(self, classes=0):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 3, 3, padding=1)
+        self.emb = nn.Embedding(classes, 3) if classes else None
+
+    def forward(self, t, x, y=None):
+        while t.dim() > 1:
+            t = t[:, 0]
+        if t.dim() == 0:
+            t = t.repeat(x.shape[0])
+        h = self.conv(x) * (1 + t.view(-1, 1, 1, 1))
+        if self.emb is not None:
+            h = h + self.emb(y).view(-1, 3, 1, 1)
+        return h
+
+
+def _lit(net=None, solver="euler", **kw):
+    return ConditionalFlowMatchingLitModule(
+        net=net or TinyField(), flow_matcher=ConditionalFlowMatcher(0.0),
+        solver=functools.partial(NeuralODE, solver=solver, sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+        optimizer=functools.partial(torch.optim.Adam, lr=1e-3, weight_decay=0.0),
+        scheduler=functools.partial(torch.optim.lr_scheduler.ReduceLROnPlateau, mode="min", factor=0.1, patience=10),
+        **kw)
+
+
+def test_unet_tree_matches_oracle_for_every_reference_spelling():
+    with torch.device("meta"):
+        for cfg in (ounet.CONFIG_A, ounet.CONFIG_B):
+            a, b = ounet.UNetModel(**cfg).state_dict(), UNetModel(**cfg).state_dict()
+            assert list(a) == list(b) and all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        raw = dict(image_size=256, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                   attention_resolutions=[16, 8], dropout=0.1, channel_mult=(1, 2, 2, 4), num_head_channels=32,
+                   use_scale_shift_norm=True)  # raw ctor spelling: src/models/components/unet_4to3.py:51-67
+        a, b = ounet.RawUNetModel(**raw).state_dict(), RawUNetModel(**raw).state_dict()
+        assert list(a) == list(b) and sum(v.numel() for v in b.values()) == 76_214_275 - 128 * 9  # 3-ch stem
+    net = UNetModel(**dict(ounet.CONFIG_A, num_channels=32))
+    assert float(net.out[2].weight.abs().max()) == 0.0  # zero_module init like the reference
+
+
+def test_unsupported_reference_options_raise_instead_of_falling_back():
+    with pytest.raises(NotImplementedError):
+        UNetModel(dim=[3, 32, 32], num_channels=32, num_res_blocks=1, use_scale_shift_norm=False)
+    with pytest.raises(NotImplementedError):
+        UNetModel(dim=[3, 32, 32], num_channels=32, num_res_blocks=1, use_scale_shift_norm=True, use_fp16=True)
+    with pytest.raises(ValueError):
+        UNetModel(dim=[3, 48, 48], num_channels=32, num_res_blocks=1, use_scale_shift_norm=True)
+
+
+def test_litmodule_surface_matches_reference():
+    lit = _lit()
+    x0, x1 = torch.rand(2, 3, 8, 8), torch.rand(2, 3, 8, 8)
+    t = torch.tensor([0.2, 0.9])
+    loss = lit.model_step((x0, x1), t=t)
+    want = oflow.model_step(lit.net, oflow.ConditionalFlowMatcher(0.0), (x0, x1), t=t)
+    assert torch.allclose(loss, want)
+    assert lit.training_step((x0, x1), 0).dim() == 0 and "train/loss" in lit.logged
+    lit.validation_step((x0, x1), 0), lit.test_step((x0, x1), 0)
+    assert {"val/loss", "test/loss"} <= set(lit.logged)
+    cfg = lit.configure_optimizers()
+    assert isinstance(cfg["optimizer"], torch.optim.Adam)
+    assert cfg["lr_scheduler"]["monitor"] == "val/loss" and cfg["lr_scheduler"]["interval"] == "epoch"
+    assert cfg["lr_scheduler"]["frequency"] == 1
+    assert all(k.startswith("net.") for k in lit.state_dict())
+    pickle.loads(pickle.dumps(TinyField()))  # nets must stay picklable (save_hyperparameters pickles `net`)
+
+
+def test_generate_semantics():
+    lit = _lit()
+    x = torch.rand(3, 8, 8)
+    out = lit.generate(x, num_steps=6)  # (C,H,W) accepted; eval mode; num_steps time points = 5 Euler steps
+    assert out.shape == (1, 3, 8, 8) and not lit.training
+    want = oflow.generate(lit.net, x, num_steps=6, solver="euler")
+    assert torch.allclose(out, want, atol=1e-6)
+    lit_none = ConditionalFlowMatchingLitModule(net=TinyField(), flow_matcher=ConditionalFlowMatcher(0.0), solver=None)
+    with pytest.raises(ValueError, match="Solver is not initialized"):
+        lit_none.generate(x)
+    # literal reference behaviour: a functools.partial has no .solver/.atol attributes -> dopri5 @ 1e-4 always
+    ref_like = _lit(solver="euler", reference_solver_defaults=True)
+    node = ref_like._make_node(ref_like.net)
+    assert (node.solver, node.atol, node.rtol, node.sensitivity) == ("dopri5", 1e-4, 1e-4, "adjoint")
+    out_d = ref_like.generate(x, num_steps=2)
+    want_d = oflow.generate(ref_like.net, x, num_steps=2, solver="dopri5")
+    assert torch.allclose(out_d, want_d, atol=1e-5)
+
+
+def test_class_conditional_module():
+    net = TinyField(classes=3)
+    lit = ClassConditionalFlowMatchingLitModule(
+        net=net, flow_matcher=ConditionalFlowMatcher(0.0),
+        solver=functools.partial(NeuralODE, solver="euler"), optimizer=functools.partial(torch.optim.Adam, lr=1e-3))
+    x0, x1 = torch.rand(2, 3, 8, 8), torch.rand(2, 3, 8, 8)
+    y = torch.tensor([0, 2])
+    t = torch.tensor([0.1, 0.6])
+    loss = lit.model_step((x0, x1, y.float()), t=t)  # labels arrive as any dtype; `.long()` like the reference
+    tt = t.view(-1, 1, 1, 1)
+    assert torch.allclose(loss, torch.mean((net(t, tt * x1 + (1 - tt) * x0, y=y) - (x1 - x0)) ** 2))
+    a = lit.generate(x0, 2, num_steps=4)
+    b = lit.generate(x0, torch.tensor(2), num_steps=4)
+    c = lit.generate(x0, torch.tensor([2, 2]), num_steps=4)
+    assert torch.allclose(a, b) and torch.allclose(a, c)
+    w = ConditionalWrapper(net, y)
+    assert torch.allclose(w(t, x0, args=None), net(t, x0, y=y))  # absorbs torchdyn's `args=` keyword
+
+
+def test_neural_ode_generic_paths_match_oracle():
+    f = TinyField().eval()
+    x = torch.rand(2, 3, 8, 8)
+    for solver in ("euler", "midpoint", "rk4", "dopri5"):
+        ts = torch.linspace(0, 1, 4)
+        with torch.no_grad():
+            got = NeuralODE(f, solver=solver, atol=1e-4, rtol=1e-4).trajectory(x, ts)
+            want = oflow.NeuralODE(f, solver=solver, atol=1e-4, rtol=1e-4).trajectory(x, ts)
+        assert got.shape == (4, 2, 3, 8, 8)
+        assert torch.allclose(got, want, atol=1e-5), solver
+    t_eval, sol = NeuralODE(f, solver="euler")(x, torch.linspace(0, 1, 3))
+    assert sol.shape[0] == 3 and len(t_eval) == 3
+    with pytest.raises(NotImplementedError):
+        NeuralODE(f, solver="tsit5").trajectory(x, torch.linspace(0, 1, 3))
+
+
+def test_flow_matcher_semantics():
+    fm = ConditionalFlowMatcher(0.5)
+    x0, x1 = torch.zeros(4, 3, 4, 4), torch.ones(4, 3, 4, 4)
+    torch.manual_seed(3)
+    t, xt, ut, eps = fm.sample_location_and_conditional_flow(x0, x1, return_noise=True)
+    torch.manual_seed(3)
+    t_o, xt_o, ut_o, eps_o = oflow.ConditionalFlowMatcher(0.5).sample_location_and_conditional_flow(
+        x0, x1, return_noise=True)
+    assert torch.equal(t, t_o) and torch.equal(xt, xt_o) and torch.equal(ut, ut_o) and torch.equal(eps, eps_o)
+
+
+def test_conv_plan_bookkeeping():
+    p = ConvPlan((Seg(0, 0, 0, 128, 9, 1), Seg(1, 1, 0, 256, 1, 1), Seg(2, 1, 256, 96, 1, 1)), 128)
+    assert p.ktot() == 9 * 128 + 256 + 128  # channel counts are padded to 64-wide k-blocks per segment
+    q = ConvPlan((Seg(0, 0, 0, 64, 9, 2),), 64)
+    assert q.uid != p.uid and q.ktot() == 576
