@@ -253,6 +253,8 @@ def run_train(args, rank, world, local):
                 e["frac_hbm_peak"] = e["gbs"] / pk["hbm"]
             kern[name] = e
         out["kernels"] = kern
+        out["profiled_kernel_ms_per_step"] = round(sum(d["ms"] for d in prof.values()), 3)
+        out["peak_mem_gb"] = round(torch.cuda.max_memory_allocated() / 2**30, 2)
         out["model_flops_utilisation"] = (FLOP_TRAIN_PER_TILE * B / (step_ms / 1e3)) / 1e12 / pk["tf"]
         out["clocks"] = clocks
         out["cpu_baseline"] = cpu_baseline(sample_steps=1) if (world == 1 and not args.no_cpu) else None

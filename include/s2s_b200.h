@@ -151,8 +151,8 @@ int s2s_adam_chunk(void);
  * chunk index), one CTA each.  `step` is the 1-based step count, grad_scale multiplies every gradient first.
  * Replaces: torch.optim.Adam / _multi_tensor_adam (configs/model/conditional_flow_matching.yaml:3-7,
  * src/models/conditional_flow_matching.py:112-131). */
-int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int step, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ class ConvSrc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("C", C.c_int), ("taps", C.c_int), ("stride", C.c_int)]
 
 
-_vp, _i, _f, _u64, _ll = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_longlong
+_vp, _i, _f, _d, _u64, _ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must mirror include/s2s_b200.h exactly.
 SIGNATURES = {
@@ -51,7 +51,7 @@ SIGNATURES = {
     "s2s_nchw_f32_to_nhwc16": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_adam_chunk": [],
-    "s2s_adam_multi": [_vp, _vp, _i, _f, _f, _f, _f, _f, _i, _f, _vp],
+    "s2s_adam_multi": [_vp, _vp, _i, _d, _d, _d, _d, _d, _i, _d, _vp],
 }
 _RESTYPES = {"s2s_last_error": C.c_char_p}
 

@@ -107,6 +107,28 @@ int set_smem(K kernel, size_t bytes) {
 
 constexpr size_t kSmemBudget = 227 * 1024;
 
+// run-time flag / format -> template argument
+#define S2S_BOOL(cond, NAME, ...)                 \
+    do {                                          \
+        if (cond) {                               \
+            constexpr bool NAME = true;           \
+            __VA_ARGS__;                          \
+        } else {                                  \
+            constexpr bool NAME = false;          \
+            __VA_ARGS__;                          \
+        }                                         \
+    } while (0)
+#define S2S_FMT(fmt, NAME, ...)                   \
+    do {                                          \
+        if ((fmt) == S2S_FMT_F16) {               \
+            constexpr int NAME = kFmtF16;         \
+            __VA_ARGS__;                          \
+        } else {                                  \
+            constexpr int NAME = kFmtBF16;        \
+            __VA_ARGS__;                          \
+        }                                         \
+    } while (0)
+
 int ew_grid(long long work_items, int threads = kEwThreads) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)num_sms() * 16;
@@ -115,16 +137,19 @@ int ew_grid(long long work_items, int threads = kEwThreads) {
     return (int)blocks;
 }
 
-// pixels per CTA for the (chunk, sample) grids of the normalisation kernels: ~4 CTAs per SM-wave, >= 64 pixel rows
-// Depends on (B, HW) only, so that every source of a channel concat is cut into the same pixel chunks (the
-// per-chunk partial statistics of the sources then line up).
+// Pixels per CTA for the (chunk, sample) grids of the normalisation kernels.  The kernels run at 2, 3 or 4 CTAs per SM
+// (register-bound), so the grid B x chunks is made a multiple of 148 * lcm(2,3,4) = 1776 CTAs whenever the tensor is
+// big enough: every wave is full and there is no tail wave (a 2.05-wave grid costs 3 waves).  Depends on (B, HW) only,
+// so that every source of a channel concat is cut into the same pixel chunks (their partial statistics line up).
 int pick_pix_per_cta(int B, int HW, int /*C*/) {
-    long long target_ctas = (long long)num_sms() * 8;
-    long long chunks = (target_ctas + B - 1) / B;
-    if (chunks < 1) chunks = 1;
+    const long long wave = (long long)num_sms() * 12;
+    long long a = B, b = wave;
+    while (b) { long long t = a % b; a = b; b = t; }  // a = gcd(B, wave)
+    const long long base = wave / a;                  // smallest chunk count with (B * chunks) % wave == 0
+    long long k = (2 * wave + (long long)B * base - 1) / ((long long)B * base);  // aim at >= 2 * wave CTAs in total
+    long long chunks = base * (k < 1 ? 1 : k);
     long long ppc = (HW + chunks - 1) / chunks;
-    if (ppc < 128) ppc = 128;
-    ppc = (ppc + 31) / 32 * 32;
+    if (ppc < 32) ppc = 32;  // tiny tensors: launch latency dominates, keep some work per CTA
     if (ppc > HW) ppc = HW;
     return (int)ppc;
 }
@@ -210,13 +235,17 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
         if (rc) return rc;
     }
     p.B = B; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout;
+    // narrow-N layers (Cout <= 128) would re-fetch the weight tile once per 128 pixels and run into the shared-memory /
+    // L2 feed limit (A + B = 32 KB per 256 MMA cycles); two pixel sub-tiles per CTA tile share one weight tile instead.
+    const int mt = (!out_f32 && BN <= 128 && Hout >= 2 * kTileH) ? 2 : 1;
+    p.mt = mt;
     p.tiles_x = (Wout + kTileW - 1) / kTileW;
-    p.tiles_y = (Hout + kTileH - 1) / kTileH;
+    p.tiles_y = (Hout + kTileH * mt - 1) / (kTileH * mt);
     p.n_tiles_n = npad / BN;
     p.total_tiles = B * p.tiles_x * p.tiles_y * p.n_tiles_n;
     p.BN = BN;
     p.kblocks = kblocks;
-    p.tmem_cols = pow2_cols(2 * BN);
+    p.tmem_cols = pow2_cols(2 * mt * BN);
     p.bias = bias;
     p.residual = (const __nv_bfloat16*)residual;
     p.out_f32 = out_f32;
@@ -224,7 +253,7 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
     p.axpy_a = axpy_a;
     p.a_fmt = a_fmt; p.w_fmt = w_fmt; p.out_fmt = out_fmt; p.res_fmt = res_fmt;
     const size_t b_bytes = (size_t)(BN < 64 ? 64 : BN) * kBlockK * 2;
-    const size_t stage_bytes = kABytes + b_bytes;
+    const size_t stage_bytes = (size_t)mt * kABytes + b_bytes;
     const size_t fixed = 2 * kOutStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
     int stages = (int)((kSmemBudget - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -260,7 +289,9 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     p.tiles_y = (Hout + kTileH - 1) / kTileH;
     p.pix_tiles = B * p.tiles_x * p.tiles_y;
     const int mn = taps * p.m_tiles * p.n_tiles;
-    int splits = (2 * num_sms() + mn - 1) / mn;
+    // one CTA per SM (shared memory bound): size the split-K factor so that the grid is at most ONE full wave --
+    // 297 CTAs on 148 SMs would cost three waves for two waves of work.
+    int splits = num_sms() / mn;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     if (splits < 1) splits = 1;
     p.splits = splits;
@@ -304,8 +335,8 @@ int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, in
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    gn_stats_kernel<<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, C, HW, ppc, (float2*)stats,
-                                                                  Ctot, c_off, x_fmt);
+    S2S_FMT(x_fmt, XF, (gn_stats_kernel<XF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+                           (const __nv_bfloat16*)x, C, HW, ppc, (float2*)stats, Ctot, c_off)));
     LAUNCH_CHECK("gn_stats_kernel");
     return S2S_OK;
 }
@@ -318,7 +349,8 @@ int s2s_gn_chunks(int B, int HW) {
 int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
                 int HW, float eps, float* coef, float* mean_rstd, void* stream) {
     if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_coef: G = %d, C = %d unsupported", G, C);
-    gn_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)stats, s2s_gn_chunks(B, HW), gamma, beta, film,
+    if (C > 4096) return fail(S2S_ERR_INVALID, "gn_coef: C = %d unsupported (<= 4096)", C);
+    gn_coef_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const float2*)stats, s2s_gn_chunks(B, HW), gamma, beta, film,
                                                         C, G, HW, eps, (float2*)coef, (float2*)mean_rstd);
     LAUNCH_CHECK("gn_coef_kernel");
     return S2S_OK;
@@ -331,14 +363,10 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    if (silu)
-        gn_apply_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed,
-            x_fmt, y_fmt);
-    else
-        gn_apply_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p, seed,
-            x_fmt, y_fmt);
+    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
+        (gn_apply_kernel<SILU, DROP, XF, YF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p,
+            seed))))));
     LAUNCH_CHECK("gn_apply_kernel");
     return S2S_OK;
 }
@@ -350,14 +378,10 @@ int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    if (silu)
-        gn_bwd_reduce_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+        (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, x_fmt, g_fmt);
-    else
-        gn_bwd_reduce_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, x_fmt, g_fmt);
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed))))));
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
 }
@@ -380,14 +404,10 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    if (silu)
-        gn_bwd_apply_kernel<true><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, x_fmt, g_fmt);
-    else
-        gn_bwd_apply_kernel<false><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float4*)pqr, Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, x_fmt, g_fmt);
+    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+        (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
+            Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed)))))));
     LAUNCH_CHECK("gn_bwd_apply_kernel");
     return S2S_OK;
 }
@@ -458,18 +478,19 @@ int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int
 
 int s2s_adam_chunk(void) { return kAdamChunk; }
 
-int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int step, float grad_scale, void* stream) {
+int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int step, double grad_scale, void* stream) {
     static_assert(sizeof(s2s_adam_tensor) == sizeof(AdamTensor), "ABI struct drifted from the kernel's");
     if (n_work <= 0) return S2S_OK;
     if (!tensors_dev || !work_dev || step < 1) return fail(S2S_ERR_INVALID, "adam_multi: bad arguments");
     AdamHyper h;
-    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
-    h.omb1 = (float)(1.0 - (double)beta1);
-    h.omb2 = (float)(1.0 - (double)beta2);
-    h.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
-    h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)step)));
-    h.grad_scale = grad_scale;
+    h.lr = (float)lr; h.beta1 = (float)beta1; h.beta2 = (float)beta2; h.eps = (float)eps;
+    h.weight_decay = (float)weight_decay;
+    h.omb1 = (float)(1.0 - beta1);
+    h.omb2 = (float)(1.0 - beta2);
+    h.bias_corr1 = (float)(1.0 - pow(beta1, (double)step));
+    h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
+    h.grad_scale = (float)grad_scale;
     adam_multi_kernel<<<n_work, kAdamThreads, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors_dev,
                                                                           (const int2*)work_dev, h);
     LAUNCH_CHECK("adam_multi_kernel");

@@ -218,10 +218,26 @@ __device__ __forceinline__ float unpack1(uint16_t u, int fmt) {
     if (fmt == kFmtF16) return __half2float(*reinterpret_cast<__half*>(&u));
     return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
 }
-__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
+// silu(z) = z / (1 + 2^(-z log2 e)): two MUFU ops (ex2, rcp), no range-fixup branches (ftz; z -> -inf gives -0)
+__device__ __forceinline__ float silu_f(float z) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(z * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return z * r;
+}
 __device__ __forceinline__ float silu_grad_f(float z) {
     float s = 1.0f / (1.0f + __expf(-z));
     return s * (1.0f + z * (1.0f - s));
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// d silu / dz with sigmoid(z) = 0.5 tanh(z / 2) + 0.5: ONE MUFU op per element (backward kernels; bf16 gradients)
+__device__ __forceinline__ float silu_grad_fast(float z) {
+    const float s = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+    return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -49,6 +49,7 @@ struct ConvParams {
     int B, Hout, Wout, Cout;
     int tiles_x, tiles_y, n_tiles_n, total_tiles;
     int BN;          // 16, 64, 128 or 256
+    int mt;          // M sub-tiles (8 x 16 pixel patches stacked in y) per CTA tile sharing one weight tile: 1 or 2
     int kblocks;     // total k-blocks per tile
     int num_stages;
     uint32_t tmem_cols;
@@ -78,7 +79,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
     const uint32_t b_bytes = (uint32_t)(BN < 64 ? 64 : BN) * kBlockK * 2;  // B region per stage (>= 8 KB keeps 1 KB alignment)
-    const uint32_t stage_bytes = kABytes + b_bytes;
+    const int MT = p.mt;
+    const uint32_t a_bytes = (uint32_t)MT * kABytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
     const int S = p.num_stages;
 
     uint8_t* ring = smem;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int b, ty, tx, nt;
                 conv_decode_tile(p, tile, b, ty, tx, nt);
-                const int x0 = tx * kTileW, y0 = ty * kTileH, n0 = nt * BN;
+                const int x0 = tx * kTileW, y0 = ty * kTileH * MT, n0 = nt * BN;
                 int kb = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const ConvSeg sg = p.seg[s];
@@ -145,9 +148,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
                             mbar_wait(&empty[stage], phase ^ 1);
                             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-                            uint8_t* b_dst = a_dst + kABytes;
-                            mbar_arrive_expect_tx(&full[stage], kABytes + (uint32_t)BN * kBlockK * 2);
-                            tma_load_5d(a_dst, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp, cy, b);
+                            uint8_t* b_dst = a_dst + a_bytes;
+                            mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)BN * kBlockK * 2);
+                            for (int h = 0; h < MT; ++h)
+                                tma_load_5d(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp,
+                                            cy + h * kTileH, b);
                             tma_load_2d(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
                             if (++stage == S) {
                                 stage = 0;
@@ -170,17 +175,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty[as], aphase ^ 1);  // epilogue drained this accumulator stage
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                    const uint32_t b_addr = a_addr + a_bytes;
+                    for (int h = 0; h < MT; ++h) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
+                            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                            umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
                     if (++stage == S) {
@@ -201,16 +208,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             int b, ty, tx, nt;
             conv_decode_tile(p, tile, b, ty, tx, nt);
-            const int x0 = tx * kTileW, y0 = ty * kTileH, n0 = nt * BN;
-            const int py = y0 + row / kTileW, px = x0 + row % kTileW;
-            const bool in_img = (py < p.Hout) && (px < p.Wout);
+            const int x0 = tx * kTileW, y0 = ty * kTileH * MT, n0 = nt * BN;
+            const int px = x0 + row % kTileW;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
-            if (p.mode == kModeF32Nchw) {
+            if (p.mode == kModeF32Nchw) {  // narrow head conv (MT == 1)
+                const int py = y0 + row / kTileW;
+                const bool in_img = (py < p.Hout) && (px < p.Wout);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
                 uint32_t v[16];
                 tmem_ld_32x16(t_row, v);
                 tmem_ld_wait();
@@ -229,62 +237,68 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
 
             const int nchunks = BN / 64;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(t_row + ch * 64, v0);
-                tmem_ld_32x32(t_row + ch * 64 + 32, v1);
-                tmem_ld_wait();
-                if (ch == nchunks - 1) {
-                    // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
-                }
-                const int nbase = n0 + ch * 64;
-                uint32_t packed[32];
-                const uint4* res = nullptr;
-                if (p.residual && in_img)
-                    res = reinterpret_cast<const uint4*>(p.residual + (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout +
-                                                         nbase);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = j * 8 + e;
-                        f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
-                        if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+            for (int h = 0; h < MT; ++h) {
+                const int ys = y0 + h * kTileH;  // first image row of this sub-tile
+                const int py = ys + row / kTileW;
+                const bool in_img = (py < p.Hout) && (px < p.Wout);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(t_row + ch * 64, v0);
+                    tmem_ld_32x32(t_row + ch * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (h == MT - 1 && ch == nchunks - 1) {
+                        // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[as]);
                     }
-                    if (res) {
-                        const uint4 r = __ldg(res + j);
-                        float2 t;
-                        t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
-                        t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
-                        t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
-                        t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
-                    }
-                    packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
-                    packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
-                    packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
-                    packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
-                }
-                // staging buffer `ob` was last read by the TMA store issued two chunks ago
-                if (et == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
-                uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
+                    const int nbase = n0 + ch * 64;
+                    uint32_t packed[32];
+                    const uint4* res = nullptr;
+                    if (p.residual && in_img)
+                        res = reinterpret_cast<const uint4*>(p.residual +
+                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
-                    *reinterpret_cast<uint4*>(dst + sw * 16) =
-                        make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                    for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = j * 8 + e;
+                            f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                            if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                        }
+                        if (res) {
+                            const uint4 r = __ldg(res + j);
+                            float2 t;
+                            t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                            t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                            t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                            t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
+                        }
+                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
+                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
+                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
+                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
+                    }
+                    // staging buffer `ob` was last read by the TMA store issued two chunks ago
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
+                        *reinterpret_cast<uint4*>(dst + sw * 16) =
+                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (et == 0) {
+                        tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, ys, b);
+                        tma_store_commit();
+                    }
+                    ob ^= 1;
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(2, 128);
-                if (et == 0) {
-                    tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, y0, b);
-                    tma_store_commit();
-                }
-                ob ^= 1;
             }
         }
         if (et == 0) tma_store_wait_all<0>();
@@ -336,11 +350,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
 
     // work item decode
+    // tap fastest: the CTAs that share a pixel range (same split) and differ only in tap / m-tile / n-tile are
+    // launched next to each other, run concurrently and walk the same dY / X tiles, so the 9x (taps) re-reads of both
+    // operands are L2 hits instead of HBM traffic.
     int w = blockIdx.x;
-    const int split = w % p.splits;  w /= p.splits;
-    const int nt = w % p.n_tiles;    w /= p.n_tiles;
+    const int tap = w % p.taps;      w /= p.taps;
     const int mt = w % p.m_tiles;    w /= p.m_tiles;
-    const int tap = w;
+    const int nt = w % p.n_tiles;    w /= p.n_tiles;
+    const int split = w;
     const int per = (p.pix_tiles + p.splits - 1) / p.splits;
     const int kbeg = split * per;
     const int kend = min(p.pix_tiles, kbeg + per);

@@ -22,6 +22,28 @@ __device__ __forceinline__ void cvt8_in(const uint4& u, int fmt, float (&f)[8]) 
 __device__ __forceinline__ uint4 cvt8_out(const float (&f)[8], int fmt) {
     return make_uint4(pack2(f[0], f[1], fmt), pack2(f[2], f[3], fmt), pack2(f[4], f[5], fmt), pack2(f[6], f[7], fmt));
 }
+// compile-time format variants (the hot kernels are instantiated per format: a run-time format costs two predicated
+// conversion sequences per element, and these kernels are instruction-issue bound next to the HBM roofline)
+template <int F>
+__device__ __forceinline__ float2 unpack2_t(uint32_t u) {
+    return F == kFmtF16 ? unpack_f16x2(u) : unpack_bf16x2(u);
+}
+template <int F>
+__device__ __forceinline__ uint32_t pack2_t(float lo, float hi) {
+    return F == kFmtF16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+template <int F>
+__device__ __forceinline__ void cvt8_in_t(const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack2_t<F>(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack2_t<F>(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack2_t<F>(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack2_t<F>(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <int F>
+__device__ __forceinline__ uint4 cvt8_out_t(const float (&f)[8]) {
+    return make_uint4(pack2_t<F>(f[0], f[1]), pack2_t<F>(f[2], f[3]), pack2_t<F>(f[4], f[5]), pack2_t<F>(f[6], f[7]));
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -35,13 +57,16 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
                  : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ Philox4x32-10
-// Counter-based dropout mask: element i of a tensor draws from counter (i / 4), lane (i % 4).  The mask is a pure
-// function of (seed, element index), so backward regenerates it instead of storing it.
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-    uint32_t c2 = 0, c3 = 0;
+// ------------------------------------------------------------------------------------------------ Philox4x32-7
+// Counter-based dropout mask: the 8 consecutive elements starting at element index 8*e8 draw from counter e8, one
+// 16-bit lane each (keep iff lane >= round(p * 65536): p is honoured to 2^-16).  The mask is a pure function of
+// (seed, element index), so backward regenerates it instead of storing it.  7 rounds is the smallest Philox4x32
+// variant that passes BigCrush; one call per 8 elements keeps the integer work at ~7 ops / element, inside the
+// HBM-roofline instruction budget of the normalisation kernels (~20 lane-ops per 4 bytes moved).
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0x243F6A88u, c3 = 0x85A308D3u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -51,14 +76,15 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
     }
     return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask bits for 8 consecutive elements starting at element index e8*8 (8 bits, bit j = keep element j)
-__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsigned long long e8, uint32_t thresh) {
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const uint4 a = philox4x32((uint32_t)(2 * e8), (uint32_t)((2 * e8) >> 32), k0, k1);
-    const uint4 b = philox4x32((uint32_t)(2 * e8 + 1), (uint32_t)((2 * e8 + 1) >> 32), k0, k1);
+__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+// keep-mask bits for 8 consecutive elements starting at element index e8*8 (bit j = keep element j)
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsigned long long e8, uint32_t thresh16) {
+    const uint4 r = philox4x32_7((uint32_t)e8, (uint32_t)(e8 >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
     uint32_t m = 0;
-    m |= (a.x >= thresh) << 0; m |= (a.y >= thresh) << 1; m |= (a.z >= thresh) << 2; m |= (a.w >= thresh) << 3;
-    m |= (b.x >= thresh) << 4; m |= (b.y >= thresh) << 5; m |= (b.z >= thresh) << 6; m |= (b.w >= thresh) << 7;
+    m |= ((r.x & 0xffffu) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;
+    m |= ((r.y & 0xffffu) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
+    m |= ((r.z & 0xffffu) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
+    m |= ((r.w & 0xffffu) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
     return m;
 }
 
@@ -150,10 +176,13 @@ __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
+constexpr int kGnUnroll = 4;  // independent 16 B loads in flight per thread and per input tensor
+
 // stats[b][chunk][c_off + c] = (sum, sumsq) over the pixels of one chunk of the sample (no atomics: deterministic).
-__global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
-                                                              int pix_per_cta, float2* __restrict__ stats, int Ctot,
-                                                              int c_off, int xfmt) {
+template <int XF>
+__global__ void __launch_bounds__(kEwThreads, 4) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
+                                                                 int pix_per_cta, float2* __restrict__ stats, int Ctot,
+                                                                 int c_off) {
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
@@ -165,28 +194,28 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
     int p = p0 + prow;
-    for (; p + 3 * pstep < p1; p += 4 * pstep) {  // 4 independent 16 B loads in flight per thread
-        uint4 u[4];
+    for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {
+        uint4 u[kGnUnroll];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
+        for (int i = 0; i < kGnUnroll; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kGnUnroll; ++i) {
             float f[8];
-            cvt8_in(u[i], xfmt, f);
+            cvt8_in_t<XF>(u[i], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 s[e] += f[e];
-                ss[e] += f[e] * f[e];
+                ss[e] = fmaf(f[e], f[e], ss[e]);
             }
         }
     }
     for (; p < p1; p += pstep) {
         float f[8];
-        cvt8_in(ldg_stream(src + (size_t)p * vpp + slot), xfmt, f);
+        cvt8_in_t<XF>(ldg_stream(src + (size_t)p * vpp + slot), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s[e] += f[e];
-            ss[e] += f[e] * f[e];
+            ss[e] = fmaf(f[e], f[e], ss[e]);
         }
     }
 #pragma unroll
@@ -195,7 +224,6 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
         red[threadIdx.x][8 + e] = ss[e];
     }
     __syncthreads();
-    // thread (slot, e) for prow == 0..: reduce over pixel rows.  vpp*8 = C channels, up to 2048 -> loop
     for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
         const int sl = ci >> 3, e = ci & 7;
         float a = 0.f, q = 0.f;
@@ -211,20 +239,38 @@ __global__ void __launch_bounds__(kEwThreads) gn_stats_kernel(const __nv_bfloat1
 // Per-(sample, channel) affine coefficients of the fused normalisation:
 //   y = silu?( x * A + Bc ),  A = rstd_g * gamma_c * (1 + scale_bc),  Bc = (beta_c - mean_g*rstd_g*gamma_c)*(1+scale_bc) + shift_bc
 // Also records (mean, rstd) per (sample, group) for backward.  film: [B][2C] fp32 (scale | shift) or nullptr.
-__global__ void gn_coef_kernel(const float2* __restrict__ stats, int nchunks, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ film, int C, int G, int HW,
-                               float eps, float2* __restrict__ coef, float2* __restrict__ mean_rstd) {
+// One CTA per sample; dynamic smem = 2 * C floats (per-channel totals).
+__global__ void __launch_bounds__(256) gn_coef_kernel(const float2* __restrict__ stats, int nchunks,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ film, int C, int G, int HW, float eps,
+                                                      float2* __restrict__ coef, float2* __restrict__ mean_rstd) {
+    extern __shared__ float s_tot[];  // [C] sums, [C] sums of squares
+    __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.x;
     const int cpg = C / G;
-    __shared__ float s_mean[64], s_rstd[64];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float2* sp = stats + (size_t)b * nchunks * C + c;
+        float a = 0.f, q = 0.f;
+        int k = 0;
+        for (; k + 4 <= nchunks; k += 4) {  // fixed summation order (deterministic), 4 loads in flight
+            const float2 t0 = sp[(size_t)(k + 0) * C], t1 = sp[(size_t)(k + 1) * C];
+            const float2 t2 = sp[(size_t)(k + 2) * C], t3 = sp[(size_t)(k + 3) * C];
+            a += t0.x; q += t0.y; a += t1.x; q += t1.y; a += t2.x; q += t2.y; a += t3.x; q += t3.y;
+        }
+        for (; k < nchunks; ++k) {
+            const float2 t = sp[(size_t)k * C];
+            a += t.x; q += t.y;
+        }
+        s_tot[c] = a;
+        s_tot[C + c] = q;
+    }
+    __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float a = 0.f, q = 0.f;
-        for (int k = 0; k < nchunks; ++k)
-            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-                const float2 st = stats[((size_t)b * nchunks + k) * C + c];
-                a += st.x;
-                q += st.y;
-            }
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += s_tot[c];
+            q += s_tot[C + c];
+        }
         const float n = (float)cpg * (float)HW;
         const float mean = a / n;
         const float var = fmaxf(q / n - mean * mean, 0.f);
@@ -249,13 +295,12 @@ __global__ void gn_coef_kernel(const float2* __restrict__ stats, int nchunks, co
     }
 }
 
-// y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), bf16 NHWC in / out (out row stride ld_out channels).
-template <bool kSilu>
-__global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
-                                                              int pix_per_cta, const float2* __restrict__ coef,
-                                                              int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
-                                                              int ld_out, float drop_p, unsigned long long seed,
-                                                              int xfmt, int yfmt) {
+// y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), 16-bit NHWC in / out (out row stride ld_out channels).
+template <bool kSilu, bool kDrop, int XF, int YF>
+__global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
+                                                                 int pix_per_cta, const float2* __restrict__ coef,
+                                                                 int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
+                                                                 int ld_out, float drop_p, unsigned long long seed) {
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
@@ -270,100 +315,165 @@ __global__ void __launch_bounds__(kEwThreads) gn_apply_kernel(const __nv_bfloat1
     }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
     __nv_bfloat16* dst = y + (size_t)b * HW * ld_out + c_off + slot * 8;
-    const bool drop = drop_p > 0.f;
-    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
-    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
+    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_out >> 3) +
+                                       (unsigned long long)((c_off >> 3) + slot);
     auto body = [&](const uint4& u, int p) {
         float f[8];
-        cvt8_in(u, xfmt, f);
+        cvt8_in_t<XF>(u, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float z = fmaf(f[e], A[e], Bc[e]);
+            const float z = fmaf(f[e], A[e], Bc[e]);
             f[e] = kSilu ? silu_f(z) : z;
         }
-        if (drop) {
-            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_out >> 3) +
-                                          (unsigned long long)((c_off >> 3) + slot);
-            const uint32_t m = dropout_keep8(seed, e8, thresh);
+        if (kDrop) {
+            const uint32_t m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_out >> 3), thresh);
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
         }
-        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), cvt8_out(f, yfmt));
+        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), cvt8_out_t<YF>(f));
     };
     int p = p0 + prow;
-    for (; p + 3 * pstep < p1; p += 4 * pstep) {
-        uint4 u[4];
+    for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {
+        uint4 u[kGnUnroll];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
+        for (int i = 0; i < kGnUnroll; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) body(u[i], p + i * pstep);
+        for (int i = 0; i < kGnUnroll; ++i) body(u[i], p + i * pstep);
     }
     for (; p < p1; p += pstep) body(ldg_stream(src + (size_t)p * vpp + slot), p);
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm backward
 // Forward: z = x*A + Bc, a = dropout(silu(z)).  Given g = dL/da:  dz = g * mask/keep * silu'(z).
-// Pass 1 (this kernel): red[b][c] = (sum_p dz, sum_p dz * xhat) with xhat = (x - mean_g) * rstd_g.
-template <bool kSilu>
-__global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                   const __nv_bfloat16* __restrict__ g, int ld_g,
-                                                                   int C, int HW, int pix_per_cta,
-                                                                   const float2* __restrict__ coef,
-                                                                   const float2* __restrict__ mean_rstd, int G,
-                                                                   int Ctot, int c_off, float2* __restrict__ red_out,
-                                                                   float drop_p, unsigned long long seed, int xfmt,
-                                                                   int gfmt) {
+// The sigmoid inside silu' uses one tanh.approx (relative error 2^-11, far below the bf16 gradient storage); the
+// forward keeps the two-MUFU exact form because its result is stored with an 11-bit significand.
+// Pass 1 (this kernel): per chunk, (sum_p dz, sum_p dz * xhat) with xhat = (x - mean_g) * rstd_g, accumulated as
+// (sum dz, sum dz*x) in the streaming loop and centred once per channel at the end.
+// Per-thread channel coefficients of z = x*A + Bc.  fp16 activations: held as 4 half2 pairs (z and silu' are then
+// evaluated with packed half2 arithmetic and ONE tanh.approx.f16x2 per two elements -- z only feeds silu', whose
+// result multiplies a bf16 gradient, so 11 significant bits are ample); otherwise 8 + 8 fp32 values.
+template <int XF>
+struct GnZCoef {
+    float A[8], Bc[8];
+    __device__ __forceinline__ void load(const float2* __restrict__ cf) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 c = cf[e];
+            A[e] = c.x;
+            Bc[e] = c.y;
+        }
+    }
+};
+template <>
+struct GnZCoef<kFmtF16> {
+    __half2 A[4], Bc[4];
+    __device__ __forceinline__ void load(const float2* __restrict__ cf) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 c0 = cf[2 * e], c1 = cf[2 * e + 1];
+            A[e] = __floats2half2_rn(c0.x, c1.x);
+            Bc[e] = __floats2half2_rn(c0.y, c1.y);
+        }
+    }
+};
+__device__ __forceinline__ __half2 tanh_approx_h2(__half2 x) {
+    uint32_t r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&x)));
+    return *reinterpret_cast<__half2*>(&r);
+}
+// silu'(z) for two elements in half2: s = 0.5 tanh(z/2) + 0.5 ; s * (1 + z (1 - s))
+__device__ __forceinline__ __half2 silu_grad_h2(__half2 z) {
+    const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
+    const __half2 s = __hfma2(half, tanh_approx_h2(__hmul2(half, z)), half);
+    return __hmul2(s, __hfma2(z, __hsub2(one, s), one));
+}
+
+// xf = x as fp32, dz = g * keep/(1-p) * silu'(x*A + Bc) for 8 consecutive channels of one pixel
+template <bool kSilu, bool kDrop, int XF, int GF>
+__device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const GnZCoef<XF>& cf, uint32_t keep,
+                                       float keep_scale, float (&xf)[8], float (&dz)[8]) {
+    cvt8_in_t<XF>(xu, xf);
+    cvt8_in_t<GF>(gu, dz);
+    if (kDrop) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dz[e] = ((keep >> e) & 1u) ? dz[e] * keep_scale : 0.f;
+    }
+    if (kSilu) {
+        if constexpr (XF == kFmtF16) {
+            const uint32_t xs[4] = {xu.x, xu.y, xu.z, xu.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half2 z = __hfma2(*reinterpret_cast<const __half2*>(&xs[e]), cf.A[e], cf.Bc[e]);
+                const float2 gr = __half22float2(silu_grad_h2(z));
+                dz[2 * e] *= gr.x;
+                dz[2 * e + 1] *= gr.y;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dz[e] *= silu_grad_fast(fmaf(xf[e], cf.A[e], cf.Bc[e]));
+        }
+    }
+}
+
+template <bool kSilu, bool kDrop, int XF, int GF>
+__global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                      const __nv_bfloat16* __restrict__ g, int ld_g,
+                                                                      int C, int HW, int pix_per_cta,
+                                                                      const float2* __restrict__ coef,
+                                                                      const float2* __restrict__ mean_rstd, int G,
+                                                                      int Ctot, int c_off, float2* __restrict__ red_out,
+                                                                      float drop_p, unsigned long long seed) {
+    constexpr int U = 2;
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    const int cpg = Ctot / G;
-    float A[8], Bc[8], mu[8], rs[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = c_off + slot * 8 + e;
-        const float2 cf = coef[(size_t)b * Ctot + c];
-        A[e] = cf.x;
-        Bc[e] = cf.y;
-        const float2 mr = mean_rstd[(size_t)b * G + c / cpg];
-        mu[e] = mr.x;
-        rs[e] = mr.y;
-    }
+    GnZCoef<XF> cf;
+    cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
     const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
     const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
-    const bool drop = drop_p > 0.f;
-    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
-    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
+    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
+                                       (unsigned long long)((c_off >> 3) + slot);
     float s1[8], s2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-    for (int p = p0 + prow; p < p1; p += pstep) {
-        float xf[8], gf[8];
-        cvt8_in(ldg_stream(xs + (size_t)p * vpp + slot), xfmt, xf);
-        cvt8_in(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gfmt, gf);
+    auto body = [&](const uint4& xu, const uint4& gu, int p) {
         uint32_t m = 0xffu;
-        if (drop) {
-            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
-                                          (unsigned long long)((c_off >> 3) + slot);
-            m = dropout_keep8(seed, e8, thresh);
-        }
+        if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+        float xf[8], dz[8];
+        gn_dz8<kSilu, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float z = fmaf(xf[e], A[e], Bc[e]);
-            float dz = ((m >> e) & 1u) ? gf[e] * keep_scale : 0.f;
-            if (kSilu) dz *= silu_grad_f(z);
-            s1[e] += dz;
-            s2[e] += dz * (xf[e] - mu[e]) * rs[e];
+            s1[e] += dz[e];
+            s2[e] = fmaf(dz[e], xf[e], s2[e]);
         }
+    };
+    int p = p0 + prow;
+    for (; p + (U - 1) * pstep < p1; p += U * pstep) {
+        uint4 xu[U], gu[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
+            gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) body(xu[i], gu[i], p + i * pstep);
     }
+    for (; p < p1; p += pstep)
+        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), p);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         red[threadIdx.x][e] = s1[e];
         red[threadIdx.x][8 + e] = s2[e];
     }
     __syncthreads();
+    const int cpg = Ctot / G;
     for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
         const int sl = ci >> 3, e = ci & 7;
         float a = 0.f, q = 0.f;
@@ -371,7 +481,8 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
             a += red[r * vpp + sl][e];
             q += red[r * vpp + sl][8 + e];
         }
-        red_out[((size_t)b * gridDim.x + blockIdx.x) * Ctot + c_off + ci] = make_float2(a, q);
+        const float2 mr = mean_rstd[(size_t)b * G + (c_off + ci) / cpg];
+        red_out[((size_t)b * gridDim.x + blockIdx.x) * Ctot + c_off + ci] = make_float2(a, (q - mr.x * a) * mr.y);
     }
 }
 
@@ -379,21 +490,28 @@ __global__ void __launch_bounds__(kEwThreads) gn_bwd_reduce_kernel(const __nv_bf
 //   dx = dz * P + x * Q + R,  P = rstd*gamma',  Q = -rstd^2 * m2,  R = -rstd*m1 + mean*rstd^2*m2
 //   m1 = sum_{c in g} gamma'_c S1_c / N,  m2 = sum_{c in g} gamma'_c S2_c / N,  gamma' = gamma * (1 + scale)
 //   dgamma_c += sum_b S2 (1+scale)   dbeta_c += sum_b S1 (1+scale)   dscale_bc = gamma S2 + beta S1   dshift_bc = S1
-__global__ void gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchunks, float2* __restrict__ red,
-                                   const float2* __restrict__ mean_rstd,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ film, int C, int G, int HW, float4* __restrict__ pqr,
-                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm) {
+__global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchunks,
+                                                          float2* __restrict__ red, const float2* __restrict__ mean_rstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ film, int C, int G, int HW,
+                                                          float4* __restrict__ pqr, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, float* __restrict__ dfilm) {
     const int b = blockIdx.x;
     const int cpg = C / G;
     __shared__ float s_m1[64], s_m2[64];
     // fold the per-chunk partials (deterministic order) into red[b][c]
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float2* rp = red_part + (size_t)b * nchunks * C + c;
         float a = 0.f, q = 0.f;
-        for (int k = 0; k < nchunks; ++k) {
-            const float2 r = red_part[((size_t)b * nchunks + k) * C + c];
-            a += r.x;
-            q += r.y;
+        int k = 0;
+        for (; k + 4 <= nchunks; k += 4) {
+            const float2 t0 = rp[(size_t)(k + 0) * C], t1 = rp[(size_t)(k + 1) * C];
+            const float2 t2 = rp[(size_t)(k + 2) * C], t3 = rp[(size_t)(k + 3) * C];
+            a += t0.x; q += t0.y; a += t1.x; q += t1.y; a += t2.x; q += t2.y; a += t3.x; q += t3.y;
+        }
+        for (; k < nchunks; ++k) {
+            const float2 t = rp[(size_t)k * C];
+            a += t.x; q += t.y;
         }
         red[(size_t)b * C + c] = make_float2(a, q);
     }
@@ -430,66 +548,70 @@ __global__ void gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchu
     }
 }
 
-// Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; bf16 NHWC.
-template <bool kSilu>
-__global__ void __launch_bounds__(kEwThreads) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                  const __nv_bfloat16* __restrict__ g, int ld_g,
-                                                                  int C, int HW, int pix_per_cta,
-                                                                  const float2* __restrict__ coef,
-                                                                  const float4* __restrict__ pqr, int Ctot, int c_off,
-                                                                  const __nv_bfloat16* __restrict__ add,
-                                                                  __nv_bfloat16* __restrict__ dx, float drop_p,
-                                                                  unsigned long long seed, int xfmt, int gfmt) {
+// Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; 16-bit NHWC.
+template <bool kSilu, bool kDrop, bool kAdd, int XF, int GF>
+__global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                     const __nv_bfloat16* __restrict__ g, int ld_g,
+                                                                     int C, int HW, int pix_per_cta,
+                                                                     const float2* __restrict__ coef,
+                                                                     const float4* __restrict__ pqr, int Ctot, int c_off,
+                                                                     const __nv_bfloat16* __restrict__ add,
+                                                                     __nv_bfloat16* __restrict__ dx, float drop_p,
+                                                                     unsigned long long seed) {
+    constexpr int U = 2;
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    float A[8], Bc[8], P[8], Q[8], R[8];
+    GnZCoef<XF> cf;
+    cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
+    float P[8], Q[8], R[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int c = c_off + slot * 8 + e;
-        const float2 cf = coef[(size_t)b * Ctot + c];
-        A[e] = cf.x;
-        Bc[e] = cf.y;
-        const float4 t = pqr[(size_t)b * Ctot + c];
+        const float4 t = pqr[(size_t)b * Ctot + c_off + slot * 8 + e];
         P[e] = t.x;
         Q[e] = t.y;
         R[e] = t.z;
     }
     const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
-    const uint4* as = add ? reinterpret_cast<const uint4*>(add + (size_t)b * HW * C) : nullptr;
+    const uint4* as = kAdd ? reinterpret_cast<const uint4*>(add + (size_t)b * HW * C) : nullptr;
     uint4* ds = reinterpret_cast<uint4*>(dx + (size_t)b * HW * C);
     const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
-    const bool drop = drop_p > 0.f;
-    const uint32_t thresh = drop ? (uint32_t)(drop_p * 4294967296.0) : 0u;
-    const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
-    for (int p = p0 + prow; p < p1; p += pstep) {
-        float xf[8], gf[8];
-        cvt8_in(ldg_stream(xs + (size_t)p * vpp + slot), xfmt, xf);
-        cvt8_in(ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), gfmt, gf);
+    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
+    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
+    const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
+                                       (unsigned long long)((c_off >> 3) + slot);
+    auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, int p) {
         uint32_t m = 0xffu;
-        if (drop) {
-            const unsigned long long e8 = ((unsigned long long)b * HW + p) * (unsigned long long)(ld_g >> 3) +
-                                          (unsigned long long)((c_off >> 3) + slot);
-            m = dropout_keep8(seed, e8, thresh);
-        }
-        float o[8];
+        if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+        float xf[8], dz[8], o[8];
+        gn_dz8<kSilu, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float z = fmaf(xf[e], A[e], Bc[e]);
-            float dz = ((m >> e) & 1u) ? gf[e] * keep_scale : 0.f;
-            if (kSilu) dz *= silu_grad_f(z);
-            o[e] = dz * P[e] + xf[e] * Q[e] + R[e];
-        }
-        if (as) {
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
+        if (kAdd) {
             float af[8];
-            cvt8_in(ldg_stream(as + (size_t)p * vpp + slot), gfmt, af);
+            cvt8_in_t<GF>(au, af);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += af[e];
         }
-        stg_stream(ds + (size_t)p * vpp + slot, cvt8_out(o, gfmt));
+        stg_stream(ds + (size_t)p * vpp + slot, cvt8_out_t<GF>(o));
+    };
+    int p = p0 + prow;
+    for (; p + (U - 1) * pstep < p1; p += U * pstep) {
+        uint4 xu[U], gu[U], au[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
+            gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
+            au[i] = kAdd ? ldg_stream(as + (size_t)(p + i * pstep) * vpp + slot) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) body(xu[i], gu[i], au[i], p + i * pstep);
     }
+    for (; p < p1; p += pstep)
+        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)),
+             kAdd ? ldg_stream(as + (size_t)p * vpp + slot) : make_uint4(0, 0, 0, 0), p);
 }
 
 // ------------------------------------------------------------------------------------------------ resampling

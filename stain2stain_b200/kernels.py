@@ -103,8 +103,9 @@ def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begi
     taps = w[0, 0].numel() if w.dim() > 2 else 1
     ci_count = cin - ci_begin if ci_count is None else ci_count
     assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == T16 and dst.is_contiguous()
-    check(_L().s2s_pack_conv_weight(ptr(w), cout, cin, taps, ci_begin, ci_count, ptr(dst), dst.shape[1], k_off,
-                                    int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
+    with _Prof("pack_conv_weight", 0.0, 6.0 * cout * ci_count * taps):
+        check(_L().s2s_pack_conv_weight(ptr(w), cout, cin, taps, ci_begin, ci_count, ptr(dst), dst.shape[1], k_off,
+                                        int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
 
 
 def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tensor, cout: int, hout: int, wout: int,
@@ -162,8 +163,9 @@ def unpack_wgrad(dw: torch.Tensor, grad: torch.Tensor, n_off: int, n_count: int,
     taps, m, ldn = dw.shape
     cin_total = grad.shape[1]
     assert grad.dtype == torch.float32 and grad.is_contiguous() and grad.shape[0] == m
-    check(_L().s2s_unpack_wgrad(ptr(dw), taps, m, ldn, n_off, n_count, ptr(grad), cin_total, n_begin, float(beta),
-                                stream_ptr()), "unpack_wgrad")
+    with _Prof("unpack_wgrad", 0.0, 8.0 * m * n_count * taps):
+        check(_L().s2s_unpack_wgrad(ptr(dw), taps, m, ldn, n_off, n_count, ptr(grad), cin_total, n_begin, float(beta),
+                                    stream_ptr()), "unpack_wgrad")
 
 
 def patch27_pack(x0: torch.Tensor, sgn: int = 1, x1: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None,
@@ -176,8 +178,9 @@ def patch27_pack(x0: torch.Tensor, sgn: int = 1, x1: Optional[torch.Tensor] = No
     if x1 is not None:
         assert x1.shape == x0.shape and x1.is_contiguous() and x1.dtype == torch.float32
         assert t.dtype == torch.float32 and t.numel() == B and t.is_contiguous()
-    check(_L().s2s_patch27_pack(ptr(x0), ptr(x1), ptr(t), B, H, W, sgn, ptr(dst), ptr(xt), fmt, stream_ptr()),
-          "patch27_pack")
+    with _Prof("patch27_pack", 0.0, (12.0 * (2 if x1 is not None else 1) + 128.0) * B * H * W):
+        check(_L().s2s_patch27_pack(ptr(x0), ptr(x1), ptr(t), B, H, W, sgn, ptr(dst), ptr(xt), fmt, stream_ptr()),
+              "patch27_pack")
     return (dst, xt) if want_xt else dst
 
 
@@ -212,7 +215,7 @@ def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int 
              y_fmt: int = ACT):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    with _Prof("gn_apply", 0.0, 4.0 * x.numel()):  # 1 read + 1 write of 2-byte elements
+    with _Prof("gn_apply_dropout" if drop_p > 0 else "gn_apply", 0.0, 4.0 * x.numel()):  # 1 read + 1 write of 2-byte elements
         check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), y.shape[3], int(silu),
                                 float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
 
@@ -249,7 +252,8 @@ def upsample2x(x):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=T16, device=x.device)
-    check(_L().s2s_upsample2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "upsample2x")
+    with _Prof("upsample2x", 0.0, 2.5 * out.numel()):
+        check(_L().s2s_upsample2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "upsample2x")
     return out
 
 
@@ -257,7 +261,8 @@ def sumpool2x(x, fmt: int = GRAD):
     _nhwc_check(x)
     B, H2, W2, Cc = x.shape
     out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=T16, device=x.device)
-    check(_L().s2s_sumpool2x(ptr(x), ptr(out), B, H2 // 2, W2 // 2, Cc, fmt, stream_ptr()), "sumpool2x")
+    with _Prof("sumpool2x", 0.0, 2.0 * x.numel() + 2.0 * out.numel()):
+        check(_L().s2s_sumpool2x(ptr(x), ptr(out), B, H2 // 2, W2 // 2, Cc, fmt, stream_ptr()), "sumpool2x")
     return out
 
 
@@ -265,21 +270,24 @@ def zero_insert2x(x):
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=T16, device=x.device)
-    check(_L().s2s_zero_insert2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "zero_insert2x")
+    with _Prof("zero_insert2x", 0.0, 2.0 * x.numel() + 2.0 * out.numel()):
+        check(_L().s2s_zero_insert2x(ptr(x), ptr(out), B, H, W, Cc, stream_ptr()), "zero_insert2x")
     return out
 
 
 def channel_sum(x, out, fmt: int = GRAD):
     _nhwc_check(x)
     npix = x.shape[0] * x.shape[1] * x.shape[2]
-    check(_L().s2s_channel_sum(ptr(x), npix, x.shape[3], ptr(out), fmt, stream_ptr()), "channel_sum")
+    with _Prof("channel_sum", 0.0, 2.0 * x.numel()):
+        check(_L().s2s_channel_sum(ptr(x), npix, x.shape[3], ptr(out), fmt, stream_ptr()), "channel_sum")
 
 
 def fm_loss(v, x0, x1, want_grad: bool):
     assert v.dtype == torch.float32 and v.is_contiguous() and x0.is_contiguous() and x1.is_contiguous()
     loss = torch.zeros((), dtype=torch.float32, device=v.device)
     dv = torch.empty_like(v) if want_grad else None
-    check(_L().s2s_fm_loss(ptr(v), ptr(x0), ptr(x1), v.numel(), ptr(loss), ptr(dv), stream_ptr()), "fm_loss")
+    with _Prof("fm_loss", 0.0, (12.0 + (4.0 if want_grad else 0.0)) * v.numel()):
+        check(_L().s2s_fm_loss(ptr(v), ptr(x0), ptr(x1), v.numel(), ptr(loss), ptr(dv), stream_ptr()), "fm_loss")
     return loss, dv
 
 
@@ -305,5 +313,6 @@ def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
         return x
     assert x.is_cuda and x.dtype == T16 and x.is_contiguous()
     out = torch.empty_like(x)
-    check(_L().s2s_convert16(ptr(x), ptr(out), x.numel(), in_fmt, out_fmt, stream_ptr()), "convert16")
+    with _Prof("convert16", 0.0, 4.0 * x.numel()):
+        check(_L().s2s_convert16(ptr(x), ptr(out), x.numel(), in_fmt, out_fmt, stream_ptr()), "convert16")
     return out
