@@ -89,7 +89,8 @@ def _dist_setup(n_gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return rank, world, local
 
 
@@ -189,7 +190,7 @@ def run_train(args, rank, world, local):
     ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
     launches = K.LAUNCHES[0]
     clocks = sampler.stop() if rank == 0 else None
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
 
     # ---- end to end through the public API: pinned host inputs -> device, loss back to the host, every step
     _barrier(world)
@@ -197,7 +198,7 @@ def run_train(args, rank, world, local):
     for i in range(args.steps):
         x0 = host0[i % 2].to(dev, non_blocking=True)
         x1 = host1[i % 2].to(dev, non_blocking=True)
-        loss_host = float(step(x0, x1))  # device -> host read of the step's result
+        loss_host = float(step(x0, x1).detach())  # device -> host read of the step's result
     e1.record()
     _barrier(world)
     ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
@@ -205,11 +206,13 @@ def run_train(args, rank, world, local):
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, one instrumented step
     roof = None
     prof = {}
+    # (every rank takes the step -- it contains the gradient all-reduce -- but only rank 0 records events)
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         K.PROFILE = []
-        step(x0s[0], x1s[0])
-        torch.cuda.synchronize()
+    step(x0s[0], x1s[0])
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = K.profile_summary(K.PROFILE)
         K.PROFILE = None
     _barrier(world)

@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.pt by running the REFERENCE'S OWN code (through oracle/ref_bridge.py) in the build
+container:  python -m oracle.make_golden
+
+Every fixture holds seeds + small inputs + the reference's outputs; weights are NOT stored -- they are re-drawn from
+the recorded seed by a construction that consumes the RNG exactly like the reference's (per-parameter checksums are
+stored so a drift is caught).  What executes for real: src/models/conditional_flow_matching.py,
+src/models/class_conditional_flow_matching.py, src/models/conditional_flow_matching_multitask_multiclassloss.py,
+src/models/components/shared_encoder.py, src/models/components/task_decoders.py.  What is restated (absent third-party
+packages): the torchcfm UNet / matcher and the torchdyn solver (oracle/unet.py, oracle/flow.py).
+"""
+from __future__ import annotations
+
+import functools
+import os
+
+import torch
+
+from . import flow as oflow
+from . import ref_bridge as rb
+from . import unet as ounet
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SMALL = dict(dim=[3, 64, 64], num_channels=64, num_res_blocks=1, attention_resolutions="16,8", dropout=0.0,
+             use_scale_shift_norm=True, num_heads=4, num_head_channels=32, channel_mult=[1, 2, 2, 4])
+MT = dict(features=[64, 128, 256], num_classes=5, time_emb_dim=64, size=32, batch=2)
+
+
+def checksums(module):
+    return {k: float(v.double().sum()) for k, v in module.state_dict().items() if v.dtype.is_floating_point}
+
+
+def inputs(seed, B, H, classes=0, mask_classes=0):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(x0=torch.rand(B, 3, H, H, generator=g) * 2 - 1, x1=torch.rand(B, 3, H, H, generator=g) * 2 - 1,
+             t=torch.rand(B, generator=g))
+    if classes:
+        d["y"] = torch.randint(0, classes, (B,), generator=g)
+    if mask_classes:
+        d["mask"] = torch.randint(0, mask_classes, (B, 1, H, H), generator=g).float()
+    return d
+
+
+def simple_fm(class_cond: bool):
+    name = "class_conditional_flow_matching" if class_cond else "conditional_flow_matching"
+    mod = rb.reference_module(f"src.models.{name}")
+    cls = mod.ClassConditionalFlowMatchingLitModule if class_cond else mod.ConditionalFlowMatchingLitModule
+    cfg = dict(SMALL, class_cond=True, num_classes=3) if class_cond else dict(SMALL)
+    torch.manual_seed(0)
+    net = ounet.dezero_(ounet.UNetModel(**cfg), seed=1984)
+    kw = {} if class_cond else dict(log_images=False)
+    lit = cls(net=net, flow_matcher=oflow.ConditionalFlowMatcher(0.0),
+              solver=functools.partial(oflow.NeuralODE, solver="dopri5", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+              optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None, **kw)
+    lit.eval()
+    inp = inputs(21, 2, 64, classes=3 if class_cond else 0)
+    x0, x1, t = inp["x0"], inp["x1"], inp["t"]
+    out = dict(config=cfg, weight_seed=0, dezero_seed=1984, input_seed=21, checksums=checksums(lit))
+    with torch.no_grad():
+        out["forward"] = lit(t, x0, inp["y"]) if class_cond else lit(t, x0)
+    # model_step draws t from the CPU default generator (torchcfm semantics): seed it and record the draw
+    torch.manual_seed(77)
+    t_drawn = torch.rand(2)
+    torch.manual_seed(77)
+    batch = (x0, x1, inp["y"]) if class_cond else (x0, x1)
+    loss = lit.model_step(batch)
+    lit.zero_grad()
+    loss.backward()
+    out["model_step"] = dict(rng_seed=77, t=t_drawn, loss=loss.detach(),
+                             grad_norms={k: float(p.grad.double().norm()) for k, p in lit.named_parameters()})
+    # generate(): the reference always ends up with dopri5 @ 1e-4 (functools.partial has no .solver attribute)
+    gen = lit.generate(x0[:1], 1, num_steps=2) if class_cond else lit.generate(x0[:1], num_steps=2)
+    out["generate_num_steps2"] = gen
+    torch.save(out, os.path.join(OUT, ("class_cond" if class_cond else "simple_fm") + "_small.pt"))
+    return out
+
+
+def multitask():
+    m = rb.reference_module("src.models.conditional_flow_matching_multitask_multiclassloss")
+    se = rb.reference_module("src.models.components.shared_encoder")
+    td = rb.reference_module("src.models.components.task_decoders")
+    f = MT["features"]
+    torch.manual_seed(5)
+    enc = se.SharedEncoder(3, f, True)
+    fd = td.FlowMatchingDecoder(f[-1], f[:-1][::-1], 3, MT["time_emb_dim"], True)
+    sd = td.SegmentationDecoder(f[-1], f[:-1][::-1], MT["num_classes"], True)
+    lit = m.MultiTaskFlowMatchingLitModule(
+        enc, fd, sd, oflow.ConditionalFlowMatcher(0.0), num_classes=MT["num_classes"],
+        solver=functools.partial(oflow.NeuralODE, solver="dopri5", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+        optimizer=functools.partial(torch.optim.Adam, lr=1e-4, weight_decay=1e-5), scheduler=None,
+        time_emb_dim=MT["time_emb_dim"], log_images=False)
+    inp = inputs(31, MT["batch"], MT["size"], mask_classes=MT["num_classes"])
+    x0, x1, t, mask = inp["x0"], inp["x1"], inp["t"], inp["mask"]
+    out = dict(config=MT, weight_seed=5, input_seed=31, checksums=checksums(lit))
+    lit.train()  # BatchNorm in batch-statistics mode, as in training_step
+    torch.manual_seed(78)
+    t_drawn = torch.rand(MT["batch"])
+    torch.manual_seed(78)
+    total, d = lit.model_step((x0, x1, mask))
+    lit.zero_grad()
+    total.backward()
+    out["model_step_train"] = dict(rng_seed=78, t=t_drawn, losses={k: v.detach() for k, v in d.items()},
+                                   grad_norms={k: float(p.grad.double().norm()) for k, p in lit.named_parameters()},
+                                   running_mean_inc=lit.encoder.inc.double_conv[1].running_mean.clone(),
+                                   running_var_inc=lit.encoder.inc.double_conv[1].running_var.clone(),
+                                   num_batches_tracked=int(lit.encoder.inc.double_conv[1].num_batches_tracked))
+    lit.eval()  # running statistics (after exactly one training step = two encoder passes)
+    with torch.no_grad():
+        out["forward_flow_eval"] = lit.forward_flow(t, x0)
+        out["forward_segmentation_eval"] = lit.forward_segmentation(x0)
+    img, pm = lit.generate(x0, num_steps=3)
+    out["generate_num_steps3"] = dict(image=img, mask=pm)
+    torch.save(out, os.path.join(OUT, "multitask_small.pt"))
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)  # fixed reduction order on the CPU
+    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask):
+        o = fn()
+        print({k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__) for k, v in o.items()})
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

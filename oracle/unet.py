@@ -1,6 +1,7 @@
 """ORACLE (test infrastructure only) -- fp32 PyTorch restatement of the torchcfm 1.0.7 UNet.
 
-PARITY UNPINNED: torchcfm==1.0.7 (uv.lock:4618-4619 of the reference) is not vendored under
+PARITY UNPINNED for the UNet internals (pinned only through the reference LitModule vectors in tests/golden, see
+oracle/make_golden.py): torchcfm==1.0.7 (uv.lock:4618-4619 of the reference) is not vendored under
 /root/reference and is not installable here, and the reference's tests hold no golden vector for
 this path.  This file restates the published guided-diffusion style UNet that
 torchcfm ships (`torchcfm.models.unet.UNetModel` == `UNetModelWrapper`) from its specification
