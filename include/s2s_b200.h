@@ -95,7 +95,8 @@ int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, in
 int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
                 int HW, float eps, float* coef, float* mean_rstd, void* stream);
 
-/* y[b,p,c_off+c] = dropout(silu?(x[b,p,c]*A + Bc)); y row stride ld_out channels (concat written in place).
+/* y[b,p,c_off+c] = dropout(act(x[b,p,c]*A + Bc)); y row stride ld_out channels (concat written in place).
+ * The `silu` argument of the four streaming kernels is the activation: 0 = none, 1 = SiLU, 2 = ReLU.
  * Replaces: GroupNorm32 apply + `* (1 + scale) + shift` + SiLU + Dropout (+ torch.cat) of torchcfm ResBlock. */
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
                  int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream);
@@ -133,6 +134,43 @@ int s2s_convert16(const void* in, void* out, long long n, int in_fmt, int out_fm
 
 int s2s_nchw_f32_to_nhwc16(const float* in, void* out, int B, int C, int HW, int fmt, void* stream);
 int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int fmt, void* stream);
+
+/* ---- multitask model (config M): src/models/components/shared_encoder.py, task_decoders.py ------------------------ */
+
+/* Train-mode torch.nn.BatchNorm2d folds.  The streaming passes are s2s_gn_stats / s2s_gn_apply / s2s_gn_bwd_reduce /
+ * s2s_gn_bwd_apply with act = 2 (ReLU) and G = C; these two kernels fold their per-chunk partials over the BATCH:
+ *   bn_coef    : stats [B][nchunks][C][2] -> coef [B][C][2] (A = gamma*rstd, Bc = beta - mean*A, same for every b),
+ *                mean_rstd [B][C][2], running_mean/var <- (1-momentum)*running + momentum*(mean, unbiased var) (may be NULL)
+ *   bn_bwd_coef: red [B][nchunks][C][2] -> pqr [B][C][4], dgamma += sum dz*xhat, dbeta += sum dz
+ * Replaces: nn.BatchNorm2d (+ nn.ReLU) forward / backward in DoubleConv (shared_encoder.py:14-21, task_decoders.py:14-21). */
+int s2s_bn_coef(const float* stats, int B, int nchunks, int C, int HW, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream);
+int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const float* mean_rstd, const float* gamma,
+                    float* pqr, float* dgamma, float* dbeta, void* stream);
+
+/* nn.MaxPool2d(2) (shared_encoder.py:32-34) and its backward (gradient to the first maximum in row-major order, as ATen);
+ * 16-bit NHWC, H, W = OUTPUT spatial dims. */
+int s2s_maxpool2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream);
+int s2s_maxpool2x_bwd(const void* x, const void* g, void* dx, int B, int H, int W, int C, int x_fmt, int g_fmt,
+                      void* stream);
+
+/* nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) (task_decoders.py:34) and its adjoint; 16-bit NHWC,
+ * H, W = INPUT (small) spatial dims. */
+int s2s_bilinear2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream);
+int s2s_bilinear2x_bwd(const void* g, void* din, int B, int H, int W, int C, int fmt, void* stream);
+
+/* fp32 NCHW [B, C, HW] -> 16-bit NHWC [B, HW, Cpad], zero channels beyond C (narrow image-space gradients as GEMM operands). */
+int s2s_nchw_f32_to_nhwc16_pad(const float* in, void* out, int B, int C, int Cpad, int HW, int fmt, void* stream);
+
+/* Segmentation loss pieces: softmax Dice (sums over the WHOLE batch) + cross-entropy on fp32 NCHW logits [B, C, HW]
+ * (C <= 8), int64 targets [B, HW].  sums: double[3C + 2] = I_c | P_c | T_c | sum(-log p_t) | #non-ignored, accumulated
+ * (zero it first).  bwd writes dlogits = *gscale * (w_dice * dDice + w_ce * dCE).
+ * Replaces: MulticlassDiceLoss.forward + nn.CrossEntropyLoss (conditional_flow_matching_multitask_multiclassloss.py:31-83, 231-236). */
+int s2s_seg_loss_sums(const float* logits, const long long* target, int B, int C, int HW, long long ignore_index,
+                      double* sums, void* stream);
+int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C, int HW, long long ignore_index,
+                     const double* sums, float smooth, float w_dice, float w_ce, const float* gscale, float* dlogits,
+                     void* stream);
 
 /* One parameter tensor of the fused optimizer: fp32 param / grad / exp_avg / exp_avg_sq of n elements. */
 typedef struct {

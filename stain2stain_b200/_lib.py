@@ -50,6 +50,15 @@ SIGNATURES = {
     "s2s_convert16": [_vp, _vp, _ll, _i, _i, _vp],
     "s2s_nchw_f32_to_nhwc16": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "s2s_bn_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "s2s_bn_bwd_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "s2s_maxpool2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "s2s_maxpool2x_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "s2s_bilinear2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "s2s_bilinear2x_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "s2s_nchw_f32_to_nhwc16_pad": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "s2s_seg_loss_sums": [_vp, _vp, _i, _i, _i, _ll, _vp, _vp],
+    "s2s_seg_loss_bwd": [_vp, _vp, _i, _i, _i, _ll, _vp, _f, _f, _f, _vp, _vp, _vp],
     "s2s_adam_chunk": [],
     "s2s_adam_multi": [_vp, _vp, _i, _d, _d, _d, _d, _d, _i, _d, _vp],
 }

@@ -8,6 +8,7 @@
 
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
+#include "multitask.cuh"
 #include "optim.cuh"
 
 using namespace s2s;
@@ -115,6 +116,19 @@ constexpr size_t kSmemBudget = 227 * 1024;
             __VA_ARGS__;                          \
         } else {                                  \
             constexpr bool NAME = false;          \
+            __VA_ARGS__;                          \
+        }                                         \
+    } while (0)
+#define S2S_ACT(act, NAME, ...)                   \
+    do {                                          \
+        if ((act) == 1) {                         \
+            constexpr int NAME = kActSilu;        \
+            __VA_ARGS__;                          \
+        } else if ((act) == 2) {                  \
+            constexpr int NAME = kActRelu;        \
+            __VA_ARGS__;                          \
+        } else {                                  \
+            constexpr int NAME = kActNone;        \
             __VA_ARGS__;                          \
         }                                         \
     } while (0)
@@ -363,7 +377,7 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
+    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
         (gn_apply_kernel<SILU, DROP, XF, YF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p,
             seed))))));
@@ -378,7 +392,7 @@ int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
             (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed))))));
@@ -404,7 +418,7 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_BOOL(silu != 0, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
             Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed)))))));
@@ -473,6 +487,81 @@ int s2s_nhwc16_to_nchw_f32(const void* in, float* out, int B, int C, int HW, int
     const long long total = (long long)B * C * HW;
     nhwc_bf16_to_nchw_f32_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint16_t*)in, out, B, C, HW, fmt);
     LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+    return S2S_OK;
+}
+
+int s2s_bn_coef(const float* stats, int B, int nchunks, int C, int HW, const float* gamma, const float* beta, float eps,
+                float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream) {
+    if (!stats || !gamma || !beta || !coef || !mean_rstd || C <= 0) return fail(S2S_ERR_INVALID, "bn_coef: bad arguments");
+    bn_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
+        (const float2*)stats, B * nchunks, B, C, (long long)B * HW, gamma, beta, eps, momentum, running_mean, running_var,
+        (float2*)coef, (float2*)mean_rstd);
+    LAUNCH_CHECK("bn_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const float* mean_rstd, const float* gamma,
+                    float* pqr, float* dgamma, float* dbeta, void* stream) {
+    if (!red || !mean_rstd || !gamma || !pqr || !dgamma || !dbeta) return fail(S2S_ERR_INVALID, "bn_bwd_coef: bad arguments");
+    bn_bwd_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
+        (const float2*)red, B * nchunks, B, C, (long long)B * HW, (const float2*)mean_rstd, gamma, (float4*)pqr, dgamma,
+        dbeta);
+    LAUNCH_CHECK("bn_bwd_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_maxpool2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "maxpool2x: C %% 8 != 0");
+    const long long total = (long long)B * H * W * (C / 8);
+    maxpool2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8, fmt);
+    LAUNCH_CHECK("maxpool2x_kernel");
+    return S2S_OK;
+}
+int s2s_maxpool2x_bwd(const void* x, const void* g, void* dx, int B, int H, int W, int C, int x_fmt, int g_fmt,
+                      void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "maxpool2x_bwd: C %% 8 != 0");
+    const long long total = (long long)B * H * W * (C / 8);
+    maxpool2x_bwd_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)g, (uint4*)dx,
+                                                                                   B, H, W, C / 8, x_fmt, g_fmt);
+    LAUNCH_CHECK("maxpool2x_bwd_kernel");
+    return S2S_OK;
+}
+int s2s_bilinear2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "bilinear2x: C %% 8 != 0");
+    const long long total = (long long)B * 4 * H * W * (C / 8);
+    bilinear2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8, fmt);
+    LAUNCH_CHECK("bilinear2x_kernel");
+    return S2S_OK;
+}
+int s2s_bilinear2x_bwd(const void* g, void* din, int B, int H, int W, int C, int fmt, void* stream) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "bilinear2x_bwd: C %% 8 != 0");
+    const long long total = (long long)B * H * W * (C / 8);
+    bilinear2x_bwd_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)g, (uint4*)din, B, H, W, C / 8, fmt);
+    LAUNCH_CHECK("bilinear2x_bwd_kernel");
+    return S2S_OK;
+}
+int s2s_nchw_f32_to_nhwc16_pad(const float* in, void* out, int B, int C, int Cpad, int HW, int fmt, void* stream) {
+    if (C > Cpad || Cpad % 8) return fail(S2S_ERR_INVALID, "nchw_f32_to_nhwc16_pad: need C <= Cpad, Cpad %% 8 == 0");
+    const long long total = (long long)B * Cpad * HW;
+    nchw_f32_to_nhwc16_pad_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(in, (uint16_t*)out, B, C, Cpad, HW, fmt);
+    LAUNCH_CHECK("nchw_f32_to_nhwc16_pad_kernel");
+    return S2S_OK;
+}
+
+int s2s_seg_loss_sums(const float* logits, const long long* target, int B, int C, int HW, long long ignore_index,
+                      double* sums, void* stream) {
+    if (C < 1 || C > kSegMaxC) return fail(S2S_ERR_INVALID, "seg_loss: C = %d (1..%d)", C, kSegMaxC);
+    seg_loss_sums_kernel<<<ew_grid((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(logits, target, B, C, HW, ignore_index, sums);
+    LAUNCH_CHECK("seg_loss_sums_kernel");
+    return S2S_OK;
+}
+int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C, int HW, long long ignore_index,
+                     const double* sums, float smooth, float w_dice, float w_ce, const float* gscale, float* dlogits,
+                     void* stream) {
+    if (C < 1 || C > kSegMaxC) return fail(S2S_ERR_INVALID, "seg_loss: C = %d (1..%d)", C, kSegMaxC);
+    seg_loss_bwd_kernel<<<ew_grid((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(
+        logits, target, B, C, HW, ignore_index, sums, smooth, w_dice, w_ce, gscale, dlogits);
+    LAUNCH_CHECK("seg_loss_bwd_kernel");
     return S2S_OK;
 }
 

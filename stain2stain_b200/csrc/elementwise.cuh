@@ -176,7 +176,8 @@ __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
-constexpr int kGnUnroll = 4;  // independent 16 B loads in flight per thread and per input tensor
+constexpr int kGnUnroll = 4;
+enum Act : int { kActNone = 0, kActSilu = 1, kActRelu = 2 };  // activation fused behind the normalisation  // independent 16 B loads in flight per thread and per input tensor
 
 // stats[b][chunk][c_off + c] = (sum, sumsq) over the pixels of one chunk of the sample (no atomics: deterministic).
 template <int XF>
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float2* __restrict__
 }
 
 // y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), 16-bit NHWC in / out (out row stride ld_out channels).
-template <bool kSilu, bool kDrop, int XF, int YF>
+template <int kAct, bool kDrop, int XF, int YF>
 __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
                                                                  int pix_per_cta, const float2* __restrict__ coef,
                                                                  int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const float z = fmaf(f[e], A[e], Bc[e]);
-            f[e] = kSilu ? silu_f(z) : z;
+            f[e] = kAct == kActSilu ? silu_f(z) : (kAct == kActRelu ? fmaxf(z, 0.f) : z);
         }
         if (kDrop) {
             const uint32_t m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_out >> 3), thresh);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
 // Per-thread channel coefficients of z = x*A + Bc.  fp16 activations: held as 4 half2 pairs (z and silu' are then
 // evaluated with packed half2 arithmetic and ONE tanh.approx.f16x2 per two elements -- z only feeds silu', whose
 // result multiplies a bf16 gradient, so 11 significant bits are ample); otherwise 8 + 8 fp32 values.
-template <int XF>
+template <bool kHalf>
 struct GnZCoef {
     float A[8], Bc[8];
     __device__ __forceinline__ void load(const float2* __restrict__ cf) {
@@ -367,7 +368,7 @@ struct GnZCoef {
     }
 };
 template <>
-struct GnZCoef<kFmtF16> {
+struct GnZCoef<true> {
     __half2 A[4], Bc[4];
     __device__ __forceinline__ void load(const float2* __restrict__ cf) {
 #pragma unroll
@@ -378,6 +379,9 @@ struct GnZCoef<kFmtF16> {
         }
     }
 };
+// packed-half2 evaluation of silu' is used for fp16 activations behind a SiLU; everything else keeps fp32 coefficients
+template <int kAct, int XF>
+__host__ __device__ constexpr bool gn_half_path() { return kAct == kActSilu && XF == kFmtF16; }
 __device__ __forceinline__ __half2 tanh_approx_h2(__half2 x) {
     uint32_t r;
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&x)));
@@ -390,17 +394,17 @@ __device__ __forceinline__ __half2 silu_grad_h2(__half2 z) {
     return __hmul2(s, __hfma2(z, __hsub2(one, s), one));
 }
 
-// xf = x as fp32, dz = g * keep/(1-p) * silu'(x*A + Bc) for 8 consecutive channels of one pixel
-template <bool kSilu, bool kDrop, int XF, int GF>
-__device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const GnZCoef<XF>& cf, uint32_t keep,
-                                       float keep_scale, float (&xf)[8], float (&dz)[8]) {
+// xf = x as fp32, dz = g * keep/(1-p) * act'(x*A + Bc) for 8 consecutive channels of one pixel
+template <int kAct, bool kDrop, int XF, int GF>
+__device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const GnZCoef<gn_half_path<kAct, XF>()>& cf,
+                                       uint32_t keep, float keep_scale, float (&xf)[8], float (&dz)[8]) {
     cvt8_in_t<XF>(xu, xf);
     cvt8_in_t<GF>(gu, dz);
     if (kDrop) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) dz[e] = ((keep >> e) & 1u) ? dz[e] * keep_scale : 0.f;
     }
-    if (kSilu) {
+    if constexpr (kAct == kActSilu) {
         if constexpr (XF == kFmtF16) {
             const uint32_t xs[4] = {xu.x, xu.y, xu.z, xu.w};
 #pragma unroll
@@ -414,10 +418,13 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
 #pragma unroll
             for (int e = 0; e < 8; ++e) dz[e] *= silu_grad_fast(fmaf(xf[e], cf.A[e], cf.Bc[e]));
         }
+    } else if constexpr (kAct == kActRelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dz[e] = fmaf(xf[e], cf.A[e], cf.Bc[e]) > 0.f ? dz[e] : 0.f;  // same fp32 z as forward
     }
 }
 
-template <bool kSilu, bool kDrop, int XF, int GF>
+template <int kAct, bool kDrop, int XF, int GF>
 __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                       int C, int HW, int pix_per_cta,
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    GnZCoef<XF> cf;
+    GnZCoef<gn_half_path<kAct, XF>()> cf;
     cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
     const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
     const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
         uint32_t m = 0xffu;
         if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8];
-        gn_dz8<kSilu, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
+        gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s1[e] += dz[e];
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restri
 }
 
 // Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; 16-bit NHWC.
-template <bool kSilu, bool kDrop, bool kAdd, int XF, int GF>
+template <int kAct, bool kDrop, bool kAdd, int XF, int GF>
 __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                      int C, int HW, int pix_per_cta,
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    GnZCoef<XF> cf;
+    GnZCoef<gn_half_path<kAct, XF>()> cf;
     cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
     float P[8], Q[8], R[8];
 #pragma unroll
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
         uint32_t m = 0xffu;
         if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8], o[8];
-        gn_dz8<kSilu, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
+        gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
         if (kAdd) {

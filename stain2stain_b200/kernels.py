@@ -316,3 +316,91 @@ def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
     with _Prof("convert16", 0.0, 4.0 * x.numel()):
         check(_L().s2s_convert16(ptr(x), ptr(out), x.numel(), in_fmt, out_fmt, stream_ptr()), "convert16")
     return out
+
+
+# ---- multitask model (config M) kernels ---------------------------------------------------------------------------
+ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2  # the `silu` argument of gn_apply / gn_bwd_* is the activation code
+
+
+def bn_coef(stats, gamma, beta, HW: int, eps: float, momentum: float, running_mean, running_var):
+    """Batch statistics fold of train-mode BatchNorm2d -> (coef [B,C,2], mean_rstd [B,C,2]); updates running stats."""
+    B, nchunks, C, _ = stats.shape
+    coef = torch.empty((B, C, 2), dtype=torch.float32, device=stats.device)
+    mr = torch.empty((B, C, 2), dtype=torch.float32, device=stats.device)
+    check(_L().s2s_bn_coef(ptr(stats), B, nchunks, C, HW, ptr(gamma), ptr(beta), float(eps), float(momentum),
+                           ptr(running_mean), ptr(running_var), ptr(coef), ptr(mr), stream_ptr()), "bn_coef")
+    return coef, mr
+
+
+def bn_bwd_coef(red, mr, gamma, HW: int, dgamma, dbeta):
+    B, nchunks, C, _ = red.shape
+    pqr = torch.empty((B, C, 4), dtype=torch.float32, device=red.device)
+    check(_L().s2s_bn_bwd_coef(ptr(red), B, nchunks, C, HW, ptr(mr), ptr(gamma), ptr(pqr), ptr(dgamma), ptr(dbeta),
+                               stream_ptr()), "bn_bwd_coef")
+    return pqr
+
+
+def maxpool2x(x, fmt: int = ACT):
+    _nhwc_check(x)
+    B, H2, W2, Cc = x.shape
+    assert H2 % 2 == 0 and W2 % 2 == 0
+    out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=T16, device=x.device)
+    with _Prof("maxpool2x", 0.0, 2.0 * x.numel() + 2.0 * out.numel()):
+        check(_L().s2s_maxpool2x(ptr(x), ptr(out), B, H2 // 2, W2 // 2, Cc, fmt, stream_ptr()), "maxpool2x")
+    return out
+
+
+def maxpool2x_bwd(x, g, x_fmt: int = ACT, g_fmt: int = GRAD):
+    _nhwc_check(x)
+    _nhwc_check(g)
+    B, H2, W2, Cc = x.shape
+    dx = torch.empty_like(x)
+    with _Prof("maxpool2x_bwd", 0.0, 4.0 * x.numel() + 2.0 * g.numel()):
+        check(_L().s2s_maxpool2x_bwd(ptr(x), ptr(g), ptr(dx), B, H2 // 2, W2 // 2, Cc, x_fmt, g_fmt, stream_ptr()),
+              "maxpool2x_bwd")
+    return dx
+
+
+def bilinear2x(x, fmt: int = ACT):
+    _nhwc_check(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=T16, device=x.device)
+    with _Prof("bilinear2x", 0.0, 2.0 * x.numel() + 2.0 * out.numel()):
+        check(_L().s2s_bilinear2x(ptr(x), ptr(out), B, H, W, Cc, fmt, stream_ptr()), "bilinear2x")
+    return out
+
+
+def bilinear2x_bwd(g, fmt: int = GRAD):
+    _nhwc_check(g)
+    B, H2, W2, Cc = g.shape
+    out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=T16, device=g.device)
+    with _Prof("bilinear2x_bwd", 0.0, 2.0 * g.numel() + 2.0 * out.numel()):
+        check(_L().s2s_bilinear2x_bwd(ptr(g), ptr(out), B, H2 // 2, W2 // 2, Cc, fmt, stream_ptr()), "bilinear2x_bwd")
+    return out
+
+
+def nchw_to_nhwc16_pad(x, cpad: int, fmt: int = GRAD):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, cpad), dtype=T16, device=x.device)
+    check(_L().s2s_nchw_f32_to_nhwc16_pad(ptr(x), ptr(out), B, Cc, cpad, H * W, fmt, stream_ptr()), "nchw_to_nhwc16_pad")
+    return out
+
+
+def seg_loss_sums(logits, target, ignore_index: int):
+    """-> double[3C+2]: I_c | P_c | T_c | sum(-log p_t) | #non-ignored (see include/s2s_b200.h)."""
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and target.dtype == torch.int64 and target.is_contiguous()
+    B, Cc, H, W = logits.shape
+    assert target.numel() == B * H * W
+    sums = torch.zeros(3 * Cc + 2, dtype=torch.float64, device=logits.device)
+    check(_L().s2s_seg_loss_sums(ptr(logits), ptr(target), B, Cc, H * W, int(ignore_index), ptr(sums), stream_ptr()),
+          "seg_loss_sums")
+    return sums
+
+
+def seg_loss_bwd(logits, target, ignore_index: int, sums, smooth: float, w_dice: float, w_ce: float, gscale):
+    B, Cc, H, W = logits.shape
+    d = torch.empty_like(logits)
+    check(_L().s2s_seg_loss_bwd(ptr(logits), ptr(target), B, Cc, H * W, int(ignore_index), ptr(sums), float(smooth),
+                                float(w_dice), float(w_ce), ptr(gscale), ptr(d), stream_ptr()), "seg_loss_bwd")
+    return d

@@ -361,3 +361,176 @@ def act_to_bf16(x):
 
 def bf16_to_act(x):
     return _BF16ToAct.apply(x)
+
+
+# ============================================================================================= multitask model (config M)
+class _BatchNormRelu(torch.autograd.Function):
+    """nn.BatchNorm2d (+ ReLU) on a 16-bit NHWC tensor: train mode = batch statistics (running stats updated in
+    place), eval mode = running statistics.  The streaming passes are the GroupNorm kernels with act = ReLU, G = C."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool):
+        B, H, W, C = x.shape
+        act = K.ACT_RELU if relu else K.ACT_NONE
+        if training:
+            stats = K.gn_partial_buffer(B, H * W, C, x.device)
+            K.gn_stats(x, stats, 0)
+            coef, mr = K.bn_coef(stats, gamma.detach(), beta.detach(), H * W, eps, momentum, running_mean, running_var)
+        else:
+            A = gamma.detach() * torch.rsqrt(running_var + eps)
+            coef = torch.stack([A, beta.detach() - running_mean * A], dim=1).unsqueeze(0).expand(B, C, 2).contiguous()
+            mr = None
+        y = torch.empty_like(x)
+        K.gn_apply(x, coef, y, 0, act)
+        ctx.act, ctx.training = act, training
+        ctx.save_for_backward(x, coef, mr, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.training:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not on the reference's path")
+        x, coef, mr, gamma = ctx.saved_tensors
+        g = g.contiguous()
+        B, H, W, C = x.shape
+        red = K.gn_partial_buffer(B, H * W, C, x.device)
+        K.gn_bwd_reduce(x, g, coef, mr, red, 0, ctx.act)
+        dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
+        pqr = K.bn_bwd_coef(red, mr, gamma.detach(), H * W, dgamma, dbeta)
+        dx = torch.empty_like(x)
+        K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, ctx.act)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
+    if bn.training and bn.track_running_stats:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return _BatchNormRelu.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bool(bn.training),
+                                float(momentum), float(bn.eps), relu)
+
+
+class _MaxPool2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return K.maxpool2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return K.maxpool2x_bwd(x, g.contiguous())
+
+
+def maxpool2x(x):
+    return _MaxPool2x.apply(x)
+
+
+class _Bilinear2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.bilinear2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.bilinear2x_bwd(g.contiguous())
+
+
+def bilinear2x(x):
+    return _Bilinear2x.apply(x)
+
+
+class _ChannelBiasAdd(torch.autograd.Function):
+    """x[b, :, :, c] + t[b, c] (the time conditioning of the flow decoder's bottleneck, task_decoders.py:119-125)."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        B, H, W, C = x.shape
+        coef = torch.stack([torch.ones_like(t), t], dim=2).float().contiguous()
+        y = torch.empty_like(x)
+        K.gn_apply(x, coef, y, 0, K.ACT_NONE)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        B, H, W, C = g.shape
+        stats = K.gn_partial_buffer(B, H * W, C, g.device)
+        K.gn_stats(g, stats, 0, x_fmt=K.GRAD)
+        return K.convert16(g, K.GRAD, K.GRAD), stats[..., 0].sum(dim=1)
+
+
+def channel_bias_add(x, t):
+    return _ChannelBiasAdd.apply(x, t)
+
+
+class _Head1x1(torch.autograd.Function):
+    """1x1 conv to <= 16 channels with fp32 NCHW output (the decoders' `outc`, task_decoders.py:100,170)."""
+
+    @staticmethod
+    def forward(ctx, a, w, b):
+        cout, cin = w.shape[0], w.shape[1]
+
+        def make():
+            wp = torch.zeros((16, (cin + 63) // 64 * 64), dtype=T16, device=w.device)
+            K.pack_conv_weight(w.detach(), wp)
+            return wp
+        wp = PACK_CACHE.get(("head1x1", id(w)), [w], make)
+        B, H, W, _ = a.shape
+        out = K.conv_fwd([(a, 1, 1)], wp, cout, H, W, bias=b.detach(), out_f32=True)
+        ctx.save_for_backward(a, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dv):
+        a, w = ctx.saved_tensors
+        cout, cin = w.shape[0], w.shape[1]
+        dv = dv.contiguous().float()
+        dcol = K.nchw_to_nhwc16_pad(dv, 64, K.GRAD)  # [B,H,W,64], channels >= cout are zero
+        wd = torch.zeros((cin, 64), dtype=torch.bfloat16, device=w.device)
+        wd[:, :cout] = w.detach().reshape(cout, cin).t().to(torch.bfloat16)
+        B, H, W, _ = a.shape
+        da = K.conv_fwd([(dcol, 1, 1)], wd, cin, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD)
+        dw = torch.zeros((1, cin, 64), dtype=torch.float32, device=w.device)
+        K.conv_wgrad(K.convert16(a, K.ACT, K.GRAD), dcol, 1, 1, dw)
+        d_w = dw[0, :, :cout].t().reshape(w.shape).contiguous()
+        return da, d_w, dv.sum(dim=(0, 2, 3))
+
+
+def head_conv1x1(a, w, b):
+    return _Head1x1.apply(a, w, b)
+
+
+class _SegLoss(torch.autograd.Function):
+    """dice_weight * MulticlassDice + (1 - dice_weight) * CrossEntropy, one pass for the sums, one for the gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, target, num_classes: int, ignore_index: int, dice_weight: float, smooth: float):
+        logits = logits.contiguous()
+        target = target.contiguous()
+        C = logits.shape[1]
+        assert C == num_classes
+        sums = K.seg_loss_sums(logits, target, ignore_index)
+        inter, psum, tsum = sums[:C], sums[C:2 * C], sums[2 * C:3 * C]
+        dice = 1.0 - ((2.0 * inter + smooth) / (psum + tsum + smooth)).mean()
+        ce = sums[3 * C] / sums[3 * C + 1]
+        seg = dice_weight * dice + (1.0 - dice_weight) * ce
+        ctx.cfg = (ignore_index, dice_weight, smooth)
+        ctx.save_for_backward(logits, target, sums)
+        dice, ce = dice.float(), ce.float()
+        ctx.mark_non_differentiable(dice, ce)
+        return seg.float(), dice, ce
+
+    @staticmethod
+    def backward(ctx, g_seg, _gd, _gc):
+        logits, target, sums = ctx.saved_tensors
+        ignore_index, dice_weight, smooth = ctx.cfg
+        d = K.seg_loss_bwd(logits, target, ignore_index, sums, smooth, dice_weight, 1.0 - dice_weight,
+                           g_seg.float().contiguous())
+        return d, None, None, None, None, None
+
+
+def seg_loss(logits, target, num_classes: int, ignore_index: int = -100, dice_weight: float = 0.5, smooth: float = 1.0):
+    """-> (seg_total, dice, ce); target: int64 [B,H,W]."""
+    return _SegLoss.apply(logits, target, num_classes, ignore_index, dice_weight, smooth)
