@@ -388,7 +388,16 @@ def run_reference(args, rank, world):
             "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def _claim_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are sent to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -405,14 +414,14 @@ def main():
     if args.impl == "reference":
         out = run_reference(args, rank, world)
         if out is not None:
-            print(json.dumps(out))
+            print(json.dumps(out), file=out_stream, flush=True)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
     rank, world, local = _dist_setup(args.gpus)
     out = run_train(args, rank, world, local) if args.mode == "train" else run_sample(args, rank, world, local)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

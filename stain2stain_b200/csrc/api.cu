@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -52,6 +53,15 @@ EncodeTiledFn get_encode() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     });
     return fn;
+}
+
+int mma_order() {  // S2S_MMA_ORDER=0 restores the one-accumulator-at-a-time issue order (A/B experiments)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_MMA_ORDER");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
 }
 
 int g_num_sms = 0;
@@ -253,6 +263,9 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
     // L2 feed limit (A + B = 32 KB per 256 MMA cycles); two pixel sub-tiles per CTA tile share one weight tile instead.
     const int mt = (!out_f32 && BN <= 128 && Hout >= 2 * kTileH) ? 2 : 1;
     p.mt = mt;
+    // measured (kbench, B200): alternating the two pixel sub-tiles' accumulators is +4 %; splitting N = 256 into halves
+    // is -12 % for the K-major forward operands (A is then read twice from shared memory)
+    p.mma_order = (mt == 2) ? mma_order() : 0;
     p.tiles_x = (Wout + kTileW - 1) / kTileW;
     p.tiles_y = (Hout + kTileH * mt - 1) / (kTileH * mt);
     p.n_tiles_n = npad / BN;
@@ -312,6 +325,8 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     p.tmem_cols = pow2_cols(p.BN);
     p.dw = dw; p.ldn = ldn; p.n_off = n_off;
     p.p_fmt = dy_fmt; p.q_fmt = x_fmt;
+    // measured: two independent N = 128 halves are +12 % for the MN-major wgrad operands at BN = 256, -28 % at BN = 128
+    p.mma_order = (p.BN == 256) ? mma_order() : 0;
     const size_t stage_bytes = 2 * kABytes + (size_t)(p.BN / 64) * kABytes;
     const size_t fixed = 1024 + 512;
     int stages = (int)((kSmemBudget - fixed) / stage_bytes);

@@ -49,6 +49,7 @@ struct ConvParams {
     int B, Hout, Wout, Cout;
     int tiles_x, tiles_y, n_tiles_n, total_tiles;
     int BN;          // 16, 64, 128 or 256
+    int mma_order;   // 0: one accumulator at a time; 1: alternate independent accumulators between consecutive MMAs
     int mt;          // M sub-tiles (8 x 16 pixel patches stacked in y) per CTA tile sharing one weight tile: 1 or 2
     int kblocks;     // total k-blocks per tile
     int num_stages;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // ===================================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_16b(kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
+            const uint32_t idesc_half = umma_idesc_16b(kTileM, (uint32_t)(BN / 2), 0, 0, p.a_fmt, p.w_fmt);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -181,12 +183,37 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = a_addr + a_bytes;
-                    for (int h = 0; h < MT; ++h) {
+                    if (p.mma_order == 0) {
+                        for (int h = 0; h < MT; ++h) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
+                                const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                                umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                    } else if (MT == 2) {
+                        // consecutive MMAs go to DIFFERENT accumulators (the two pixel sub-tiles)
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
                             const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                            umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
+                                umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                    } else {
+                        // one pixel tile, N split into two independent halves of BN/2 columns
+                        const uint32_t hb = (uint32_t)(BN / 2);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t db = umma_smem_desc_sw128(b_addr + j * hb * 128 + k * 32, 16, 1024);
+                                umma_bf16(d_tmem + j * hb, da, db, idesc_half, (kb | k) != 0 ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
@@ -331,6 +358,7 @@ struct WgradParams {
     uint32_t tmem_cols;
     float* dw;                  // [taps][Mtot][ldn] fp32, pre-zeroed or accumulating
     int ldn, n_off;             // row length of dw and column offset of this segment
+    int mma_order;              // 1: split N into two independent accumulator halves, alternate between them
     int p_fmt, q_fmt;           // Fmt of P (usually bf16 gradients) and Q (usually fp16 saved activations)
 };
 
@@ -424,6 +452,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     } else if (warp == 1) {
         if (lane == 0 && nk > 0) {
             const uint32_t idesc = umma_idesc_16b(128, (uint32_t)BN, 1, 1, p.p_fmt, p.q_fmt);
+            const uint32_t idesc_half = umma_idesc_16b(128, (uint32_t)(BN / 2), 1, 1, p.p_fmt, p.q_fmt);
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < nk; ++k) {
@@ -431,11 +460,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
+                if (p.mma_order == 0 || BN < 128) {
 #pragma unroll
-                for (int kk = 0; kk < kTileM / 16; ++kk) {  // 16 pixels per MMA
-                    const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
-                    const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < kTileM / 16; ++kk) {  // 16 pixels per MMA
+                        const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
+                        const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
+                        umma_bf16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                    }
+                } else {
+                    const uint32_t hb = (uint32_t)(BN / 2);  // N halves = whole 64-channel atoms of the Q tile
+#pragma unroll
+                    for (int kk = 0; kk < kTileM / 16; ++kk) {
+                        const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t db = umma_smem_desc_sw128(b_addr + j * (hb / 64) * kABytes + kk * 2048, kABytes, 1024);
+                            umma_bf16(tmem_base + j * hb, da, db, idesc_half, (k | kk) != 0 ? 1u : 0u);
+                        }
+                    }
                 }
                 umma_commit(&empty[stage]);
                 if (++stage == S) {
