@@ -64,6 +64,15 @@ int mma_order() {  // S2S_MMA_ORDER=0 restores the one-accumulator-at-a-time iss
     return v;
 }
 
+int conv_pairs() {  // S2S_CONV_2CTA=0 forces the single-CTA conv kernel
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_CONV_2CTA");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -217,6 +226,71 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
                                      "rejects mixed fp16 x bf16 operands)");
     if ((out_bf16 != nullptr) == (out_f32 != nullptr))
         return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
+    // CTA-pair kernel (tcgen05 cta_group::2): 16-bit NHWC outputs with Cout a multiple of 128
+    if (out_bf16 && !axpy_x && Cout % 128 == 0 && conv_pairs()) {
+        Conv2Params q;
+        memset(&q, 0, sizeof(q));
+        q.nseg = nsrc;
+        int kb2 = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            const s2s_conv_src& sc = srcs[s];
+            if (sc.taps != 1 && sc.taps != 9) return fail(S2S_ERR_INVALID, "conv_fwd: taps = %d", sc.taps);
+            if (sc.taps == 1 && sc.stride != 1) return fail(S2S_ERR_INVALID, "conv_fwd: strided 1x1 unsupported");
+            int rc = make_act_tmap(&q.tmA[s], sc.x, B, Hout * sc.stride, Wout * sc.stride, sc.C, sc.stride);
+            if (rc) return rc;
+            q.seg[s].taps = sc.taps;
+            q.seg[s].cblocks = (sc.C + kBlockK - 1) / kBlockK;
+            q.seg[s].stride = sc.stride;
+            q.seg[s].C = sc.C;
+            kb2 += sc.taps * q.seg[s].cblocks;
+        }
+        if (kb2 * kBlockK != Ktot)
+            return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kb2 * kBlockK);
+        const int BN2 = (Cout % 256 == 0) ? 256 : 128;
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+            cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+            cuuint32_t box[2] = {kBlockK, (cuuint32_t)(BN2 / 2)};
+            int rc = make_tmap(&q.tmW, w_packed, 2, dims, str, box);
+            if (rc) return rc;
+        }
+        int rc = make_act_tmap(&q.tmOut, out_bf16, B, Hout, Wout, Cout, 1);
+        if (rc) return rc;
+        q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
+        q.tiles_x = (Wout + kTileW - 1) / kTileW;
+        const int mt2 = (BN2 == 128 && Hout >= 2 * kTileH) ? 2 : 1;
+        q.mt = mt2;
+        q.tiles_y = (Hout + kTileH * mt2 - 1) / (kTileH * mt2);
+        q.m_tiles = B * q.tiles_x * q.tiles_y;
+        q.m_pairs = (q.m_tiles + 1) / 2;
+        q.n_tiles_n = Cout / BN2;
+        q.total_pairs = q.m_pairs * q.n_tiles_n;
+        q.BN = BN2;
+        q.kblocks = kb2;
+        q.tmem_cols = pow2_cols(2 * mt2 * BN2);
+        q.bias = bias;
+        q.residual = (const __nv_bfloat16*)residual;
+        q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
+        const size_t stage_bytes = (size_t)mt2 * kABytes + (size_t)(BN2 / 2) * kBlockK * 2;
+        const size_t fixed = 2 * kOutStageBytes + 1024 + 512;
+        int stages = (int)((kSmemBudget - fixed) / stage_bytes);
+        if (stages > 8) stages = 8;
+        q.num_stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        int clusters = num_sms() / 2;
+        if (clusters > q.total_pairs) clusters = q.total_pairs;
+        if (mt2 == 2) {
+            rc = set_smem(conv_igemm_pair_kernel<2>, smem);
+            if (rc) return rc;
+            conv_igemm_pair_kernel<2><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
+        } else {
+            rc = set_smem(conv_igemm_pair_kernel<1>, smem);
+            if (rc) return rc;
+            conv_igemm_pair_kernel<1><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
+        }
+        LAUNCH_CHECK("conv_igemm_pair_kernel");
+        return S2S_OK;
+    }
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.nseg = nsrc;

@@ -339,6 +339,269 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
 }
 
+// ====================================================================================================== CTA-pair conv
+// Same implicit GEMM, executed by CTA PAIRS (cluster of 2 = the two SMs of a TPC) with tcgen05.mma.cta_group::2:
+// one MMA covers M = 256 output pixels (CTA r owns pixel tile 2j + r, i.e. its own A operand and its own 128
+// accumulator rows in its own TMEM) x N = BN channels, and each CTA stages only HALF of the weight tile
+// (rows r*BN/2 ...).  Per CTA and k-block that is 16 KB (A) + BN/2*128 B (B half) through TMA and shared memory
+// instead of 16 KB + BN*128 B: the single-CTA kernel is bound by exactly that shared-memory / L2->SM feed
+// (73 % tensor-pipe at BN = 256, 50 % at BN = 128; profiles/r01_ncu_kernels_summary.txt).
+//
+// Protocol (leader = even CTA): both producers wait on their OWN empty[s], the leader arms its full[s] with the bytes of
+// BOTH CTAs and every TMA load of either CTA counts on the leader's full[s]; the leader's MMA thread issues the MMAs
+// and commits with a multicast arrive on empty[s] / tfull[a] of both CTAs; the epilogue warps of both CTAs drain their
+// own TMEM rows and arrive on the leader's tempty[a] (count 8).
+struct Conv2Params {
+    CUtensorMap tmA[kMaxSeg];
+    CUtensorMap tmW;     // box {64 k, BN/2 rows}
+    CUtensorMap tmOut;
+    ConvSeg seg[kMaxSeg];
+    int nseg;
+    int B, Hout, Wout, Cout;
+    int tiles_x, tiles_y, m_tiles, m_pairs, n_tiles_n, total_pairs;
+    int BN, kblocks, num_stages;
+    int mt;  // pixel sub-tiles (8 x 16, stacked in y) per CTA sharing one weight half-tile: 1 or 2
+    uint32_t tmem_cols;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    int a_fmt, w_fmt, out_fmt, res_fmt;
+};
+
+template <int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+    conv_igemm_pair_kernel(const __grid_constant__ Conv2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN, HB = p.BN / 2;
+    constexpr uint32_t a_bytes = (uint32_t)MT * kABytes;
+    const uint32_t b_bytes = (uint32_t)HB * kBlockK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const int S = p.num_stages;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    uint8_t* ring = smem;
+    uint8_t* out_stage = smem + (size_t)S * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 2 * kOutStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+        tma_prefetch_desc(&p.tmW);
+        tma_prefetch_desc(&p.tmOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);   // the leader's own arrive.expect_tx (the peer's copy is never used)
+            mbar_init(&empty[i], 1);  // one multicast tcgen05.commit per use
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(tmem_ptr, p.tmem_cols);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto decode = [&](int pair, int& b, int& ty, int& tx, int& nt, bool& valid) {
+        nt = pair % p.n_tiles_n;
+        int m = (pair / p.n_tiles_n) * 2 + (int)rank;
+        valid = m < p.m_tiles;
+        tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        ty = m % p.tiles_y;
+        b = m / p.tiles_y;  // == B for the dummy tile of an odd tile count: TMA zero-fills loads and drops stores
+    };
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters) {
+                int b, ty, tx, nt;
+                bool valid;
+                decode(pair, b, ty, tx, nt, valid);
+                const int x0 = tx * kTileW, y0 = ty * kTileH * MT, n0 = nt * BN + (int)rank * HB;
+                int kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    for (int tap = 0; tap < sg.taps; ++tap) {
+                        int cx, cy, cp = 0, coff = 0;
+                        if (sg.taps == 1) {
+                            cx = x0;
+                            cy = y0;
+                        } else if (sg.stride == 1) {
+                            cx = x0 + (tap % 3) - 1;
+                            cy = y0 + (tap / 3) - 1;
+                        } else {
+                            const int dx = tap % 3, dy = tap / 3;
+                            cx = x0 + (dx == 0 ? -1 : 0);
+                            cy = y0 + (dy == 0 ? -1 : 0);
+                            cp = (dy == 1) ? 0 : 1;
+                            coff = ((dx == 1) ? 0 : 1) * sg.C;
+                        }
+                        for (int cb = 0; cb < sg.cblocks; ++cb, ++kb) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
+                            uint8_t* b_dst = a_dst + a_bytes;
+                            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
+#pragma unroll
+                            for (int h = 0; h < MT; ++h)
+                                tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp,
+                                                 cy + h * kTileH, b);
+                            tma_load_2d_2cta(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                            if (++stage == S) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_16b(2 * kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);  // both CTAs' epilogues drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+#pragma unroll
+                        for (int h = 0; h < MT; ++h) {  // consecutive MMAs alternate between the sub-tiles' accumulators
+                            const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
+                            umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit_2cta(&empty[stage], 0x3);  // frees the slot in BOTH CTAs
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_2cta(&tfull[as], 0x3);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (both CTAs, own 128 rows)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 128;
+        int it = 0;
+        int ob = 0;
+        const int nchunks = BN / 64;
+        for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters, ++it) {
+            int b, ty, tx, nt;
+            bool valid;
+            decode(pair, b, ty, tx, nt, valid);
+            const int x0 = tx * kTileW, y0 = ty * kTileH * MT, n0 = nt * BN;
+            const int px = x0 + row % kTileW;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            for (int h = 0; h < MT; ++h) {
+                const int ys = y0 + h * kTileH;
+                const int py = ys + row / kTileW;
+                const bool in_img = valid && (py < p.Hout) && (px < p.Wout);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(t_row + ch * 64, v0);
+                    tmem_ld_32x32(t_row + ch * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (h == MT - 1 && ch == nchunks - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tempty[as]);
+                    }
+                    const int nbase = n0 + ch * 64;
+                    uint32_t packed[32];
+                    const uint4* res = nullptr;
+                    if (p.residual && in_img)
+                        res = reinterpret_cast<const uint4*>(p.residual +
+                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = j * 8 + e;
+                            f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                            if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                        }
+                        if (res) {
+                            const uint4 r = __ldg(res + j);
+                            float2 t;
+                            t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                            t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                            t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                            t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
+                        }
+                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
+                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
+                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
+                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
+                    }
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int sw = j ^ (row & 7);
+                        *reinterpret_cast<uint4*>(dst + sw * 16) =
+                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (et == 0) {
+                        tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, ys, b);
+                        tma_store_commit();
+                    }
+                    ob ^= 1;
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA exits (or frees TMEM) while its partner may still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    }
+}
+
 // ====================================================================================================== wgrad
 //   dW[tap][m][n] += sum_{pixels in this CTA's slice} P[pixel, m] * Q[pixel (+tap shift), n]
 // P = the tensor indexing the GEMM M dimension (dY for a conv weight gradient), Q = the tensor indexing N (the conv
