@@ -97,9 +97,11 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
 
 /* y[b,p,c_off+c] = dropout(act(x[b,p,c]*A + Bc)); y row stride ld_out channels (concat written in place).
  * The `silu` argument of the four streaming kernels is the activation: 0 = none, 1 = SiLU, 2 = ReLU.
- * Replaces: GroupNorm32 apply + `* (1 + scale) + shift` + SiLU + Dropout (+ torch.cat) of torchcfm ResBlock. */
-int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
-                 int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream);
+ * Replaces: GroupNorm32 apply + `* (1 + scale) + shift` + SiLU + Dropout (+ torch.cat) of torchcfm ResBlock.
+ * y2_bf16 (may be NULL): the same values additionally stored as bf16 with the same geometry -- the weight-gradient
+ * GEMM operand of the consuming conv (one MMA cannot mix fp16 x bf16), for +2 B/element instead of a conversion pass. */
+int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
+                 int ld_out, int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream);
 
 /* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g).
  *   reduce: red_part[b][chunk][c_off+c] = (sum dz, sum dz*xhat) over the chunk   (fp32 [B][s2s_gn_chunks][Ctot][2])

@@ -37,7 +37,7 @@ SIGNATURES = {
     "s2s_patch27_pack": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "s2s_gn_stats": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp],
     "s2s_gn_coef": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
-    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _f, _u64, _i, _i, _vp],
+    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _i, _i, _vp],
     "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _i, _i, _vp],
     "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "s2s_gn_chunks": [_i, _i],

@@ -459,17 +459,17 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
     return S2S_OK;
 }
 
-int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, int ld_out,
-                 int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream) {
+int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
+                 int ld_out, int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_apply");
     if (rc) return rc;
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
-        (gn_apply_kernel<SILU, DROP, XF, YF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y, ld_out, drop_p,
-            seed))))));
+    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(y2_bf16 != nullptr, DUAL, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
+        (gn_apply_kernel<SILU, DROP, XF, YF, DUAL><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y,
+            (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed)))))));
     LAUNCH_CHECK("gn_apply_kernel");
     return S2S_OK;
 }

@@ -297,11 +297,15 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float2* __restrict__
 }
 
 // y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), 16-bit NHWC in / out (out row stride ld_out channels).
-template <int kAct, bool kDrop, int XF, int YF>
+// kDual: the same values are also written as bf16 to y2 (same geometry) -- the operand the weight-gradient GEMM of the
+// consuming conv needs (its MMA cannot mix fp16 x bf16), produced here for +2 B/element instead of a 4 B/element
+// conversion pass in backward.
+template <int kAct, bool kDrop, int XF, int YF, bool kDual>
 __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
                                                                  int pix_per_cta, const float2* __restrict__ coef,
                                                                  int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
-                                                                 int ld_out, float drop_p, unsigned long long seed) {
+                                                                 __nv_bfloat16* __restrict__ y2, int ld_out,
+                                                                 float drop_p, unsigned long long seed) {
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
     }
     const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
     __nv_bfloat16* dst = y + (size_t)b * HW * ld_out + c_off + slot * 8;
+    __nv_bfloat16* dst2 = kDual ? y2 + (size_t)b * HW * ld_out + c_off + slot * 8 : nullptr;
     const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
     const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_out >> 3) +
@@ -334,6 +339,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
             for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
         }
         stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), cvt8_out_t<YF>(f));
+        if (kDual) stg_stream(reinterpret_cast<uint4*>(dst2 + (size_t)p * ld_out), cvt8_out_t<kFmtBF16>(f));
     };
     int p = p0 + prow;
     for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {

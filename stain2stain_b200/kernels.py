@@ -212,12 +212,16 @@ def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
 
 
 def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
-             y_fmt: int = ACT):
+             y_fmt: int = ACT, y2=None):
+    """y2 (optional, same shape as y): the values additionally stored as bf16 (the consuming conv's wgrad operand)."""
     _nhwc_check(x)
     B, H, W, Cc = x.shape
-    with _Prof("gn_apply_dropout" if drop_p > 0 else "gn_apply", 0.0, 4.0 * x.numel()):  # 1 read + 1 write of 2-byte elements
-        check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), y.shape[3], int(silu),
-                                float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
+    if y2 is not None:
+        assert y2.shape == y.shape and y2.dtype == T16 and y2.is_contiguous()
+    nbytes = (4.0 + (2.0 if y2 is not None else 0.0)) * x.numel()  # 1 read + 1 (or 2) writes of 2-byte elements
+    with _Prof("gn_apply_dropout" if drop_p > 0 else "gn_apply", 0.0, nbytes):
+        check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), ptr(y2), y.shape[3],
+                                int(silu), float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
 
 
 def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,

@@ -534,3 +534,159 @@ class _SegLoss(torch.autograd.Function):
 def seg_loss(logits, target, num_classes: int, ignore_index: int = -100, dice_weight: float = 0.5, smooth: float = 1.0):
     """-> (seg_total, dice, ce); target: int64 [B,H,W]."""
     return _SegLoss.apply(logits, target, num_classes, ignore_index, dice_weight, smooth)
+
+
+# ============================================================================================= fused ResBlock
+@dataclass
+class ResBlockCfg:
+    plan1: ConvPlan                 # 3x3 conv over the normalised (concatenated) input
+    plan2: ConvPlan                 # 3x3 conv over the second normalised tensor (+ 1x1 skip segments over the raw inputs)
+    has_skip_conv: bool
+    groups: int = 32
+    eps: float = 1e-5
+
+
+def _wgrad_to(d_out, x_g, taps: int, stride: int, d_w_view, n_begin: int):
+    """d_w_view[m][n_begin + n][tap] = sum_pixels d_out[., m] * x_g[. + tap, n]   (x_g: bf16 NHWC, all its channels)."""
+    cout, cq = d_out.shape[3], x_g.shape[3]
+    dw = torch.zeros((taps, cout, cq), dtype=torch.float32, device=d_out.device)
+    K.conv_wgrad(d_out, x_g, taps, stride, dw)
+    K.unpack_wgrad(dw, d_w_view, 0, cq, n_begin, 0.0)
+
+
+class _ResBlockFn(torch.autograd.Function):
+    """One torchcfm ResBlock (GN-SiLU-conv3x3, FiLM'd GN-SiLU-dropout-conv3x3, identity / 1x1 skip) as ONE autograd node.
+
+    Compared with chaining the per-op nodes this (a) lets the normalisation kernels emit the bf16 copy the weight-
+    gradient GEMMs need next to the fp16 forward operand (no conversion pass in backward), and (b) folds the gradient
+    of the residual / skip path into the first norm's backward kernel (`add`) instead of a separate accumulation pass
+    over the block input."""
+
+    @staticmethod
+    def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, *tensors):
+        srcs = tensors[:n_src]
+        emb_act = tensors[n_src]
+        gn1w, gn1b, c1w, c1b, ew, eb, gn2w, gn2b, c2w, c2b = tensors[n_src + 1:n_src + 11]
+        skip = tensors[n_src + 11:]
+        B, H, W, _ = srcs[0].shape
+        ctot = sum(s.shape[3] for s in srcs)
+        cout = c1w.shape[0]
+        dev = srcs[0].device
+        train = any(ctx.needs_input_grad)
+        dual = train and K.ACT != K.GRAD
+        # ---- norm 1 (+SiLU) over the concatenated input
+        stats = K.gn_partial_buffer(B, H * W, ctot, dev)
+        off = 0
+        for s in srcs:
+            K.gn_stats(s, stats, off)
+            off += s.shape[3]
+        coef1, mr1 = K.gn_coef(stats, gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
+        a1 = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
+        a1g = torch.empty_like(a1) if dual else None
+        off = 0
+        for s in srcs:
+            K.gn_apply(s, coef1, a1, off, True, y2=a1g)
+            off += s.shape[3]
+        h = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach())
+        # ---- FiLM from the (already SiLU'd) embedding, norm 2 (+SiLU, dropout)
+        film = torch.addmm(eb.detach(), emb_act.detach().float(), ew.detach().t()).contiguous()
+        stats2 = K.gn_partial_buffer(B, H * W, cout, dev)
+        K.gn_stats(h, stats2, 0)
+        coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
+        a2 = torch.empty((B, H, W, cout), dtype=T16, device=dev)
+        a2g = torch.empty_like(a2) if dual else None
+        K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g)
+        # ---- conv 2 with the skip path in the same accumulator
+        if cfg.has_skip_conv:
+            sw, sb = skip
+            wp = cfg.plan2.packed_fwd([c2w, sw])
+            bias = (c2b.detach() + sb.detach()).contiguous()
+            out = K.conv_fwd([(a2, 9, 1)] + [(s, 1, 1) for s in srcs], wp, cout, H, W, bias=bias)
+        else:
+            assert n_src == 1 and ctot == cout
+            out = K.conv_fwd([(a2, 9, 1)], cfg.plan2.packed_fwd([c2w]), cout, H, W, bias=c2b.detach(), residual=srcs[0])
+        if train:
+            ctx.cfg, ctx.n_src, ctx.drop = cfg, n_src, (drop_p, seed)
+            ctx.dual = dual
+            ctx.save_for_backward(*srcs, emb_act, h, a1g if dual else a1, a2g if dual else a2, coef1, mr1, coef2, mr2,
+                                  film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, *skip[:1])
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        cfg, n_src = ctx.cfg, ctx.n_src
+        drop_p, seed = ctx.drop
+        sv = ctx.saved_tensors
+        srcs = sv[:n_src]
+        emb_act, h, a1s, a2s, coef1, mr1, coef2, mr2, film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w = sv[n_src:n_src + 16]
+        sw = sv[n_src + 16] if cfg.has_skip_conv else None
+        a1g = a1s if ctx.dual else K.convert16(a1s, K.ACT, K.GRAD)
+        a2g = a2s if ctx.dual else K.convert16(a2s, K.ACT, K.GRAD)
+        d_out = d_out.contiguous()
+        B, H, W, cout = d_out.shape
+        dev = d_out.device
+        ctot = a1g.shape[3]
+        f32 = dict(dtype=torch.float32, device=dev)
+        # ---- conv 2 (+ skip): weight / bias gradients, data gradients
+        d_c2w = torch.empty_like(c2w, dtype=torch.float32)
+        _wgrad_to(d_out, a2g, 9, 1, d_c2w.view(cout, cout, -1), 0)
+        d_b2 = torch.zeros(cout, **f32)
+        K.channel_sum(d_out, d_b2)
+        d_a2 = K.conv_fwd([(d_out, 9, 1)], cfg.plan2.packed_dgrad(0, [c2w] + ([sw] if sw is not None else [])), cout, H, W,
+                          a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD)
+        d_skip: List[torch.Tensor] = []
+        d_sw = None
+        if cfg.has_skip_conv:
+            d_sw = torch.empty_like(sw, dtype=torch.float32)
+            off = 0
+            for i, s in enumerate(srcs):
+                ci = s.shape[3]
+                _wgrad_to(d_out, K.convert16(s, K.ACT, K.GRAD), 1, 1, d_sw.view(cout, ctot, -1), off)
+                d_skip.append(K.conv_fwd([(d_out, 1, 1)], cfg.plan2.packed_dgrad(1 + i, [c2w, sw]), ci, H, W,
+                                         a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD))
+                off += ci
+        else:
+            d_skip.append(d_out)
+        # ---- norm 2 backward
+        red2 = K.gn_partial_buffer(B, H * W, cout, dev)
+        K.gn_bwd_reduce(h, d_a2, coef2, mr2, red2, 0, True, drop_p, seed)
+        d_gn2w, d_gn2b = torch.zeros(cout, **f32), torch.zeros(cout, **f32)
+        pqr2, dfilm = K.gn_bwd_coef(red2, mr2, gn2w, gn2b, film, H * W, d_gn2w, d_gn2b, True)
+        d_h = torch.empty_like(h)
+        K.gn_bwd_apply(h, d_a2, coef2, pqr2, 0, None, d_h, True, drop_p, seed)
+        # ---- FiLM linear
+        emb32 = emb_act.float()
+        d_emb = dfilm @ ew.float()
+        d_ew = dfilm.t() @ emb32
+        d_eb = dfilm.sum(dim=0)
+        # ---- conv 1
+        d_c1w = torch.empty_like(c1w, dtype=torch.float32)
+        _wgrad_to(d_h, a1g, 9, 1, d_c1w.view(cout, ctot, -1), 0)
+        d_b1 = torch.zeros(cout, **f32)
+        K.channel_sum(d_h, d_b1)
+        d_a1 = K.conv_fwd([(d_h, 9, 1)], cfg.plan1.packed_dgrad(0, [c1w]), ctot, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD,
+                          out_fmt=K.GRAD)
+        # ---- norm 1 backward; the skip-path gradient is added in the same pass
+        red1 = K.gn_partial_buffer(B, H * W, ctot, dev)
+        off = 0
+        for s in srcs:
+            K.gn_bwd_reduce(s, d_a1, coef1, mr1, red1, off, True)
+            off += s.shape[3]
+        d_gn1w, d_gn1b = torch.zeros(ctot, **f32), torch.zeros(ctot, **f32)
+        pqr1, _ = K.gn_bwd_coef(red1, mr1, gn1w, gn1b, None, H * W, d_gn1w, d_gn1b, False)
+        d_srcs = []
+        off = 0
+        for i, s in enumerate(srcs):
+            dx = torch.empty_like(s)
+            K.gn_bwd_apply(s, d_a1, coef1, pqr1, off, d_skip[i], dx, True)
+            d_srcs.append(dx)
+            off += s.shape[3]
+        grads = [None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
+                 d_gn2w, d_gn2b, d_c2w, d_b2]
+        if cfg.has_skip_conv:
+            grads += [d_sw, d_b2]
+        return tuple(grads)
+
+
+def res_block(cfg: ResBlockCfg, srcs, emb_act, params, drop_p: float, seed: int):
+    return _ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), *srcs, emb_act, *params)

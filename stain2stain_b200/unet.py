@@ -139,6 +139,7 @@ class ResBlock(TimestepBlock):
         self._plan1 = ConvPlan((Seg(0, 0, 0, channels, 9, 1),), oc)
         self._plan2 = ConvPlan((Seg(0, 0, 0, oc, 9, 1),), oc)
         self._skip_plans = {}
+        self._cfgs = {}
 
     def _plan2_skip(self, widths):
         key = tuple(widths)
@@ -153,17 +154,19 @@ class ResBlock(TimestepBlock):
     def forward(self, srcs, emb_act):
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
         gn2, conv2 = self.out_layers[0], self.out_layers[3]
-        a1 = ops.group_norm_act(srcs, gn1.weight, gn1.bias, None, silu=True)
-        h = ops.fused_conv(self._plan1, [a1], [conv1.weight], [conv1.bias])
-        film = F.linear(emb_act, self.emb_layers[1].weight, self.emb_layers[1].bias)
+        lin = self.emb_layers[1]
         p = self.dropout if (self.training and self.dropout > 0) else 0.0
-        a2 = ops.group_norm_act([h], gn2.weight, gn2.bias, film, silu=True, drop_p=p,
-                                seed=_next_dropout_seed() if p > 0 else 0)
-        if isinstance(self.skip_connection, nn.Identity):
-            return ops.fused_conv(self._plan2, [a2], [conv2.weight], [conv2.bias], residual=_single(srcs))
-        plan = self._plan2_skip([s.shape[3] for s in srcs])
-        sk = self.skip_connection
-        return ops.fused_conv(plan, [a2, *srcs], [conv2.weight, sk.weight], [conv2.bias, sk.bias])
+        has_skip = not isinstance(self.skip_connection, nn.Identity)
+        widths = tuple(s.shape[3] for s in srcs)
+        cfg = self._cfgs.get(widths)
+        if cfg is None:
+            cfg = self._cfgs[widths] = ops.ResBlockCfg(self._plan1, self._plan2_skip(widths) if has_skip else self._plan2,
+                                                       has_skip)
+        params = [gn1.weight, gn1.bias, conv1.weight, conv1.bias, lin.weight, lin.bias, gn2.weight, gn2.bias,
+                  conv2.weight, conv2.bias]
+        if has_skip:
+            params += [self.skip_connection.weight, self.skip_connection.bias]
+        return ops.res_block(cfg, list(srcs), emb_act, params, p, _next_dropout_seed() if p > 0 else 0)
 
 
 class AttentionBlock(nn.Module):
