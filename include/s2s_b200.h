@@ -99,9 +99,11 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
  * The `silu` argument of the four streaming kernels is the activation: 0 = none, 1 = SiLU, 2 = ReLU.
  * Replaces: GroupNorm32 apply + `* (1 + scale) + shift` + SiLU + Dropout (+ torch.cat) of torchcfm ResBlock.
  * y2_bf16 (may be NULL): the same values additionally stored as bf16 with the same geometry -- the weight-gradient
- * GEMM operand of the consuming conv (one MMA cannot mix fp16 x bf16), for +2 B/element instead of a conversion pass. */
+ * GEMM operand of the consuming conv (one MMA cannot mix fp16 x bf16), for +2 B/element instead of a conversion pass.
+ * mask_out (may be NULL; uint8 [B*HW*ld_out/8]): the dropout keep bits, one byte per 8 channels, so that backward
+ * reads 1 bit / element instead of re-evaluating the Philox hash (mask_in of the backward kernels; NULL = re-hash). */
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
-                 int ld_out, int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream);
+                 int ld_out, int silu, float drop_p, uint64_t seed, void* mask_out, int x_fmt, int y_fmt, void* stream);
 
 /* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g).
  *   reduce: red_part[b][chunk][c_off+c] = (sum dz, sum dz*xhat) over the chunk   (fp32 [B][s2s_gn_chunks][Ctot][2])
@@ -109,13 +111,13 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
  *   apply : dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c])                      (bf16 NHWC [B,HW,C]) */
 int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
                       const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
-                      uint64_t seed, int x_fmt, int g_fmt, void* stream);
+                      uint64_t seed, const void* mask_in, int x_fmt, int g_fmt, void* stream);
 int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,
                     const float* film, int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta,
                     float* dfilm, void* stream);
 int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef, const float* pqr,
-                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed, int x_fmt,
-                     int g_fmt, void* stream);
+                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed,
+                     const void* mask_in, int x_fmt, int g_fmt, void* stream);
 
 /* nearest x2 upsample (F.interpolate(scale_factor=2, mode="nearest")), its adjoint, and zero insertion (the adjoint of
  * a stride-2 subsampling), all bf16 NHWC with C % 8 == 0.  H, W are the SMALL spatial dims. */

@@ -109,6 +109,11 @@ def bench_gn(B, iters, out):
             pqr, _ = K.gn_bwd_coef(red, mr, gamma, beta, film, HW, dgamma, dbeta, True)
             rec("gn_bwd_apply" + tag, timeit(lambda: K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, True, p, 1234), iters), 6.0 * n)
             rec("gn_bwd_apply_add" + tag, timeit(lambda: K.gn_bwd_apply(x, g, coef, pqr, 0, g, dx, True, p, 1234), iters), 8.0 * n)
+            if p:
+                mask = torch.empty((B, H, H, C // 8), dtype=torch.uint8, device=DEV)
+                rec("gn_apply_dropout_dual_mask", timeit(lambda: K.gn_apply(x, coef, y, 0, True, p, 1234, y2=dx, mask=mask), iters), 6.0 * n)
+                rec("gn_bwd_reduce_dropout_mask", timeit(lambda: K.gn_bwd_reduce(x, g, coef, mr, red, 0, True, p, 1234, mask=mask), iters), 4.0 * n)
+                rec("gn_bwd_apply_dropout_mask", timeit(lambda: K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, True, p, 1234, mask=mask), iters), 6.0 * n)
         xb = torch.empty_like(x)
         rec("convert16", timeit(lambda: K.convert16(x, K.ACT, K.GRAD), iters), 4.0 * n)
         del x, g, y, dx, xb

@@ -37,11 +37,11 @@ SIGNATURES = {
     "s2s_patch27_pack": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "s2s_gn_stats": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp],
     "s2s_gn_coef": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
-    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _i, _i, _vp],
-    "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _i, _i, _vp],
+    "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _vp, _i, _i, _vp],
+    "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _vp, _i, _i, _vp],
     "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "s2s_gn_chunks": [_i, _i],
-    "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _i, _i, _vp],
+    "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _vp, _i, _i, _vp],
     "s2s_upsample2x": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_sumpool2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "s2s_zero_insert2x": [_vp, _vp, _i, _i, _i, _i, _vp],

@@ -460,7 +460,7 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
 }
 
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
-                 int ld_out, int silu, float drop_p, uint64_t seed, int x_fmt, int y_fmt, void* stream) {
+                 int ld_out, int silu, float drop_p, uint64_t seed, void* mask_out, int x_fmt, int y_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_apply");
     if (rc) return rc;
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
@@ -469,14 +469,14 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(y2_bf16 != nullptr, DUAL, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
         (gn_apply_kernel<SILU, DROP, XF, YF, DUAL><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y,
-            (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed)))))));
+            (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed, (uint8_t*)mask_out)))))));
     LAUNCH_CHECK("gn_apply_kernel");
     return S2S_OK;
 }
 
 int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
                       const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
-                      uint64_t seed, int x_fmt, int g_fmt, void* stream) {
+                      uint64_t seed, const void* mask_in, int x_fmt, int g_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_bwd_reduce");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
@@ -484,7 +484,7 @@ int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed))))));
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in))))));
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
 }
@@ -501,8 +501,8 @@ int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, c
 }
 
 int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef, const float* pqr,
-                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed, int x_fmt,
-                     int g_fmt, void* stream) {
+                     int Ctot, int c_off, const void* add, void* dx, int silu, float drop_p, uint64_t seed,
+                     const void* mask_in, int x_fmt, int g_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_bwd_apply");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
@@ -510,7 +510,7 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
-            Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed)))))));
+            Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in)))))));
     LAUNCH_CHECK("gn_bwd_apply_kernel");
     return S2S_OK;
 }

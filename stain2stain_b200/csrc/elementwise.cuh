@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
                                                                  int pix_per_cta, const float2* __restrict__ coef,
                                                                  int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
                                                                  __nv_bfloat16* __restrict__ y2, int ld_out,
-                                                                 float drop_p, unsigned long long seed) {
+                                                                 float drop_p, unsigned long long seed,
+                                                                 uint8_t* __restrict__ mask_out) {
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
@@ -334,7 +335,9 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
             f[e] = kAct == kActSilu ? silu_f(z) : (kAct == kActRelu ? fmaxf(z, 0.f) : z);
         }
         if (kDrop) {
-            const uint32_t m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_out >> 3), thresh);
+            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_out >> 3);
+            const uint32_t m = dropout_keep8(seed, e8, thresh);
+            if (mask_out != nullptr) mask_out[e8] = (uint8_t)m;  // 1 bit / element: backward reads it instead of re-hashing
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
         }
@@ -437,7 +440,8 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
                                                                       const float2* __restrict__ coef,
                                                                       const float2* __restrict__ mean_rstd, int G,
                                                                       int Ctot, int c_off, float2* __restrict__ red_out,
-                                                                      float drop_p, unsigned long long seed) {
+                                                                      float drop_p, unsigned long long seed,
+                                                                      const uint8_t* __restrict__ mask_in) {
     constexpr int U = 2;
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
@@ -458,7 +462,10 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
     auto body = [&](const uint4& xu, const uint4& gu, int p) {
         uint32_t m = 0xffu;
-        if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+        if (kDrop) {
+            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3);
+            m = mask_in != nullptr ? (uint32_t)__ldg(mask_in + e8) : dropout_keep8(seed, e8, thresh);
+        }
         float xf[8], dz[8];
         gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
@@ -570,7 +577,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
                                                                      const float4* __restrict__ pqr, int Ctot, int c_off,
                                                                      const __nv_bfloat16* __restrict__ add,
                                                                      __nv_bfloat16* __restrict__ dx, float drop_p,
-                                                                     unsigned long long seed) {
+                                                                     unsigned long long seed,
+                                                                     const uint8_t* __restrict__ mask_in) {
     constexpr int U = 2;
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
@@ -597,7 +605,10 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
                                        (unsigned long long)((c_off >> 3) + slot);
     auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, int p) {
         uint32_t m = 0xffu;
-        if (kDrop) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+        if (kDrop) {
+            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3);
+            m = mask_in != nullptr ? (uint32_t)__ldg(mask_in + e8) : dropout_keep8(seed, e8, thresh);
+        }
         float xf[8], dz[8], o[8];
         gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll

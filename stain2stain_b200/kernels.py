@@ -212,8 +212,9 @@ def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
 
 
 def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
-             y_fmt: int = ACT, y2=None):
-    """y2 (optional, same shape as y): the values additionally stored as bf16 (the consuming conv's wgrad operand)."""
+             y_fmt: int = ACT, y2=None, mask=None):
+    """y2 (optional, same shape as y): the values additionally stored as bf16 (the consuming conv's wgrad operand).
+    mask (optional, uint8 [B,H,W,ld_out/8]): receives the dropout keep bits for the backward kernels."""
     _nhwc_check(x)
     B, H, W, Cc = x.shape
     if y2 is not None:
@@ -221,16 +222,16 @@ def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int 
     nbytes = (4.0 + (2.0 if y2 is not None else 0.0)) * x.numel()  # 1 read + 1 (or 2) writes of 2-byte elements
     with _Prof("gn_apply_dropout" if drop_p > 0 else "gn_apply", 0.0, nbytes):
         check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), ptr(y2), y.shape[3],
-                                int(silu), float(drop_p), int(seed), x_fmt, y_fmt, stream_ptr()), "gn_apply")
+                                int(silu), float(drop_p), int(seed), ptr(mask), x_fmt, y_fmt, stream_ptr()), "gn_apply")
 
 
 def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
-                  g_fmt: int = GRAD):
+                  g_fmt: int = GRAD, mask=None):
     B, H, W, Cc = x.shape
-    with _Prof("gn_bwd_reduce", 0.0, 4.0 * x.numel()):  # reads x and g
+    with _Prof("gn_bwd_reduce_dropout" if drop_p > 0 else "gn_bwd_reduce", 0.0, 4.0 * x.numel()):  # reads x and g
         check(_L().s2s_gn_bwd_reduce(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
-                                     coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), x_fmt,
-                                     g_fmt, stream_ptr()), "gn_bwd_reduce")
+                                     coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), ptr(mask),
+                                     x_fmt, g_fmt, stream_ptr()), "gn_bwd_reduce")
 
 
 def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool):
@@ -244,12 +245,13 @@ def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_df
 
 
 def gn_bwd_apply(x, g, coef, pqr, c_off: int, add, dx, silu: bool, drop_p: float = 0.0, seed: int = 0,
-                 x_fmt: int = ACT, g_fmt: int = GRAD):
+                 x_fmt: int = ACT, g_fmt: int = GRAD, mask=None):
     B, H, W, Cc = x.shape
-    with _Prof("gn_bwd_apply", 0.0, (6.0 + (2.0 if add is not None else 0.0)) * x.numel()):  # x, g (+add) in, dx out
+    nbytes = (6.0 + (2.0 if add is not None else 0.0)) * x.numel()  # x, g (+add) in, dx out
+    with _Prof("gn_bwd_apply_dropout" if drop_p > 0 else "gn_bwd_apply", 0.0, nbytes):
         check(_L().s2s_gn_bwd_apply(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(pqr), coef.shape[1],
-                                    c_off, ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), x_fmt, g_fmt,
-                                    stream_ptr()), "gn_bwd_apply")
+                                    c_off, ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), ptr(mask), x_fmt,
+                                    g_fmt, stream_ptr()), "gn_bwd_apply")
 
 
 def upsample2x(x):

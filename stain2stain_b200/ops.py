@@ -595,7 +595,8 @@ class _ResBlockFn(torch.autograd.Function):
         coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
         a2 = torch.empty((B, H, W, cout), dtype=T16, device=dev)
         a2g = torch.empty_like(a2) if dual else None
-        K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g)
+        mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if (train and drop_p > 0) else None
+        K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g, mask=mask)
         # ---- conv 2 with the skip path in the same accumulator
         if cfg.has_skip_conv:
             sw, sb = skip
@@ -608,6 +609,7 @@ class _ResBlockFn(torch.autograd.Function):
         if train:
             ctx.cfg, ctx.n_src, ctx.drop = cfg, n_src, (drop_p, seed)
             ctx.dual = dual
+            ctx.mask = mask  # uint8 keep bits of the dropout (1 bit / element), read by the two norm-backward passes
             ctx.save_for_backward(*srcs, emb_act, h, a1g if dual else a1, a2g if dual else a2, coef1, mr1, coef2, mr2,
                                   film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, *skip[:1])
         return out
@@ -649,11 +651,11 @@ class _ResBlockFn(torch.autograd.Function):
             d_skip.append(d_out)
         # ---- norm 2 backward
         red2 = K.gn_partial_buffer(B, H * W, cout, dev)
-        K.gn_bwd_reduce(h, d_a2, coef2, mr2, red2, 0, True, drop_p, seed)
+        K.gn_bwd_reduce(h, d_a2, coef2, mr2, red2, 0, True, drop_p, seed, mask=ctx.mask)
         d_gn2w, d_gn2b = torch.zeros(cout, **f32), torch.zeros(cout, **f32)
         pqr2, dfilm = K.gn_bwd_coef(red2, mr2, gn2w, gn2b, film, H * W, d_gn2w, d_gn2b, True)
         d_h = torch.empty_like(h)
-        K.gn_bwd_apply(h, d_a2, coef2, pqr2, 0, None, d_h, True, drop_p, seed)
+        K.gn_bwd_apply(h, d_a2, coef2, pqr2, 0, None, d_h, True, drop_p, seed, mask=ctx.mask)
         # ---- FiLM linear
         emb32 = emb_act.float()
         d_emb = dfilm @ ew.float()

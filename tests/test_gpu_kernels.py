@@ -354,3 +354,35 @@ def test_fused_adam_matches_torch_adam(wd):
         assert set(sa["state"][k]) == set(sb["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 3.0
         assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-8)
+
+
+def test_stored_dropout_mask_equals_rehash():
+    """The keep bits written by gn_apply (1 bit / element) are exactly the Philox mask, and the backward kernels give
+    bit-identical results whether they read the stored bits or re-evaluate the hash."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(12)
+    B, H, W, Cc = 2, 16, 24, 128
+    x = nhwc(rb(torch.randn(B, Cc, H, W, device=DEV, generator=g)))
+    gy = nhwc(rb(torch.randn(B, Cc, H, W, device=DEV, generator=g), "grad"), "grad")
+    gamma, beta = torch.ones(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    stats = k.gn_partial_buffer(B, H * W, Cc, DEV)
+    k.gn_stats(x, stats, 0)
+    coef, mr = k.gn_coef(stats, gamma, beta, None, H * W)
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    mask = torch.zeros((B, H, W, Cc // 8), dtype=torch.uint8, device=DEV)
+    k.gn_apply(x, coef, y, 0, True, 0.1, 77, y2=y2, mask=mask)
+    yf = k.to_float(y, k.ACT)
+    bits = ((mask.unsqueeze(-1) >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).reshape(B, H, W, Cc).bool()
+    assert torch.equal(bits | (yf == 0), torch.ones_like(bits)) and torch.equal(yf[~bits], torch.zeros_like(yf[~bits]))
+    assert abs(float(bits.float().mean()) - 0.9) < 0.01
+    assert float((y2.float() - yf).abs().max()) <= 2 ** -8 * float(yf.abs().max())  # bf16 copy of the same values
+    outs = []
+    for m in (None, mask):
+        red = k.gn_partial_buffer(B, H * W, Cc, DEV)
+        k.gn_bwd_reduce(x, gy, coef, mr, red, 0, True, 0.1, 77, mask=m)
+        dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+        pqr, _ = k.gn_bwd_coef(red, mr, gamma, beta, None, H * W, dg, db, False)
+        dx = torch.empty_like(x)
+        k.gn_bwd_apply(x, gy, coef, pqr, 0, None, dx, True, 0.1, 77, mask=m)
+        outs.append((red.clone(), dx.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
