@@ -326,6 +326,116 @@ def run_sample(args, rank, world, local):
     }
 
 
+def run_multitask(args, rank, world, local):
+    """configs[4]: multitask multiclass model (shared encoder + flow / segmentation decoders), 512x512 tiles, train step
+    = FM sample -> encoder+flow decoder -> MSE; second encoder pass -> segmentation decoder -> Dice+CE; backward; Adam."""
+    import functools
+    from stain2stain_b200 import kernels as K
+    from stain2stain_b200 import multitask as mt
+    from stain2stain_b200.flow_matching import ConditionalFlowMatcher
+    from stain2stain_b200.neural_ode import NeuralODE
+    from stain2stain_b200.optim import FusedAdam
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, S = args.batch, 512
+    torch.manual_seed(1984)
+    f = [64, 128, 256, 512, 1024]
+    lit = mt.MultiTaskFlowMatchingLitModule(
+        mt.SharedEncoder(3, f, True), mt.FlowMatchingDecoder(1024, f[:-1][::-1], 3, 256, True),
+        mt.SegmentationDecoder(1024, f[:-1][::-1], 5, True), ConditionalFlowMatcher(0.0), num_classes=5,
+        solver=functools.partial(NeuralODE, solver="euler"), optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=1e-5),
+        scheduler=None, log_images=False).to(dev)
+    lit.train()
+
+    class Step(torch.nn.Module):
+        def __init__(self, lit):
+            super().__init__()
+            self.lit = lit
+
+        def forward(self, x0, x1, m):
+            return self.lit.training_step((x0, x1, m), 0)
+    step_mod = Step(lit)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True)
+    opt = lit.configure_optimizers()["optimizer"]
+    g = torch.Generator(device=dev).manual_seed(1984 + rank)
+    sets = [(torch.rand(B, 3, S, S, device=dev, generator=g) * 2 - 1, torch.rand(B, 3, S, S, device=dev, generator=g) * 2 - 1,
+             torch.randint(0, 5, (B, 1, S, S), device=dev, generator=g).float()) for _ in range(2)]
+    hosts = [tuple(t.cpu().pin_memory() for t in s) for s in sets]
+
+    def step(x0, x1, m):
+        opt.zero_grad(set_to_none=True)
+        loss = step_mod(x0, x1, m)
+        loss.backward()
+        opt.step()
+        return loss
+    for i in range(args.warmup):
+        step(*sets[i % 2])
+    _barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.LAUNCHES[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*sets[i % 2])
+    e1.record()
+    _barrier(world)
+    ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = K.LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    _barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        loss_host = float(step(*(t.to(dev, non_blocking=True) for t in hosts[i % 2])).detach())
+    e1.record()
+    _barrier(world)
+    ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    torch.cuda.synchronize()
+    if rank == 0:
+        K.PROFILE = []
+    step(*sets[0])
+    torch.cuda.synchronize()
+    prof = {}
+    if rank == 0:
+        prof = K.profile_summary(K.PROFILE)
+        K.PROFILE = None
+    _barrier(world)
+    tiles = B * world * args.steps
+    pk = _peaks()
+    step_ms = ms / args.steps
+    flop_tile = 2674e9  # SURVEY 8(d): config M at 512^2, fwd_flow + fwd_seg + backward
+    out = {"metric": "512x512 tiles/s, multitask (flow + segmentation) train step", "value": tiles / (ms / 1e3),
+           "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f16 forward / bf16 backward operands, fp32 accumulate",
+           "data": "synthetic U(-1,1) 3x512x512 tile pairs + 5-class masks, default-init config-M model, seed 1984",
+           "config": {"workload": "configs[4]: multi-task multi-class-loss model at 512x512 tiles", "per_gpu_batch": B,
+                      "params": sum(p.numel() for p in lit.parameters()), "parallelism": f"dp{world}"},
+           "loss": float(loss.detach()), "gpu_launches": launches,
+           "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "loss": loss_host,
+                   "h2d_bytes_per_step": B * S * S * 4 * 7, "d2h_bytes_per_step": 4},
+           "model_flops_utilisation": (flop_tile * B / (step_ms / 1e3)) / 1e12 / pk["tf"], "clocks": clocks,
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}
+    kern = {}
+    for name, d in prof.items():
+        e = {"launches": d["launches"], "ms": round(d["ms"], 3)}
+        if d["flops"]:
+            e["tflops"] = d["flops"] / (d["ms"] / 1e3) / 1e12
+            e["frac_tensor_peak"] = e["tflops"] / pk["tf"]
+        if d["bytes"]:
+            e["gbs"] = d["bytes"] / (d["ms"] / 1e3) / 1e9
+            e["frac_hbm_peak"] = e["gbs"] / pk["hbm"]
+        kern[name] = e
+    out["kernels"] = kern
+    c = prof.get("conv_igemm")
+    out["roofline"] = None if not c else {
+        "bound": "tensor", "kernel": "conv_igemm (fwd + dgrad)", "achieved": c["flops"] / (c["ms"] / 1e3) / 1e12,
+        "peak": pk["tf"], "unit": "TFLOP/s", "frac": c["flops"] / (c["ms"] / 1e3) / 1e12 / pk["tf"], "traffic": None}
+    return out
+
+
 # --------------------------------------------------------------------------------------------------- CPU reference arm
 def _oracle_step_fn(batch=4):
     """configs[0]: `src/train.py trainer=cpu`-equivalent step on the fp32 oracle (the reference's packages are absent)."""
@@ -403,12 +513,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "sample"])
+    ap.add_argument("--mode", default="train", choices=["train", "sample", "multitask"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 32)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 64 if args.mode == "train" else 32
+        args.batch = {"train": 64, "sample": 32, "multitask": 16}[args.mode]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -419,7 +529,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
     rank, world, local = _dist_setup(args.gpus)
-    out = run_train(args, rank, world, local) if args.mode == "train" else run_sample(args, rank, world, local)
+    out = {"train": run_train, "sample": run_sample, "multitask": run_multitask}[args.mode](args, rank, world, local)
     if rank == 0:
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:

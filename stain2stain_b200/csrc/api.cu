@@ -73,6 +73,15 @@ int conv_pairs() {  // S2S_CONV_2CTA=0 forces the single-CTA conv kernel
     return v;
 }
 
+int wgrad_pairs() {  // S2S_WGRAD_2CTA=0 forces the single-CTA wgrad kernel
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_WGRAD_2CTA");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -376,6 +385,40 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
         return fail(S2S_ERR_INVALID, "conv_wgrad: dy and x must share one 16-bit format (convert with s2s_convert16)");
     if (Cq % 64) return fail(S2S_ERR_INVALID, "conv_wgrad: input channels must be a multiple of 64 (got %d)", Cq);
     if (ldn % 4 || n_off % 4) return fail(S2S_ERR_INVALID, "conv_wgrad: ldn / n_off must be multiples of 4");
+    if (Cm % 256 == 0 && Cq % 128 == 0 && wgrad_pairs()) {  // CTA-pair kernel: M = 256 output channels per MMA
+        Wgrad2Params q;
+        memset(&q, 0, sizeof(q));
+        int rc = make_act_tmap(&q.tmP, dy, B, Hout, Wout, Cm, 1);
+        if (rc) return rc;
+        rc = make_act_tmap(&q.tmQ, x, B, Hout * stride, Wout * stride, Cq, stride);
+        if (rc) return rc;
+        q.taps = taps; q.stride = stride; q.Cq = Cq; q.Mtot = Cm; q.Ntot = Cq;
+        q.BN = (Cq % 256 == 0) ? 256 : 128;
+        q.m_pairs = Cm / 256;
+        q.n_tiles = Cq / q.BN;
+        q.tiles_x = (Wout + kTileW - 1) / kTileW;
+        q.tiles_y = (Hout + kTileH - 1) / kTileH;
+        q.pix_tiles = B * q.tiles_x * q.tiles_y;
+        const int mn = taps * q.m_pairs * q.n_tiles;
+        int splits = (num_sms() / 2) / mn;
+        if (splits > q.pix_tiles) splits = q.pix_tiles;
+        if (splits < 1) splits = 1;
+        q.splits = splits;
+        q.tmem_cols = pow2_cols(q.BN);
+        q.dw = dw; q.ldn = ldn; q.n_off = n_off;
+        q.p_fmt = dy_fmt; q.q_fmt = x_fmt;
+        const size_t stage_bytes = 2 * kABytes + (size_t)(q.BN / 128) * kABytes;
+        const size_t fixed = 1024 + 512;
+        int stages = (int)((kSmemBudget - fixed) / stage_bytes);
+        if (stages > 6) stages = 6;
+        q.num_stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        rc = set_smem(conv_wgrad_pair_kernel, smem);
+        if (rc) return rc;
+        conv_wgrad_pair_kernel<<<2 * mn * splits, kConvThreads, smem, (cudaStream_t)stream>>>(q);
+        LAUNCH_CHECK("conv_wgrad_pair_kernel");
+        return S2S_OK;
+    }
     WgradParams p;
     memset(&p, 0, sizeof(p));
     int rc = make_act_tmap(&p.tmP, dy, B, Hout, Wout, Cm, 1);

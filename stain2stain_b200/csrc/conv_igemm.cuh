@@ -787,4 +787,172 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     }
 }
 
+// ====================================================================================================== CTA-pair wgrad
+// Weight gradient by CTA pairs (tcgen05 cta_group::2): one MMA covers M = 256 output channels (CTA r owns rows
+// m0 + r*128 ... of dW and the matching half of the dY tile) x N = BN input channels, each CTA staging only HALF of the
+// X tile.  Per CTA and pixel tile: 32 KB (dY half) + BN/2 * 256 B (X half) instead of 32 KB + BN * 256 B.
+struct Wgrad2Params {
+    CUtensorMap tmP, tmQ;
+    int taps, stride, Cq;
+    int Mtot, Ntot, BN;
+    int m_pairs, n_tiles, splits;
+    int tiles_x, tiles_y, pix_tiles;
+    int num_stages;
+    uint32_t tmem_cols;
+    float* dw;
+    int ldn, n_off;
+    int p_fmt, q_fmt;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+    conv_wgrad_pair_kernel(const __grid_constant__ Wgrad2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    const int q_atoms = BN / 128;                           // 64-channel atoms of the X half this CTA stages
+    const uint32_t a_bytes = 2 * kABytes;                   // 128 dY channels
+    const uint32_t stage_bytes = a_bytes + (uint32_t)q_atoms * kABytes;
+    const int S = p.num_stages;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+    int w = blockIdx.x >> 1;  // cluster id; tap fastest (see conv_wgrad_kernel)
+    const int tap = w % p.taps;      w /= p.taps;
+    const int mp = w % p.m_pairs;    w /= p.m_pairs;
+    const int nt = w % p.n_tiles;    w /= p.n_tiles;
+    const int split = w;
+    const int per = (p.pix_tiles + p.splits - 1) / p.splits;
+    const int kbeg = split * per;
+    const int kend = min(p.pix_tiles, kbeg + per);
+    const int nk = max(0, kend - kbeg);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmP);
+        tma_prefetch_desc(&p.tmQ);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(tmem_ptr, p.tmem_cols);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sx = 0, sy = 0, cp = 0, coff = 0;
+            if (p.taps == 9) {
+                const int dx = tap % 3, dy = tap / 3;
+                if (p.stride == 1) {
+                    sx = dx - 1;
+                    sy = dy - 1;
+                } else {
+                    sx = (dx == 0 ? -1 : 0);
+                    sy = (dy == 0 ? -1 : 0);
+                    cp = (dy == 1) ? 0 : 1;
+                    coff = ((dx == 1) ? 0 : 1) * p.Cq;
+                }
+            }
+            const int m0 = mp * 256 + (int)rank * 128;
+            const int n0 = coff + nt * BN + (int)rank * (BN / 2);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = kbeg; k < kend; ++k) {
+                int m = k;
+                const int tx = m % p.tiles_x;  m /= p.tiles_x;
+                const int ty = m % p.tiles_y;
+                const int b = m / p.tiles_y;
+                const int x0 = tx * kTileW, y0 = ty * kTileH;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+                uint8_t* b_dst = a_dst + a_bytes;
+                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
+                tma_load_5d_2cta(a_dst, &p.tmP, &full[stage], m0, x0, 0, y0, b);
+                tma_load_5d_2cta(a_dst + kABytes, &p.tmP, &full[stage], m0 + 64, x0, 0, y0, b);
+                for (int j = 0; j < q_atoms; ++j)
+                    tma_load_5d_2cta(b_dst + j * kABytes, &p.tmQ, &full[stage], n0 + j * 64, x0 + sx, cp, y0 + sy, b);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader && nk > 0) {
+            const uint32_t idesc = umma_idesc_16b(256, (uint32_t)BN, 1, 1, p.p_fmt, p.q_fmt);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < nk; ++k) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int kk = 0; kk < kTileM / 16; ++kk) {
+                    const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
+                    const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
+                    umma_bf16_2cta(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit_2cta(&empty[stage], 0x3);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit_2cta(tfull, 0x3);
+        }
+    } else if (warp >= 4 && nk > 0) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int m = mp * 256 + (int)rank * 128 + row;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* dst_row = p.dw + ((size_t)tap * p.Mtot + m) * p.ldn + p.n_off + nt * BN;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c0, v);
+            tmem_ld_wait();
+            if (m < p.Mtot) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = nt * BN + c0 + j;
+                    if (n + 3 < p.Ntot) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + j),
+                                     "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                     "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (n + e < p.Ntot) atomicAdd(dst_row + c0 + j + e, __uint_as_float(v[j + e]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    }
+}
+
 }  // namespace s2s
