@@ -82,6 +82,15 @@ int wgrad_pairs() {  // S2S_WGRAD_2CTA=0 forces the single-CTA wgrad kernel
     return v;
 }
 
+int conv_halo() {  // S2S_CONV_HALO: 0 = off, 1 = halo-tiled A operand (matrix base offset set), 2 = same without base offset
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_CONV_HALO");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -119,6 +128,15 @@ int make_act_tmap(CUtensorMap* m, const void* x, int B, int H, int W, int C, int
     cuuint64_t str[4] = {(cuuint64_t)C * s * 2, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 2 * s,
                          (cuuint64_t)H * W * C * 2};
     cuuint32_t box[5] = {64, kTileW, 1, kTileH, 1};
+    return make_tmap(m, x, 5, dims, str, box);
+}
+
+// stride-1 activation view {C, W, 1, H, B} with a custom pixel box (halo-tiled conv)
+int make_act_tmap_box(CUtensorMap* m, const void* x, int B, int H, int W, int C, int box_w, int box_h) {
+    if (C % 8) return fail(S2S_ERR_INVALID, "activation channels (%d) must be a multiple of 8", C);
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 1, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
     return make_tmap(m, x, 5, dims, str, box);
 }
 
@@ -235,6 +253,83 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
                                      "rejects mixed fp16 x bf16 operands)");
     if ((out_bf16 != nullptr) == (out_f32 != nullptr))
         return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
+    // halo-tiled CTA-pair kernel: stride-1 convs with at least one 3x3 segment
+    {
+        bool ok = out_bf16 && !axpy_x && Cout % 128 == 0 && conv_pairs() && conv_halo();
+        bool any3 = false;
+        for (int s = 0; s < nsrc && ok; ++s) {
+            ok = ok && srcs[s].stride == 1 && (srcs[s].taps == 1 || srcs[s].taps == 9);
+            any3 = any3 || srcs[s].taps == 9;
+        }
+        if (ok && any3) {
+            Conv3Params q;
+            memset(&q, 0, sizeof(q));
+            const int BN3 = (Cout % 256 == 0) ? 256 : 128;
+            const int mt3 = (BN3 == 128 && Hout >= 2 * kHaloTH) ? 2 : 1;
+            q.nseg = nsrc;
+            int kb3 = 0;
+            for (int s = 0; s < nsrc; ++s) {
+                const s2s_conv_src& sc = srcs[s];
+                int rc = sc.taps == 9 ? make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, kHaloPitch, kHaloTH * mt3 + 2)
+                                      : make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, kHaloTW, kHaloTH);
+                if (rc) return rc;
+                q.seg[s].taps = sc.taps;
+                q.seg[s].cblocks = (sc.C + kBlockK - 1) / kBlockK;
+                q.seg[s].stride = 1;
+                q.seg[s].C = sc.C;
+                q.seg_kb[s] = kb3;
+                kb3 += sc.taps * q.seg[s].cblocks;
+            }
+            if (kb3 * kBlockK != Ktot)
+                return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kb3 * kBlockK);
+            {
+                cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+                cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+                cuuint32_t box[2] = {kBlockK, (cuuint32_t)(BN3 / 2)};
+                int rc = make_tmap(&q.tmW, w_packed, 2, dims, str, box);
+                if (rc) return rc;
+            }
+            int rc = make_act_tmap_box(&q.tmOut, out_bf16, B, Hout, Wout, Cout, kHaloTW, kHaloTH);
+            if (rc) return rc;
+            q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
+            q.tiles_x = (Wout + kHaloTW - 1) / kHaloTW;
+            q.tiles_y = (Hout + kHaloTH * mt3 - 1) / (kHaloTH * mt3);
+            q.m_tiles = B * q.tiles_x * q.tiles_y;
+            q.n_tiles_n = Cout / BN3;
+            q.total_pairs = ((q.m_tiles + 1) / 2) * q.n_tiles_n;
+            q.BN = BN3;
+            q.tmem_cols = pow2_cols(2 * mt3 * BN3);
+            q.base_off_mode = conv_halo() == 1 ? 1 : 0;
+            q.bias = bias;
+            q.residual = (const __nv_bfloat16*)residual;
+            q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
+            const size_t halo_bytes = (size_t)(kHaloTH * mt3 + 2) * kHaloPitch * 128;
+            size_t a_slot = halo_bytes > (size_t)mt3 * kABytes ? halo_bytes : (size_t)mt3 * kABytes;
+            a_slot = (a_slot + 1023) / 1024 * 1024;
+            q.a_slot = (uint32_t)a_slot;
+            const size_t b_bytes = (size_t)(BN3 / 2) * kBlockK * 2;
+            const size_t fixed = 2 * kOutStageBytes + 1024 + 1024;
+            q.sa = 3;
+            int sb = (int)((kSmemBudget - fixed - (size_t)q.sa * a_slot) / b_bytes);
+            if (sb > 8) sb = 8;
+            if (sb < 2) return fail(S2S_ERR_INVALID, "conv_fwd(halo): tile does not fit in shared memory");
+            q.sb = sb;
+            const size_t smem = (size_t)q.sa * a_slot + (size_t)sb * b_bytes + fixed;
+            int clusters = num_sms() / 2;
+            if (clusters > q.total_pairs) clusters = q.total_pairs;
+            if (mt3 == 2) {
+                rc = set_smem(conv_halo_pair_kernel<2>, smem);
+                if (rc) return rc;
+                conv_halo_pair_kernel<2><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
+            } else {
+                rc = set_smem(conv_halo_pair_kernel<1>, smem);
+                if (rc) return rc;
+                conv_halo_pair_kernel<1><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
+            }
+            LAUNCH_CHECK("conv_halo_pair_kernel");
+            return S2S_OK;
+        }
+    }
     // CTA-pair kernel (tcgen05 cta_group::2): 16-bit NHWC outputs with Cout a multiple of 128
     if (out_bf16 && !axpy_x && Cout % 128 == 0 && conv_pairs()) {
         Conv2Params q;

@@ -602,6 +602,296 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     }
 }
 
+// ====================================================================================================== halo-tiled CTA-pair conv
+// The kernels above re-stage the A operand once per filter tap: nine overlapping 16 KB boxes per 64-channel block.  Here
+// the pixel tile is 8 wide x 16 high, so one GEMM row group of 8 pixels is one image row segment, and the whole
+// (16+2) x (8+2) halo of the tile is fetched by ONE TMA box {64 ch, 10 w, 1, 18 h, 1} per channel block (23 KB instead
+// of 9 x 16 KB).  Its shared-memory image is [18 rows][10 px][64 ch] with the 128-byte swizzle, and the A operand of tap
+// (dy, dx) is simply a UMMA descriptor on the SAME buffer: start + ((dy*10 + dx) * 128 B), stride between 8-row groups
+// = one halo row = 1280 B, matrix base offset = (start >> 7) & 7 because the start is no longer 1024 B aligned.
+// Weights still arrive per (tap, channel block) through their own ring.  1x1 segments (skip convs) use plain boxes.
+constexpr int kHaloTW = 8, kHaloTH = 16, kHaloPitch = kHaloTW + 2;
+
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                             int base_off_mode) {
+    uint64_t d = umma_smem_desc_sw128(smem_addr, lbo_bytes, sbo_bytes);
+    if (base_off_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+    return d;
+}
+
+struct Conv3Params {
+    CUtensorMap tmA[kMaxSeg];  // 3x3 segments: halo box {64, 10, 1, 16*MT + 2, 1}; 1x1 segments: {64, 8, 1, 16, 1}
+    CUtensorMap tmW;           // box {64 k, BN/2 rows}
+    CUtensorMap tmOut;         // box {64, 8, 1, 16, 1}
+    ConvSeg seg[kMaxSeg];
+    int seg_kb[kMaxSeg];       // first k-block of each segment in the packed weight
+    int nseg;
+    int B, Hout, Wout, Cout;
+    int tiles_x, tiles_y, m_tiles, n_tiles_n, total_pairs;
+    int BN, sa, sb;            // A / B ring depths
+    uint32_t a_slot, tmem_cols;
+    int base_off_mode;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    int a_fmt, w_fmt, out_fmt, res_fmt;
+};
+
+template <int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+    conv_halo_pair_kernel(const __grid_constant__ Conv3Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN, HB = p.BN / 2;
+    const uint32_t b_bytes = (uint32_t)HB * kBlockK * 2;
+    constexpr uint32_t halo_bytes = (uint32_t)(kHaloTH * MT + 2) * kHaloPitch * 128;
+    const int SA = p.sa, SB = p.sb;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    uint8_t* ringA = smem;
+    uint8_t* ringB = ringA + (size_t)SA * p.a_slot;
+    uint8_t* out_stage = ringB + (size_t)SB * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 2 * kOutStageBytes);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + SA;
+    uint64_t* fullB = emptyA + SA;
+    uint64_t* emptyB = fullB + SB;
+    uint64_t* tfull = emptyB + SB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+        tma_prefetch_desc(&p.tmW);
+        tma_prefetch_desc(&p.tmOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(&fullB[i], 1);
+            mbar_init(&emptyB[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(tmem_ptr, p.tmem_cols);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto decode = [&](int pair, int& b, int& ty, int& tx, int& nt, bool& valid) {
+        nt = pair % p.n_tiles_n;
+        int m = (pair / p.n_tiles_n) * 2 + (int)rank;
+        valid = m < p.m_tiles;
+        tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        ty = m % p.tiles_y;
+        b = m / p.tiles_y;
+    };
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            int ia = 0, ib = 0;
+            uint32_t pha = 0, phb = 0;
+            for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters) {
+                int b, ty, tx, nt;
+                bool valid;
+                decode(pair, b, ty, tx, nt, valid);
+                const int x0 = tx * kHaloTW, y0 = ty * kHaloTH * MT, n0 = nt * BN + (int)rank * HB;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    for (int cb = 0; cb < sg.cblocks; ++cb) {
+                        mbar_wait(&emptyA[ia], pha ^ 1);
+                        uint8_t* a_dst = ringA + (size_t)ia * p.a_slot;
+                        if (sg.taps == 9) {
+                            if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * halo_bytes);
+                            tma_load_5d_2cta(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
+                        } else {
+                            if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * MT * kABytes);
+#pragma unroll
+                            for (int h = 0; h < MT; ++h)
+                                tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0, 0,
+                                                 y0 + h * kHaloTH, b);
+                        }
+                        if (++ia == SA) {
+                            ia = 0;
+                            pha ^= 1;
+                        }
+                        for (int tap = 0; tap < sg.taps; ++tap) {
+                            mbar_wait(&emptyB[ib], phb ^ 1);
+                            if (leader) mbar_arrive_expect_tx(&fullB[ib], 2 * b_bytes);
+                            tma_load_2d_2cta(ringB + (size_t)ib * b_bytes, &p.tmW, &fullB[ib],
+                                             (p.seg_kb[s] + tap * sg.cblocks + cb) * kBlockK, n0);
+                            if (++ib == SB) {
+                                ib = 0;
+                                phb ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_16b(2 * kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
+            int ia = 0, ib = 0;
+            uint32_t pha = 0, phb = 0;
+            int it = 0;
+            for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
+                uint32_t acc = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    for (int cb = 0; cb < sg.cblocks; ++cb) {
+                        mbar_wait(&fullA[ia], pha);
+                        const uint32_t a_base = smem_u32(ringA + (size_t)ia * p.a_slot);
+                        for (int tap = 0; tap < sg.taps; ++tap) {
+                            mbar_wait(&fullB[ib], phb);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(ringB + (size_t)ib * b_bytes);
+                            const uint32_t tap_off =
+                                sg.taps == 9 ? (uint32_t)(((tap / 3) * kHaloPitch + (tap % 3)) * 128) : 0u;
+                            const uint32_t a_sbo = sg.taps == 9 ? (uint32_t)(kHaloPitch * 128) : 1024u;
+                            const uint32_t a_sub = sg.taps == 9 ? (uint32_t)(kHaloTH * kHaloPitch * 128) : (uint32_t)kABytes;
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+#pragma unroll
+                                for (int h = 0; h < MT; ++h) {
+                                    const uint64_t da = umma_smem_desc_sw128_off(a_base + h * a_sub + tap_off + k * 32, 16,
+                                                                                 a_sbo, p.base_off_mode);
+                                    umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, acc);
+                                }
+                                acc = 1;
+                            }
+                            umma_commit_2cta(&emptyB[ib], 0x3);
+                            if (++ib == SB) {
+                                ib = 0;
+                                phb ^= 1;
+                            }
+                        }
+                        umma_commit_2cta(&emptyA[ia], 0x3);
+                        if (++ia == SA) {
+                            ia = 0;
+                            pha ^= 1;
+                        }
+                    }
+                }
+                umma_commit_2cta(&tfull[as], 0x3);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (both CTAs, own 128 rows)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 128;
+        int it = 0;
+        int ob = 0;
+        const int nchunks = BN / 64;
+        for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters, ++it) {
+            int b, ty, tx, nt;
+            bool valid;
+            decode(pair, b, ty, tx, nt, valid);
+            const int x0 = tx * kHaloTW, y0 = ty * kHaloTH * MT, n0 = nt * BN;
+            const int px = x0 + row % kHaloTW;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+                const int ys = y0 + h * kHaloTH;
+                const int py = ys + row / kHaloTW;
+                const bool in_img = valid && (py < p.Hout) && (px < p.Wout);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(t_row + ch * 64, v0);
+                    tmem_ld_32x32(t_row + ch * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (h == MT - 1 && ch == nchunks - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tempty[as]);
+                    }
+                    const int nbase = n0 + ch * 64;
+                    uint32_t packed[32];
+                    const uint4* res = nullptr;
+                    if (p.residual && in_img)
+                        res = reinterpret_cast<const uint4*>(p.residual +
+                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = j * 8 + e;
+                            f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                            if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                        }
+                        if (res) {
+                            const uint4 r = __ldg(res + j);
+                            float2 t;
+                            t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                            t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                            t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                            t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
+                        }
+                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
+                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
+                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
+                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
+                    }
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int sw = j ^ (row & 7);
+                        *reinterpret_cast<uint4*>(dst + sw * 16) =
+                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (et == 0) {
+                        tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, ys, b);
+                        tma_store_commit();
+                    }
+                    ob ^= 1;
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    }
+}
+
 // ====================================================================================================== wgrad
 //   dW[tap][m][n] += sum_{pixels in this CTA's slice} P[pixel, m] * Q[pixel (+tap shift), n]
 // P = the tensor indexing the GEMM M dimension (dY for a conv weight gradient), Q = the tensor indexing N (the conv
