@@ -57,10 +57,16 @@ int s2s_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, int c
  *   out_bf16 (NHWC, Cout % 64 == 0)  = acc + bias + residual                                  when out_bf16 != NULL
  *   out_f32  (NCHW, Cout <= 16)      = axpy_x + axpy_a * (acc + bias)   (axpy_x NULL: acc+bias) when out_f32  != NULL
  * Replaces: F.conv2d (3x3 s1/s2, 1x1), the ResBlock `skip_connection(x) + h` add, torch.cat before a conv (two srcs),
- * the head conv + Euler update `x + dt * v` of torchdyn's fixed-step solver. */
+ * the head conv + Euler update `x + dt * v` of torchdyn's fixed-step solver.
+ * stats_out (may be NULL; fp32 [B][s2s_conv_stat_tiles(Hout,Wout,Cout)][Cout][2]): per 128-pixel sub-tile (sum, sumsq)
+ * of the STORED 16-bit outputs, taken from the epilogue's staging tile -- the GroupNorm statistics of the consumer
+ * without a pass over the tensor (fold with s2s_gn_coef_parts).  Only the CTA-pair path provides them. */
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
-                 const float* axpy_x, float axpy_a, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream);
+                 const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
+                 void* stream);
+/* Sub-tiles per sample of the epilogue statistics for this output geometry; 0 = not available (use s2s_gn_stats). */
+int s2s_conv_stat_tiles(int Hout, int Wout, int Cout);
 
 /* Weight gradient of one conv segment (tcgen05, split-K over pixels, fp32 reductions):
  *   dw[tap][m][n_off + n] += sum_{b,y,x} dy[b,y,x,m] * x[b, y*stride+dy, x*stride+dx, n]
@@ -94,6 +100,12 @@ int s2s_gn_stats(const void* x, int B, int HW, int C, float* stats, int Ctot, in
  * film: fp32 [B][2C] = ResBlock emb_layers output (scale | shift) or NULL.  coef: [B][C][2], mean_rstd: [B][G][2]. */
 int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const float* film, int B, int C, int G,
                 int HW, float eps, float* coef, float* mean_rstd, void* stream);
+
+/* The same fold for partial statistics that arrive per source of a channel concat (conv epilogue statistics):
+ * stats_i: fp32 [B][nchunks][Ci][2]; stats1 may be NULL (C1 = 0). */
+int s2s_gn_coef_parts(const float* stats0, int C0, const float* stats1, int C1, int nchunks, const float* gamma,
+                      const float* beta, const float* film, int B, int G, int HW, float eps, float* coef,
+                      float* mean_rstd, void* stream);
 
 /* y[b,p,c_off+c] = dropout(act(x[b,p,c]*A + Bc)); y row stride ld_out channels (concat written in place).
  * The `silu` argument of the four streaming kernels is the activation: 0 = none, 1 = SiLU, 2 = ReLU.

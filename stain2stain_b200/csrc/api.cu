@@ -244,9 +244,28 @@ int s2s_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int ci_beg
     return S2S_OK;
 }
 
+// geometry the CTA-pair conv kernel uses for an output [*, Hout, Wout, Cout]; false = that kernel does not apply
+static bool pair_geometry(int Hout, int Wout, int Cout, int* BN, int* mt, int* tiles_x, int* tiles_y) {
+    if (Cout % 128 != 0 || !conv_pairs()) return false;
+    *BN = (Cout % 256 == 0) ? 256 : 128;
+    *mt = (*BN == 128 && Hout >= 2 * kTileH) ? 2 : 1;
+    *tiles_x = (Wout + kTileW - 1) / kTileW;
+    *tiles_y = (Hout + kTileH * *mt - 1) / (kTileH * *mt);
+    return true;
+}
+
+int s2s_conv_stat_tiles(int Hout, int Wout, int Cout) {
+    int BN, mt, tx, ty;
+    if (conv_halo() || !pair_geometry(Hout, Wout, Cout, &BN, &mt, &tx, &ty)) return 0;
+    return tx * ty * mt;
+}
+
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
-                 const float* axpy_x, float axpy_a, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream) {
+                 const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
+                 void* stream) {
+    if (stats_out && (!out_bf16 || s2s_conv_stat_tiles(Hout, Wout, Cout) == 0))
+        return fail(S2S_ERR_INVALID, "conv_fwd: epilogue statistics need the CTA-pair path (s2s_conv_stat_tiles() > 0)");
     if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
     if (a_fmt != w_fmt)
         return fail(S2S_ERR_INVALID, "conv_fwd: activations and weights must share one 16-bit format (tcgen05 kind::f16 "
@@ -350,7 +369,8 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
         }
         if (kb2 * kBlockK != Ktot)
             return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kb2 * kBlockK);
-        const int BN2 = (Cout % 256 == 0) ? 256 : 128;
+        int BN2, mt2, tiles_x2, tiles_y2;
+        pair_geometry(Hout, Wout, Cout, &BN2, &mt2, &tiles_x2, &tiles_y2);
         {
             cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
             cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
@@ -361,11 +381,12 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
         int rc = make_act_tmap(&q.tmOut, out_bf16, B, Hout, Wout, Cout, 1);
         if (rc) return rc;
         q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
-        q.tiles_x = (Wout + kTileW - 1) / kTileW;
-        const int mt2 = (BN2 == 128 && Hout >= 2 * kTileH) ? 2 : 1;
+        q.tiles_x = tiles_x2;
         q.mt = mt2;
-        q.tiles_y = (Hout + kTileH * mt2 - 1) / (kTileH * mt2);
+        q.tiles_y = tiles_y2;
         q.m_tiles = B * q.tiles_x * q.tiles_y;
+        q.stats = (float2*)stats_out;
+        q.stat_tiles = tiles_x2 * tiles_y2 * mt2;
         q.m_pairs = (q.m_tiles + 1) / 2;
         q.n_tiles_n = Cout / BN2;
         q.total_pairs = q.m_pairs * q.n_tiles_n;
@@ -376,7 +397,7 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
         q.residual = (const __nv_bfloat16*)residual;
         q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
         const size_t stage_bytes = (size_t)mt2 * kABytes + (size_t)(BN2 / 2) * kBlockK * 2;
-        const size_t fixed = 2 * kOutStageBytes + 1024 + 512;
+        const size_t fixed = 2 * kOutStageBytes + 1024 + 3072;  // + alignment slack + barriers / statistics scratch
         int stages = (int)((kSmemBudget - fixed) / stage_bytes);
         if (stages > 8) stages = 8;
         q.num_stages = stages;
@@ -594,6 +615,20 @@ int s2s_gn_coef(const float* stats, const float* gamma, const float* beta, const
     gn_coef_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const float2*)stats, s2s_gn_chunks(B, HW), gamma, beta, film,
                                                         C, G, HW, eps, (float2*)coef, (float2*)mean_rstd);
     LAUNCH_CHECK("gn_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_gn_coef_parts(const float* stats0, int C0, const float* stats1, int C1, int nchunks, const float* gamma,
+                      const float* beta, const float* film, int B, int G, int HW, float eps, float* coef,
+                      float* mean_rstd, void* stream) {
+    const int C = C0 + C1;
+    if (G > 64 || C % G || !stats0 || C0 <= 0 || (C1 > 0 && !stats1))
+        return fail(S2S_ERR_INVALID, "gn_coef_parts: G = %d, C = %d + %d unsupported", G, C0, C1);
+    if (C > 4096) return fail(S2S_ERR_INVALID, "gn_coef_parts: C = %d unsupported (<= 4096)", C);
+    gn_coef_parts_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        (const float2*)stats0, C0, (const float2*)stats1, C1, nchunks, gamma, beta, film, G, HW, eps, (float2*)coef,
+        (float2*)mean_rstd);
+    LAUNCH_CHECK("gn_coef_parts_kernel");
     return S2S_OK;
 }
 

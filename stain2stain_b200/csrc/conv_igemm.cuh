@@ -364,6 +364,9 @@ struct Conv2Params {
     uint32_t tmem_cols;
     const float* bias;
     const __nv_bfloat16* residual;
+    float2* stats;  // optional [B][stat_tiles][Cout] (sum, sumsq) of the STORED 16-bit outputs per 128-pixel sub-tile:
+                    // the GroupNorm statistics of the consumer, taken from the epilogue's staging tile (no extra pass)
+    int stat_tiles;
     int a_fmt, w_fmt, out_fmt, res_fmt;
 };
 
@@ -390,6 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     uint64_t* tfull = bars + 2 * S;
     uint64_t* tempty = bars + 2 * S + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    float2* stat_scratch = reinterpret_cast<float2*>(bars + 2 * S + 6);  // 4 warps x 64 channels x float2 (2 KB)
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
@@ -585,6 +589,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     if (et == 0) {
                         tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, ys, b);
                         tma_store_commit();
+                    }
+                    if (p.stats != nullptr) {
+                        // per-channel (sum, sumsq) over the 128 pixels of this sub-tile, read back from the staged tile (so
+                        // the statistics are those of the rounded values the consumer reads): thread = (8-channel group,
+                        // 8-row group), eight 128-bit shared loads, shuffle fold inside the warp, 2 KB scratch across warps
+                        const int cg = et & 7, rg = et >> 3;
+                        const uint8_t* tile = out_stage + ob * kOutStageBytes;
+                        const bool full_tile = (ys + kTileH <= p.Hout) && (x0 + kTileW <= p.Wout);
+                        float sm[8], sq[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sm[e] = sq[e] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rg * 8 + i;
+                            if (!full_tile && ((ys + r / kTileW >= p.Hout) || (x0 + r % kTileW >= p.Wout))) continue;
+                            const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + ((cg ^ i) << 4));
+                            float f[8];
+                            float2 t2;
+                            t2 = unpack2(u.x, p.out_fmt); f[0] = t2.x; f[1] = t2.y;
+                            t2 = unpack2(u.y, p.out_fmt); f[2] = t2.x; f[3] = t2.y;
+                            t2 = unpack2(u.z, p.out_fmt); f[4] = t2.x; f[5] = t2.y;
+                            t2 = unpack2(u.w, p.out_fmt); f[6] = t2.x; f[7] = t2.y;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                sm[e] += f[e];
+                                sq[e] = fmaf(f[e], f[e], sq[e]);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 8);
+                            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
+                            sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 16);
+                            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+                        }
+                        if (lane < 8) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) stat_scratch[q * 64 + lane * 8 + e] = make_float2(sm[e], sq[e]);
+                        }
+                        named_bar_sync(3, 128);
+                        if (et < 64 && valid) {
+                            float2 o = stat_scratch[et];
+#pragma unroll
+                            for (int wq = 1; wq < 4; ++wq) {
+                                const float2 t2 = stat_scratch[wq * 64 + et];
+                                o.x += t2.x;
+                                o.y += t2.y;
+                            }
+                            const int sub = (ty * MT + h) * p.tiles_x + tx;
+                            p.stats[((size_t)b * p.stat_tiles + sub) * p.Cout + nbase + et] = o;
+                        }
                     }
                     ob ^= 1;
                 }

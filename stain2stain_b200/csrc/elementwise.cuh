@@ -296,6 +296,68 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float2* __restrict__
     }
 }
 
+// Same fold for partial statistics that arrive per SOURCE of a channel concat (written by the producing convs'
+// epilogues): source i has its own [B][nchunks][Ci] buffer.  Channel c of the concat is channel c of source 0 for
+// c < C0, else channel c - C0 of source 1.
+__global__ void __launch_bounds__(256) gn_coef_parts_kernel(const float2* __restrict__ stats0, int C0,
+                                                            const float2* __restrict__ stats1, int C1, int nchunks,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ film, int G, int HW, float eps,
+                                                            float2* __restrict__ coef, float2* __restrict__ mean_rstd) {
+    extern __shared__ float s_tot[];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.x;
+    const int C = C0 + C1;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bool first = c < C0;
+        const int Ci = first ? C0 : C1;
+        const float2* sp = (first ? stats0 : stats1) + (size_t)b * nchunks * Ci + (first ? c : c - C0);
+        float a = 0.f, q = 0.f;
+        int k = 0;
+        for (; k + 4 <= nchunks; k += 4) {
+            const float2 t0 = sp[(size_t)(k + 0) * Ci], t1 = sp[(size_t)(k + 1) * Ci];
+            const float2 t2 = sp[(size_t)(k + 2) * Ci], t3 = sp[(size_t)(k + 3) * Ci];
+            a += t0.x; q += t0.y; a += t1.x; q += t1.y; a += t2.x; q += t2.y; a += t3.x; q += t3.y;
+        }
+        for (; k < nchunks; ++k) {
+            const float2 t = sp[(size_t)k * Ci];
+            a += t.x; q += t.y;
+        }
+        s_tot[c] = a;
+        s_tot[C + c] = q;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += s_tot[c];
+            q += s_tot[C + c];
+        }
+        const float n = (float)cpg * (float)HW;
+        const float mean = a / n;
+        const float var = fmaxf(q / n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        s_mean[g] = mean;
+        s_rstd[g] = rstd;
+        mean_rstd[(size_t)b * G + g] = make_float2(mean, rstd);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float A = s_rstd[g] * gamma[c];
+        float Bc = beta[c] - s_mean[g] * A;
+        if (film != nullptr) {
+            const float sc = 1.f + film[(size_t)b * 2 * C + c];
+            const float sh = film[(size_t)b * 2 * C + C + c];
+            A *= sc;
+            Bc = Bc * sc + sh;
+        }
+        coef[(size_t)b * C + c] = make_float2(A, Bc);
+    }
+}
+
 // y[b, p, c_off + c] = dropout( silu( x[b, p, c] * A + Bc ) ), 16-bit NHWC in / out (out row stride ld_out channels).
 // kDual: the same values are also written as bf16 to y2 (same geometry) -- the operand the weight-gradient GEMM of the
 // consuming conv needs (its MMA cannot mix fp16 x bf16), produced here for +2 B/element instead of a 4 B/element

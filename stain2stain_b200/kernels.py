@@ -108,11 +108,21 @@ def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begi
                                         int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
 
 
+EPI_STATS = os.environ.get("S2S_EPI_STATS", "1") != "0"  # GroupNorm statistics from the producing conv's epilogue
+
+
+def conv_stat_tiles(hout: int, wout: int, cout: int) -> int:
+    """Sub-tiles per sample of the conv epilogue statistics for this output geometry (0 = not available)."""
+    return int(_L().s2s_conv_stat_tiles(hout, wout, cout)) if EPI_STATS else 0
+
+
 def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tensor, cout: int, hout: int, wout: int,
              bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out_f32: bool = False,
              axpy_x: Optional[torch.Tensor] = None, axpy_a: float = 0.0, out: Optional[torch.Tensor] = None,
-             a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT):
-    """srcs: [(x NHWC 16-bit, taps, stride)].  Returns 16-bit NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32."""
+             a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT, want_stats: bool = False):
+    """srcs: [(x NHWC 16-bit, taps, stride)].  Returns 16-bit NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32.
+    want_stats: returns (out, stats) with stats = fp32 [B, tiles, cout, 2] per-sub-tile (sum, sumsq) of the stored
+    output (the consumer's GroupNorm statistics, produced by the conv epilogue) or None when that path is unavailable."""
     arr = (ConvSrc * len(srcs))()
     B = srcs[0][0].shape[0]
     for i, (x, taps, stride) in enumerate(srcs):
@@ -137,11 +147,16 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     assert w_packed.dtype == T16 and w_packed.is_contiguous() and w_packed.shape[0] >= padded_rows(cout)
     # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted)
     macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs)
+    stats = None
+    if want_stats and not out_f32:
+        nt = conv_stat_tiles(hout, wout, cout)
+        if nt > 0:
+            stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=dev)
     with _Prof("conv_igemm", 2.0 * macs):
         check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
-                                ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), a_fmt, w_fmt, out_fmt, res_fmt,
-                                stream_ptr()), "conv_fwd")
-    return out
+                                ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), ptr(stats), a_fmt, w_fmt, out_fmt,
+                                res_fmt, stream_ptr()), "conv_fwd")
+    return (out, stats) if want_stats else out
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: torch.Tensor, n_off: int = 0,
@@ -208,6 +223,19 @@ def gn_coef(stats, gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
     mr = torch.empty((B, G, 2), dtype=torch.float32, device=stats.device)
     check(_L().s2s_gn_coef(ptr(stats), ptr(gamma), ptr(beta), ptr(film), B, Cc, G, HW, eps, ptr(coef), ptr(mr),
                            stream_ptr()), "gn_coef")
+    return coef, mr
+
+
+def gn_coef_parts(parts: Sequence[torch.Tensor], gamma, beta, film, HW: int, G: int = 32, eps: float = 1e-5):
+    """gn_coef for per-source partial statistics (conv epilogue statistics); parts: 1 or 2 tensors [B, n, Ci, 2]."""
+    assert 1 <= len(parts) <= 2 and all(p.shape[1] == parts[0].shape[1] for p in parts)
+    B, n = parts[0].shape[0], parts[0].shape[1]
+    C0 = parts[0].shape[2]
+    C1 = parts[1].shape[2] if len(parts) == 2 else 0
+    coef = torch.empty((B, C0 + C1, 2), dtype=torch.float32, device=parts[0].device)
+    mr = torch.empty((B, G, 2), dtype=torch.float32, device=parts[0].device)
+    check(_L().s2s_gn_coef_parts(ptr(parts[0]), C0, ptr(parts[1]) if C1 else None, C1, n, ptr(gamma), ptr(beta),
+                                 ptr(film), B, G, HW, float(eps), ptr(coef), ptr(mr), stream_ptr()), "gn_coef_parts")
     return coef, mr
 
 

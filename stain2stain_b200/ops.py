@@ -92,9 +92,15 @@ class ConvPlan:
 
 
 # --------------------------------------------------------------------------------------------- fused convolution
+def usable_stats(src_stats) -> bool:
+    """Epilogue statistics of every source are present and cut the samples into the same number of sub-tiles."""
+    return len(src_stats) <= 2 and all(st is not None for st in src_stats) and \
+        all(st.shape[1] == src_stats[0].shape[1] for st in src_stats)
+
+
 class _FusedConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: ConvPlan, n_src: int, n_w: int, residual, *tensors):
+    def forward(ctx, plan: ConvPlan, n_src: int, n_w: int, residual, stats_box, *tensors):
         srcs = tensors[:n_src]
         weights = tensors[n_src:n_src + n_w]
         biases = [b for b in tensors[n_src + n_w:] if b is not None]
@@ -108,8 +114,10 @@ class _FusedConv(torch.autograd.Function):
             for b in biases[1:]:
                 bias = bias + b.detach()
             bias = bias.contiguous()
-        out = K.conv_fwd([(srcs[s.src], s.taps, s.stride) for s in plan.segs], wp, plan.cout, hout, wout, bias=bias,
-                         residual=residual)
+        out, st = K.conv_fwd([(srcs[s.src], s.taps, s.stride) for s in plan.segs], wp, plan.cout, hout, wout, bias=bias,
+                             residual=residual, want_stats=True)
+        if stats_box is not None:
+            stats_box.append(st)
         ctx.plan, ctx.n_src, ctx.n_w = plan, n_src, n_w
         ctx.has_res = residual is not None
         ctx.bias_present = [b is not None for b in tensors[n_src + n_w:]]
@@ -123,7 +131,8 @@ class _FusedConv(torch.autograd.Function):
         srcs, weights = saved[:n_src], saved[n_src:]
         d_out = d_out.contiguous()
         B, hout, wout, cout = d_out.shape
-        need = ctx.needs_input_grad  # (plan, n_src, n_w, residual, *tensors)
+        need = ctx.needs_input_grad  # (plan, n_src, n_w, residual, stats_box, *tensors)
+        need = need[:4] + need[5:]
         d_res = d_out if (ctx.has_res and need[3]) else None
         d_srcs: List[Optional[torch.Tensor]] = [None] * n_src
         d_ws: List[Optional[torch.Tensor]] = [None] * n_w
@@ -151,28 +160,44 @@ class _FusedConv(torch.autograd.Function):
                 d_srcs[s.src] = dx if d_srcs[s.src] is None else d_srcs[s.src] + dx
         d_biases = [d_bias if (present and n) else None
                     for present, n in zip(ctx.bias_present, need[4 + n_src + n_w:])]
-        return (None, None, None, d_res, *d_srcs, *d_ws, *d_biases)
+        return (None, None, None, d_res, None, *d_srcs, *d_ws, *d_biases)
+
+
+def _tag(out, box):
+    """Attach the conv epilogue's GroupNorm statistics to the Python tensor object that travels on (never keyed by
+    address: a freed-and-reused buffer must not inherit stale statistics)."""
+    out._s2s_stats = box[0] if box else None
+    return out
+
+
+def stats_of(t):
+    return getattr(t, "_s2s_stats", None)
 
 
 def fused_conv(plan: ConvPlan, srcs: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
                biases: Sequence[Optional[torch.Tensor]], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    return _FusedConv.apply(plan, len(srcs), len(weights), residual, *srcs, *weights, *biases)
+    box = []
+    return _tag(_FusedConv.apply(plan, len(srcs), len(weights), residual, box, *srcs, *weights, *biases), box)
 
 
 # --------------------------------------------------------------------------------------------- GroupNorm (+FiLM+SiLU+dropout, +concat)
 class _GroupNormAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, n_src: int, groups: int, eps: float, silu: bool, drop_p: float, seed: int, gamma, beta, film, *srcs):
+    def forward(ctx, n_src: int, groups: int, eps: float, silu: bool, drop_p: float, seed: int, src_stats, gamma, beta,
+                film, *srcs):
         B, H, W, _ = srcs[0].shape
         ctot = sum(s.shape[3] for s in srcs)
         dev = srcs[0].device
-        stats = K.gn_partial_buffer(B, H * W, ctot, dev)
-        off = 0
-        for s in srcs:
-            K.gn_stats(s, stats, off)
-            off += s.shape[3]
         film_c = film.detach().float().contiguous() if film is not None else None
-        coef, mr = K.gn_coef(stats, gamma.detach(), beta.detach(), film_c, H * W, groups, eps)
+        if src_stats is not None and usable_stats(src_stats):
+            coef, mr = K.gn_coef_parts(list(src_stats), gamma.detach(), beta.detach(), film_c, H * W, groups, eps)
+        else:
+            stats = K.gn_partial_buffer(B, H * W, ctot, dev)
+            off = 0
+            for s in srcs:
+                K.gn_stats(s, stats, off)
+                off += s.shape[3]
+            coef, mr = K.gn_coef(stats, gamma.detach(), beta.detach(), film_c, H * W, groups, eps)
         y = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
         off = 0
         for s in srcs:
@@ -200,20 +225,23 @@ class _GroupNormAct(torch.autograd.Function):
         dxs = []
         off = 0
         for i, s in enumerate(srcs):
-            if ctx.needs_input_grad[9 + i]:
+            if ctx.needs_input_grad[10 + i]:
                 dx = torch.empty_like(s)
                 K.gn_bwd_apply(s, g, coef, pqr, off, None, dx, silu, drop_p, seed)
                 dxs.append(dx)
             else:
                 dxs.append(None)
             off += s.shape[3]
-        return (None, None, None, None, None, None, dgamma, dbeta, dfilm, *dxs)
+        return (None, None, None, None, None, None, None, dgamma, dbeta, dfilm, *dxs)
 
 
 def group_norm_act(srcs: Sequence[torch.Tensor], gamma, beta, film=None, silu=True, drop_p=0.0, seed=0, groups=32,
                    eps=1e-5) -> torch.Tensor:
-    """GroupNorm over the channel-concatenation of `srcs`, optional FiLM `(1+scale), shift`, SiLU and dropout."""
-    return _GroupNormAct.apply(len(srcs), groups, eps, bool(silu), float(drop_p), int(seed), gamma, beta, film, *srcs)
+    """GroupNorm over the channel-concatenation of `srcs`, optional FiLM `(1+scale), shift`, SiLU and dropout.
+    Statistics come from the producing convs' epilogues when every source carries them."""
+    src_stats = tuple(stats_of(t) for t in srcs)
+    return _GroupNormAct.apply(len(srcs), groups, eps, bool(silu), float(drop_p), int(seed), src_stats, gamma, beta,
+                               film, *srcs)
 
 
 # --------------------------------------------------------------------------------------------- resampling
@@ -236,7 +264,7 @@ class _Stem(torch.autograd.Function):
     """3x3 conv on the fp32 NCHW image (optionally the FM interpolant of x0, x1 at t) -> bf16 NHWC features."""
 
     @staticmethod
-    def forward(ctx, x0, x1, t, w, b):
+    def forward(ctx, x0, x1, t, w, b, stats_box):
         patches = K.patch27_pack(x0.contiguous(), 1, None if x1 is None else x1.contiguous(),
                                  None if t is None else t.float().contiguous())
         cout = w.shape[0]
@@ -247,7 +275,9 @@ class _Stem(torch.autograd.Function):
             return wp
         wp = PACK_CACHE.get(("stem", id(w)), [w], make)
         B, _, H, W = x0.shape
-        out = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach())
+        out, st = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach(), want_stats=True)
+        if stats_box is not None:
+            stats_box.append(st)
         ctx.save_for_backward(patches)
         ctx.wshape = tuple(w.shape)
         return out
@@ -262,12 +292,13 @@ class _Stem(torch.autograd.Function):
         d_w = dw[0, :, :27].reshape(cout, 9, 3).permute(0, 2, 1).reshape(ctx.wshape).contiguous()
         d_b = torch.zeros(cout, dtype=torch.float32, device=g.device)
         K.channel_sum(g, d_b)
-        return None, None, None, d_w, d_b
+        return None, None, None, d_w, d_b, None
 
 
 def stem_conv(x0, w, b, x1=None, t=None):
     assert w.shape[1] == 3 and tuple(w.shape[2:]) == (3, 3), "stem expects a 3-channel 3x3 conv"
-    return _Stem.apply(x0, x1, t, w, b)
+    box = []
+    return _tag(_Stem.apply(x0, x1, t, w, b, box), box)
 
 
 class _HeadConv(torch.autograd.Function):
@@ -369,12 +400,15 @@ class _BatchNormRelu(torch.autograd.Function):
     place), eval mode = running statistics.  The streaming passes are the GroupNorm kernels with act = ReLU, G = C."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool,
+                src_stats=None):
         B, H, W, C = x.shape
         act = K.ACT_RELU if relu else K.ACT_NONE
         if training:
-            stats = K.gn_partial_buffer(B, H * W, C, x.device)
-            K.gn_stats(x, stats, 0)
+            stats = src_stats  # per-sub-tile partials from the producing conv's epilogue, same [B, n, C, 2] layout
+            if stats is None:
+                stats = K.gn_partial_buffer(B, H * W, C, x.device)
+                K.gn_stats(x, stats, 0)
             coef, mr = K.bn_coef(stats, gamma.detach(), beta.detach(), H * W, eps, momentum, running_mean, running_var)
         else:
             A = gamma.detach() * torch.rsqrt(running_var + eps)
@@ -400,7 +434,7 @@ class _BatchNormRelu(torch.autograd.Function):
         pqr = K.bn_bwd_coef(red, mr, gamma.detach(), H * W, dgamma, dbeta)
         dx = torch.empty_like(x)
         K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, ctx.act)
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
@@ -408,7 +442,7 @@ def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
         bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
     return _BatchNormRelu.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bool(bn.training),
-                                float(momentum), float(bn.eps), relu)
+                                float(momentum), float(bn.eps), relu, stats_of(x))
 
 
 class _MaxPool2x(torch.autograd.Function):
@@ -563,7 +597,7 @@ class _ResBlockFn(torch.autograd.Function):
     over the block input."""
 
     @staticmethod
-    def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, *tensors):
+    def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, src_stats, stats_box, *tensors):
         srcs = tensors[:n_src]
         emb_act = tensors[n_src]
         gn1w, gn1b, c1w, c1b, ew, eb, gn2w, gn2b, c2w, c2b = tensors[n_src + 1:n_src + 11]
@@ -575,24 +609,30 @@ class _ResBlockFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad)
         dual = train and K.ACT != K.GRAD
         # ---- norm 1 (+SiLU) over the concatenated input
-        stats = K.gn_partial_buffer(B, H * W, ctot, dev)
-        off = 0
-        for s in srcs:
-            K.gn_stats(s, stats, off)
-            off += s.shape[3]
-        coef1, mr1 = K.gn_coef(stats, gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
+        if usable_stats(src_stats):  # statistics written by the producing convs' epilogues: no pass over the inputs
+            coef1, mr1 = K.gn_coef_parts(list(src_stats), gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
+        else:
+            stats = K.gn_partial_buffer(B, H * W, ctot, dev)
+            off = 0
+            for s in srcs:
+                K.gn_stats(s, stats, off)
+                off += s.shape[3]
+            coef1, mr1 = K.gn_coef(stats, gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
         a1 = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
         a1g = torch.empty_like(a1) if dual else None
         off = 0
         for s in srcs:
             K.gn_apply(s, coef1, a1, off, True, y2=a1g)
             off += s.shape[3]
-        h = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach())
+        h, h_stats = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach(), want_stats=True)
         # ---- FiLM from the (already SiLU'd) embedding, norm 2 (+SiLU, dropout)
         film = torch.addmm(eb.detach(), emb_act.detach().float(), ew.detach().t()).contiguous()
-        stats2 = K.gn_partial_buffer(B, H * W, cout, dev)
-        K.gn_stats(h, stats2, 0)
-        coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
+        if h_stats is not None:
+            coef2, mr2 = K.gn_coef_parts([h_stats], gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
+        else:
+            stats2 = K.gn_partial_buffer(B, H * W, cout, dev)
+            K.gn_stats(h, stats2, 0)
+            coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
         a2 = torch.empty((B, H, W, cout), dtype=T16, device=dev)
         a2g = torch.empty_like(a2) if dual else None
         mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if (train and drop_p > 0) else None
@@ -602,10 +642,13 @@ class _ResBlockFn(torch.autograd.Function):
             sw, sb = skip
             wp = cfg.plan2.packed_fwd([c2w, sw])
             bias = (c2b.detach() + sb.detach()).contiguous()
-            out = K.conv_fwd([(a2, 9, 1)] + [(s, 1, 1) for s in srcs], wp, cout, H, W, bias=bias)
+            out, out_stats = K.conv_fwd([(a2, 9, 1)] + [(s, 1, 1) for s in srcs], wp, cout, H, W, bias=bias,
+                                        want_stats=True)
         else:
             assert n_src == 1 and ctot == cout
-            out = K.conv_fwd([(a2, 9, 1)], cfg.plan2.packed_fwd([c2w]), cout, H, W, bias=c2b.detach(), residual=srcs[0])
+            out, out_stats = K.conv_fwd([(a2, 9, 1)], cfg.plan2.packed_fwd([c2w]), cout, H, W, bias=c2b.detach(),
+                                        residual=srcs[0], want_stats=True)
+        stats_box.append(out_stats)
         if train:
             ctx.cfg, ctx.n_src, ctx.drop = cfg, n_src, (drop_p, seed)
             ctx.dual = dual
@@ -683,7 +726,7 @@ class _ResBlockFn(torch.autograd.Function):
             K.gn_bwd_apply(s, d_a1, coef1, pqr1, off, d_skip[i], dx, True)
             d_srcs.append(dx)
             off += s.shape[3]
-        grads = [None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
+        grads = [None, None, None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
                  d_gn2w, d_gn2b, d_c2w, d_b2]
         if cfg.has_skip_conv:
             grads += [d_sw, d_b2]
@@ -691,4 +734,6 @@ class _ResBlockFn(torch.autograd.Function):
 
 
 def res_block(cfg: ResBlockCfg, srcs, emb_act, params, drop_p: float, seed: int):
-    return _ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), *srcs, emb_act, *params)
+    box = []
+    src_stats = tuple(stats_of(t) for t in srcs)
+    return _tag(_ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), src_stats, box, *srcs, emb_act, *params), box)

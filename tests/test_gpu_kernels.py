@@ -386,3 +386,39 @@ def test_stored_dropout_mask_equals_rehash():
         k.gn_bwd_apply(x, gy, coef, pqr, 0, None, dx, True, 0.1, 77, mask=m)
         outs.append((red.clone(), dx.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 128), (3, 16, 48, 64, 256), (2, 24, 20, 128, 128),
+                                            (1, 8, 8, 256, 512)])
+def test_conv_epilogue_statistics_match_a_stats_pass(B, H, W, Cin, Cout):
+    """GroupNorm statistics emitted by the CTA-pair conv epilogue (per 128-pixel sub-tile, from the staged 16-bit tile)
+    give the same coefficients as a separate gn_stats pass over the stored tensor -- incl. ragged tiles."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    x = nhwc(rb(torch.randn(B, Cin, H, W, device=DEV, generator=g)))
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (3 * Cin ** 0.5)
+    wp = pack_fwd(k, [(w, 0, Cin)], Cout)
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    res = k.conv_fwd([(x, 9, 1)], wp, Cout, H, W, bias=bias, want_stats=True)
+    y, st = res
+    if k.conv_stat_tiles(H, W, Cout) == 0:
+        assert st is None
+        pytest.skip("CTA-pair path not selected for this geometry")
+    assert st.shape == (B, k.conv_stat_tiles(H, W, Cout), Cout, 2)
+    gamma = 1 + 0.1 * torch.randn(Cout, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Cout, device=DEV, generator=g)
+    coef_e, mr_e = k.gn_coef_parts([st], gamma, beta, None, H * W)
+    stats = k.gn_partial_buffer(B, H * W, Cout, DEV)
+    k.gn_stats(y, stats, 0)
+    coef_s, mr_s = k.gn_coef(stats, gamma, beta, None, H * W)
+    assert torch.allclose(mr_e, mr_s, rtol=2e-4, atol=2e-5), float((mr_e - mr_s).abs().max())
+    assert torch.allclose(coef_e, coef_s, rtol=2e-4, atol=2e-5)
+    # two-source fold == fold of the concatenation
+    y2, st2 = k.conv_fwd([(x, 9, 1)], wp, Cout, H, W, bias=bias * 0.5, want_stats=True)
+    g2 = torch.cat([gamma, gamma]); b2 = torch.cat([beta, beta])
+    coef_2, mr_2 = k.gn_coef_parts([st, st2], g2, b2, None, H * W)
+    stats_c = k.gn_partial_buffer(B, H * W, 2 * Cout, DEV)
+    k.gn_stats(y, stats_c, 0)
+    k.gn_stats(y2, stats_c, Cout)
+    coef_c, mr_c = k.gn_coef(stats_c, g2, b2, None, H * W)
+    assert torch.allclose(mr_2, mr_c, rtol=2e-4, atol=2e-5) and torch.allclose(coef_2, coef_c, rtol=2e-4, atol=2e-5)
