@@ -1,0 +1,100 @@
+"""The slice of Hydra / OmegaConf the reference's entry points use on this path, for images without hydra-core:
+`OmegaConf.load(yaml)` + `hydra.utils.instantiate(cfg)` (src/train.py:59-71, src/infer_simple_flowmatching.py:48-49).
+
+Supported: nested `_target_` instantiation (recursive, children first), `_partial_: true` -> functools.partial,
+`${key}` / `${a.b}` interpolation against the root config, keyword overrides.  `remap=True` additionally swaps the
+reference's `_target_` strings for this package's drop-ins, so the reference's OWN yaml files (unmodified) build the
+B200 modules: that is the config-level boundary of SURVEY.md 8(b).
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+import re
+from typing import Any, Dict
+
+import yaml
+
+TARGET_MAP = {
+    "torchcfm.models.unet.UNetModel": "stain2stain_b200.unet.UNetModel",
+    "torchcfm.models.unet.unet.UNetModel": "stain2stain_b200.unet.RawUNetModel",
+    "torchcfm.conditional_flow_matching.ConditionalFlowMatcher": "stain2stain_b200.flow_matching.ConditionalFlowMatcher",
+    "torchdyn.core.NeuralODE": "stain2stain_b200.neural_ode.NeuralODE",
+    "src.models.conditional_flow_matching.ConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit.ConditionalFlowMatchingLitModule",
+    "src.models.class_conditional_flow_matching.ClassConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit.ClassConditionalFlowMatchingLitModule",
+    "src.models.conditional_flow_matching_multitask_multiclassloss.MultiTaskFlowMatchingLitModule":
+        "stain2stain_b200.multitask.MultiTaskFlowMatchingLitModule",
+    "src.models.components.shared_encoder.SharedEncoder": "stain2stain_b200.multitask.SharedEncoder",
+    "src.models.components.task_decoders.FlowMatchingDecoder": "stain2stain_b200.multitask.FlowMatchingDecoder",
+    "src.models.components.task_decoders.SegmentationDecoder": "stain2stain_b200.multitask.SegmentationDecoder",
+}
+FUSED_OPTIMIZER_MAP = {"torch.optim.Adam": "stain2stain_b200.optim.FusedAdam"}
+
+_INTERP = re.compile(r"\$\{([^}]+)\}")
+
+
+def load_yaml(path: str) -> Dict[str, Any]:
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def _lookup(root, dotted: str):
+    cur = root
+    for part in dotted.split("."):
+        cur = cur[int(part)] if isinstance(cur, list) else cur[part]
+    return cur
+
+
+def _resolve(node, root):
+    if isinstance(node, dict):
+        return {k: _resolve(v, root) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_resolve(v, root) for v in node]
+    if isinstance(node, str):
+        m = _INTERP.fullmatch(node)
+        if m:
+            return _resolve(_lookup(root, m.group(1)), root)
+        return _INTERP.sub(lambda mm: str(_resolve(_lookup(root, mm.group(1)), root)), node)
+    return node
+
+
+def _locate(target: str):
+    module, _, name = target.rpartition(".")
+    return getattr(importlib.import_module(module), name)
+
+
+def _coerce(v):
+    # YAML 1.1 reads `1e-4` as a string; Hydra/OmegaConf read it as a float.
+    if isinstance(v, str):
+        try:
+            return float(v) if re.fullmatch(r"[+-]?\d+(\.\d*)?[eE][+-]?\d+", v) else v
+        except ValueError:
+            return v
+    return v
+
+
+def _build(node, remap: bool, fused_optimizer: bool):
+    if isinstance(node, list):
+        return [_build(v, remap, fused_optimizer) for v in node]
+    if not isinstance(node, dict):
+        return _coerce(node)
+    if "_target_" not in node:
+        return {k: _build(v, remap, fused_optimizer) for k, v in node.items()}
+    target = node["_target_"]
+    if remap:
+        target = TARGET_MAP.get(target, target)
+    if fused_optimizer:
+        target = FUSED_OPTIMIZER_MAP.get(target, target)
+    partial = bool(node.get("_partial_", False))
+    kwargs = {k: _build(v, remap, fused_optimizer) for k, v in node.items() if not (k.startswith("_") and k.endswith("_"))}
+    fn = _locate(target)
+    return functools.partial(fn, **kwargs) if partial else fn(**kwargs)
+
+
+def instantiate(cfg: Dict[str, Any], remap: bool = False, fused_optimizer: bool = False, **overrides):
+    """`hydra.utils.instantiate(cfg, **overrides)` for the subset described in the module docstring."""
+    cfg = dict(cfg)
+    cfg.update(overrides)
+    return _build(_resolve(cfg, cfg), remap, fused_optimizer)
