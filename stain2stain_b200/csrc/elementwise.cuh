@@ -125,7 +125,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int taps, int
         const int m = (int)(i / ((long long)taps * n_count));
         const float v = src[((size_t)tap * M + m) * ldn + n_off + n];
         float* g = grad + ((size_t)m * Cin_total + n_begin + n) * taps + tap;
-        *g = beta * (*g) + v;
+        *g = (beta == 0.f) ? v : fmaf(beta, *g, v);  // beta == 0: the destination may be uninitialised (NaN bit patterns)
     }
 }
 

@@ -87,6 +87,9 @@ class FusedAdam(torch.optim.Optimizer):
                                                    float(b1), float(b2), float(group["eps"]),
                                                    float(group["weight_decay"]), step, self.grad_scale,
                                                    _lib.stream_ptr()), "adam_multi")
+            # the kernel wrote through raw pointers: tell autograd (and the packed-operand cache, which is keyed by
+            # parameter version) that the parameters changed
+            torch.autograd.graph.increment_version(ps)
             for p in ps:
                 self.state[p]["step"] += 1
         return loss

@@ -93,7 +93,7 @@ def test_train_and_infer_entry_points(tmp_path):
     # the same weights through the oracle: Euler grids agree (PSNR >= 40 dB)
     from oracle import flow as oflow
     from oracle import unet as ounet
-    ref = ounet.UNetModel(**cfg["net"]).cuda()
+    ref = ounet.UNetModel(**{k: v for k, v in cfg["net"].items() if k != "_target_"}).cuda()
     ref.load_state_dict({k[4:]: v for k, v in state["state_dict"].items()})
     want = oflow.generate(ref, src.cuda(), num_steps=6, solver="euler")
     assert oflow.psnr(gen, want) >= 40.0
