@@ -144,6 +144,43 @@ int s2s_channel_sum(const void* x, long long npix, int C, float* out, int fmt, v
  * Replaces: `ut = x1 - x0`, `torch.mean((vt - ut) ** 2)` and its backward (conditional_flow_matching.py:66,72). */
 int s2s_fm_loss(const float* v, const float* x0, const float* x1, long long n, float* loss, float* dv, void* stream);
 
+/* ---- image-space kernels either side of the UNet (f1 input pipeline, f3 mask variants, f4 output) ------- */
+
+/* Stem-conv operand for 3- or 4-channel inputs: x0/x1 fp32 NCHW [B,Cx,H,W], extra fp32 [B,1,H,W] or NULL (the
+ * condition mask that conditional_flow_matching_conditional_mask.py:54-66 concatenates as a 4th channel -- here it is
+ * never concatenated, and never interpolated).  dst: 16-bit NHWC [B,H,W,64], column tap*CT + c, CT = Cx + (extra!=NULL). */
+int s2s_patch_pack(const float* x0, const float* x1, const float* t, const float* extra, int B, int Cx, int H, int W,
+                   void* dst16, int fmt, void* stream);
+
+/* Mask-weighted flow-matching loss (src/models/conditional_flow_matching_masked.py:76-92): w = 1 + lam*mask[b,0,p];
+ * sums[0] += sum w (v-(x1-x0))^2, sums[1] += sum w (over B*C*HW); dv = 2 w (v-(x1-x0)) (may be NULL; the caller scales
+ * by 1/(sums[1]+1e-8)).  sums: fp32 [2], zeroed by the caller. */
+int s2s_fm_loss_weighted(const float* v, const float* x0, const float* x1, const float* mask, float lam, int B, int C,
+                         int HW, float* sums, float* dv, void* stream);
+
+/* ROI Charbonnier term (src/models/conditional_flow_matching_ROI_loss.py:73-97) on xt = t x1 + (1-t) x0 against x1:
+ * sums[0] += sum sqrt((xt-x1)^2 + eps^2) * m, sums[1] += sum m (per pixel).  sums: fp32 [2], zeroed by the caller. */
+int s2s_roi_charbonnier(const float* x0, const float* x1, const float* t, const float* mask, int B, int C, int HW,
+                        float eps, float* sums, void* stream);
+
+/* Input side (src/data/paired_data_module.py:171-199): uint8 HWC tile pair [B,Hs,Ws,3] (+ optional uint8 mask
+ * [B,Hs,Ws]) -> crop(top,left,S,S) -> hflip -> vflip -> to_tensor -> Normalize(0.5,0.5) -> fp32 NCHW [B,3,S,S],
+ * bit-identical to the torchvision chain.  params: int32 [B][4] = (top, left, hflip, vflip); bgr != 0 if the bytes are
+ * in cv2.imread order.  tgt/out1 and mask/outm may be NULL. */
+int s2s_tile_prep(const uint8_t* src, const uint8_t* tgt, const uint8_t* mask, const int* params, int B, int Hs, int Ws,
+                  int S, int bgr, float* out0, float* out1, float* outm, void* stream);
+
+/* One pass of Pillow's antialiased 8-bit resampling (TF.resize on a PIL image, paired_data_module.py:201-203):
+ * out = clip8((2^21 + sum_k in[first+k]*kk[k]) >> 22).  bounds int32 [n_out][2] = (first, count), kk int32
+ * [n_out][ksize] (host-built like Pillow's precompute_coeffs / normalize_coeffs_8bpc).  in uint8 [B,Hin,Win,C];
+ * vertical == 0: out [B,Hin,n_out,C]; vertical != 0: out [B,n_out,Win,C]. */
+int s2s_resample_u8(const uint8_t* in, int B, int Hin, int Win, int C, const int* bounds, const int* kk, int ksize,
+                    int n_out, int vertical, uint8_t* out, void* stream);
+
+/* Output side (src/infer_simple_flowmatching.py:37-38, 86-88): fp32 NCHW [B,C,H,W] -> uint8 NHWC [B,H,W,C] =
+ * floor(clamp(x*0.5+0.5, 0, 1)*255 + 0.5). */
+int s2s_denorm_u8(const float* x, int B, int C, int HW, uint8_t* out, void* stream);
+
 /* 16-bit storage format conversion of n elements (n % 8 == 0), e.g. fp16 saved activations -> bf16 wgrad operands
  * (the two operands of one tcgen05 kind::f16 MMA must share a format). */
 int s2s_convert16(const void* in, void* out, long long n, int in_fmt, int out_fmt, void* stream);

@@ -7,6 +7,9 @@ and follows, line by line, the in-repo numerics of
   * src/models/conditional_flow_matching.py:53-74   (model_step)
   * src/models/conditional_flow_matching.py:133-170 (generate)
   * src/models/class_conditional_flow_matching.py:49-71, 130-190
+  * the mask / ROI variants (pinned bit-for-bit against the reference's own modules, tests/golden/mask_variants_small.pt):
+    src/models/conditional_flow_matching_masked.py:59-92, conditional_flow_matching_ROI_loss.py:64-97,
+    conditional_flow_matching_conditional_mask.py:54-82, 143-199, conditional_flow_matching_conditional_toggle_mask.py:68-87, 186-187
 """
 from __future__ import annotations
 
@@ -171,6 +174,56 @@ def model_step(net, flow_matcher, batch, t=None):
     t, xt, ut = flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
     vt = net(t, xt) if y is None else net(t, xt, y=y)
     return torch.mean((vt - ut) ** 2)
+
+
+def model_step_mask_weighted(net, flow_matcher, batch, t=None, roi_lambda=10.0):
+    """src/models/conditional_flow_matching_masked.py:59-92: MSE weighted by 1 + roi_lambda * mask."""
+    x0, x1, mask = batch
+    t, xt, ut = flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
+    vt = net(t, xt)
+    weights = (1.0 + roi_lambda * mask).expand_as(vt)
+    return (weights * (vt - ut) ** 2).sum() / (weights.sum() + 1e-8)
+
+
+def model_step_roi(net, flow_matcher, batch, t=None, lambda_roi=1.0):
+    """src/models/conditional_flow_matching_ROI_loss.py:64-97: MSE + lambda_roi * ROI Charbonnier(xt, x1)."""
+    x0, x1, mask = batch
+    t, xt, ut = flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
+    vt = net(t, xt)
+    loss_fm = torch.mean((vt - ut) ** 2)
+    m = mask.float()
+    diff = xt - x1
+    charb = torch.sqrt(diff * diff + 1e-3 * 1e-3)
+    roi_charb = (charb * m).sum() / (m.sum() * xt.shape[1] + 1e-8)
+    return loss_fm + lambda_roi * roi_charb
+
+
+def model_step_mask_conditioned(net, flow_matcher, batch, t=None, use_mask_toggle=False):
+    """src/models/conditional_flow_matching_conditional_mask.py:68-82 (and ..._toggle_mask.py:68-87 with the toggle):
+    the mask is the UNet's 4th input channel."""
+    x0, x1, mask = batch
+    if use_mask_toggle and torch.rand(1).item() < 0.5:
+        mask = torch.zeros_like(mask)
+    t, xt, ut = flow_matcher.sample_location_and_conditional_flow(x0, x1, t=t)
+    vt = net(t, torch.cat([xt, mask], dim=1))
+    return torch.mean((vt - ut) ** 2)
+
+
+@torch.no_grad()
+def generate_mask_conditioned(net, source_img, mask, num_steps=100, solver="dopri5", atol=1e-4, rtol=1e-4,
+                              zero_mask=False):
+    """conditional_flow_matching_conditional_mask.py:143-199 (zero_mask: ..._toggle_mask.py:186-187)."""
+    net.eval()
+    if source_img.dim() == 3:
+        source_img = source_img.unsqueeze(0)
+    if mask.dim() == 3:
+        mask = mask.unsqueeze(0)
+    if zero_mask:
+        mask = torch.zeros_like(mask)
+    node = NeuralODE(lambda t, x: net(t, torch.cat([x, mask], dim=1)), solver=solver, sensitivity="adjoint", atol=atol,
+                     rtol=rtol)
+    t_span = torch.linspace(0, 1, num_steps, device=source_img.device)
+    return node.trajectory(source_img, t_span=t_span)[-1]
 
 
 @torch.no_grad()

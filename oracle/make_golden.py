@@ -115,10 +115,116 @@ def multitask():
     return out
 
 
+RAW4 = dict(image_size=64, in_channels=4, model_channels=64, out_channels=3, num_res_blocks=1, attention_resolutions=[8, 4],
+            dropout=0.0, channel_mult=[1, 2, 2, 4], use_scale_shift_norm=True, num_heads=4, num_head_channels=32)
+MASK_VARIANTS = {  # name -> (reference module, 4-channel raw UNet?)
+    "mask_weighted": ("conditional_flow_matching_masked", False),
+    "roi_loss": ("conditional_flow_matching_ROI_loss", False),
+    "mask_conditioned": ("conditional_flow_matching_conditional_mask", True),
+    "mask_toggle": ("conditional_flow_matching_conditional_toggle_mask", True),
+}
+
+
+def mask_variants():
+    """The four mask / ROI LitModules of the reference, each executed unmodified."""
+    out = dict(configs=dict(simple=SMALL, raw4=RAW4), weight_seed=0, dezero_seed=1984, input_seed=41)
+    inp = inputs(41, 2, 64, mask_classes=2)  # binary ROI mask
+    x0, x1, mask = inp["x0"], inp["x1"], inp["mask"]
+    out["inputs_check"] = dict(x0=float(x0.double().sum()), mask=float(mask.sum()))
+    for name, (modname, raw4) in MASK_VARIANTS.items():
+        mod = rb.reference_module(f"src.models.{modname}")
+        torch.manual_seed(0)
+        net = ounet.dezero_(ounet.RawUNetModel(**RAW4) if raw4 else ounet.UNetModel(**SMALL), seed=1984)
+        lit = mod.ConditionalFlowMatchingLitModule(
+            net=net, flow_matcher=oflow.ConditionalFlowMatcher(0.0),
+            solver=functools.partial(oflow.NeuralODE, solver="dopri5", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+            optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None, log_images=False)
+        lit.eval()
+        rec = dict(checksums=checksums(lit))
+        torch.manual_seed(79)
+        t_drawn = torch.rand(2)
+        torch.manual_seed(79)
+        loss = lit.model_step((x0, x1, mask))
+        lit.zero_grad()
+        loss.backward()
+        rec["model_step"] = dict(rng_seed=79, t=t_drawn, loss=loss.detach(),
+                                 grad_norms={k: float(p.grad.double().norm()) for k, p in lit.named_parameters()})
+        if name == "mask_toggle":  # training_step toggles: rand(1) is drawn BEFORE t; record one step of each kind
+            rec["training_step"] = []
+            seen, seed = set(), 80
+            while len(seen) < 2:
+                torch.manual_seed(seed)
+                toggled = bool(torch.rand(1).item() < 0.5)
+                t2 = torch.rand(2)
+                if toggled not in seen:
+                    seen.add(toggled)
+                    torch.manual_seed(seed)
+                    rec["training_step"].append(dict(rng_seed=seed, toggled=toggled, t=t2,
+                                                     loss=lit.training_step((x0, x1, mask), 0).detach()))
+                seed += 1
+        with torch.no_grad():
+            rec["forward"] = lit(inp["t"], x0, mask) if raw4 else lit(inp["t"], x0)
+        rec["generate_num_steps2"] = lit.generate(x0[:1], mask[:1], num_steps=2) if raw4 else lit.generate(x0[:1], num_steps=2)
+        out[name] = rec
+    torch.save(out, os.path.join(OUT, "mask_variants_small.pt"))
+    return out
+
+
+def paired_dataset():
+    """The reference's PairedDataset / PairedDataModule (src/data/paired_data_module.py), unmodified, on a tiny synthetic
+    PNG dataset.  The fixture carries the raw images so the test can rebuild the PNG files."""
+    import random
+    import tempfile
+
+    import cv2
+    import numpy as np
+    pdm = rb.reference_module("src.data.paired_data_module")
+    rng = np.random.RandomState(7)
+    n, hw = 3, 96
+    # smooth-ish random RGB images (so the antialiased resize has structure to average)
+    imgs = {f"img{k}_{kind}.png": rng.randint(0, 256, (hw, hw, 3)).astype(np.uint8) for k in range(n) for kind in ("he", "ihc")}
+    out = dict(images=imgs, rows=[(f"img{k}_he.png", f"img{k}_ihc.png", "train" if k < 2 else "test") for k in range(n)])
+    with tempfile.TemporaryDirectory() as d:
+        for split in ("train", "test"):
+            os.makedirs(os.path.join(d, split))
+        with open(os.path.join(d, "meta.csv"), "w") as f:
+            f.write("image_id,he_filepath,ihc_filepath,split\n")
+            for k, (a, b, split) in enumerate(out["rows"]):
+                f.write(f"{k},{a},{b},{split}\n")
+                for name in (a, b):
+                    cv2.imwrite(os.path.join(d, split, name), cv2.cvtColor(imgs[name], cv2.COLOR_RGB2BGR))
+        kw = dict(data_dir=d, csv_file_name="meta.csv", source_column="he_filepath", target_column="ihc_filepath")
+        # train: random crop 64 + flips, drawn from the torch / python default generators
+        ds = pdm.PairedDataset(folder="train", image_size=64, use_augmentation=True, **kw)
+        torch.manual_seed(123)
+        random.seed(123)
+        out["train_aug"] = dict(torch_seed=123, python_seed=123, image_size=64, items=[ds[0], ds[1], ds[0]])
+        # eval: antialiased resize to 48 (and to 96 = identity), T2S direction, filenames returned
+        ds = pdm.PairedDataset(folder="test", image_size=48, use_augmentation=False, direction="T2S", return_filename=True, **kw)
+        out["eval_resize48_T2S"] = ds[0]
+        ds = pdm.PairedDataset(folder="train", image_size=96, use_augmentation=False, **kw)
+        out["eval_identity96"] = ds[1]
+        dm = pdm.PairedDataModule(batch_size=8, image_size=64, **kw)
+
+        class _T:
+            world_size = 4
+        dm.trainer = _T()
+        dm.setup()
+        out["per_device_batch_8_over_4"] = dm.batch_size_per_device
+        _T.world_size = 3
+        try:
+            dm.setup()
+            out["indivisible_raises"] = None
+        except RuntimeError as e:
+            out["indivisible_raises"] = str(e)
+    torch.save(out, os.path.join(OUT, "paired_dataset_small.pt"))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order on the CPU
-    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask):
+    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask, mask_variants, paired_dataset):
         o = fn()
         print({k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__) for k, v in o.items()})
     for f in sorted(os.listdir(OUT)):

@@ -50,12 +50,24 @@ class _LightningModule(nn.Module):
         return next(self.parameters()).device
 
 
+class _LightningDataModule:
+    def __init__(self):
+        self.hparams = _HParams()
+        self.trainer = None
+
+    def save_hyperparameters(self, *a, logger=True, **k):
+        import inspect
+        frame = inspect.currentframe().f_back
+        self.hparams.update({k2: v for k2, v in frame.f_locals.items() if k2 not in ("self", "__class__")})
+
+
 def install_stubs():
     from . import flow as oflow
     from . import unet as ounet
     if "lightning" not in sys.modules:
         m = types.ModuleType("lightning")
         m.LightningModule = _LightningModule
+        m.LightningDataModule = _LightningDataModule
         sys.modules["lightning"] = m
     if "torchcfm" not in sys.modules:
         pkg = types.ModuleType("torchcfm")

@@ -49,6 +49,12 @@ SIGNATURES = {
     "s2s_zero_insert2x": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_channel_sum": [_vp, _ll, _i, _vp, _i, _vp],
     "s2s_fm_loss": [_vp, _vp, _vp, _ll, _vp, _vp, _vp],
+    "s2s_patch_pack": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "s2s_fm_loss_weighted": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp],
+    "s2s_roi_charbonnier": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp],
+    "s2s_tile_prep": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "s2s_resample_u8": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "s2s_denorm_u8": [_vp, _i, _i, _i, _vp, _vp],
     "s2s_convert16": [_vp, _vp, _ll, _i, _i, _vp],
     "s2s_nchw_f32_to_nhwc16": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],

@@ -11,6 +11,7 @@
 #include "elementwise.cuh"
 #include "multitask.cuh"
 #include "optim.cuh"
+#include "tiles.cuh"
 
 using namespace s2s;
 
@@ -728,6 +729,71 @@ int s2s_fm_loss(const float* v, const float* x0, const float* x1, long long n, f
     int grid = ew_grid(n / 4 + 1);
     fm_loss_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(v, x0, x1, n, 1.0f / (float)n, loss, dv);
     LAUNCH_CHECK("fm_loss_kernel");
+    return S2S_OK;
+}
+
+// ---- image-space kernels either side of the UNet (tiles.cuh) --------------------------------------------------------
+int s2s_patch_pack(const float* x0, const float* x1, const float* t, const float* extra, int B, int Cx, int H, int W,
+                   void* dst, int fmt, void* stream) {
+    const int CT = Cx + (extra ? 1 : 0);
+    if (!x0 || !dst || (x1 && !t) || Cx < 1) return fail(S2S_ERR_INVALID, "patch_pack: bad arguments");
+    const long long npix = (long long)B * H * W;
+    const int grid = ew_grid(npix, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (CT) {
+        case 3: patch_pack_kernel<3><<<grid, 128, 0, st>>>(x0, x1, t, extra, Cx, B, H, W, (__nv_bfloat16*)dst, fmt); break;
+        case 4: patch_pack_kernel<4><<<grid, 128, 0, st>>>(x0, x1, t, extra, Cx, B, H, W, (__nv_bfloat16*)dst, fmt); break;
+        default: return fail(S2S_ERR_INVALID, "patch_pack: %d input channels unsupported (3 or 4)", CT);
+    }
+    LAUNCH_CHECK("patch_pack_kernel");
+    return S2S_OK;
+}
+
+int s2s_fm_loss_weighted(const float* v, const float* x0, const float* x1, const float* mask, float lam, int B, int C,
+                         int HW, float* sums, float* dv, void* stream) {
+    if (!v || !x0 || !x1 || !mask || !sums) return fail(S2S_ERR_INVALID, "fm_loss_weighted: bad arguments");
+    fm_loss_weighted_kernel<<<ew_grid((long long)B * C * HW), kEwThreads, 0, (cudaStream_t)stream>>>(v, x0, x1, mask, lam, B,
+                                                                                                  C, HW, sums, dv);
+    LAUNCH_CHECK("fm_loss_weighted_kernel");
+    return S2S_OK;
+}
+
+int s2s_roi_charbonnier(const float* x0, const float* x1, const float* t, const float* mask, int B, int C, int HW,
+                        float eps, float* sums, void* stream) {
+    if (!x0 || !x1 || !t || !mask || !sums) return fail(S2S_ERR_INVALID, "roi_charbonnier: bad arguments");
+    roi_charbonnier_kernel<<<ew_grid((long long)B * HW), kEwThreads, 0, (cudaStream_t)stream>>>(x0, x1, t, mask, B, C, HW, eps,
+                                                                                             sums);
+    LAUNCH_CHECK("roi_charbonnier_kernel");
+    return S2S_OK;
+}
+
+int s2s_tile_prep(const uint8_t* src, const uint8_t* tgt, const uint8_t* mask, const int* params, int B, int Hs, int Ws,
+                  int S, int bgr, float* out0, float* out1, float* outm, void* stream) {
+    if (!src || !params || !out0 || (tgt && !out1) || (mask && !outm) || S <= 0 || S > Hs || S > Ws)
+        return fail(S2S_ERR_INVALID, "tile_prep: bad arguments");
+    tile_prep_kernel<<<ew_grid((long long)B * S * S), kEwThreads, 0, (cudaStream_t)stream>>>(src, tgt, mask, params, B, Hs, Ws,
+                                                                                          S, bgr, out0, out1, outm);
+    LAUNCH_CHECK("tile_prep_kernel");
+    return S2S_OK;
+}
+
+int s2s_resample_u8(const uint8_t* in, int B, int Hin, int Win, int C, const int* bounds, const int* kk, int ksize,
+                    int n_out, int vertical, uint8_t* out, void* stream) {
+    if (!in || !bounds || !kk || !out || ksize <= 0 || n_out <= 0) return fail(S2S_ERR_INVALID, "resample_u8: bad arguments");
+    if (vertical)
+        resample_u8_v_kernel<<<ew_grid((long long)B * n_out * Win * C), kEwThreads, 0, (cudaStream_t)stream>>>(
+            in, B, Hin, Win, C, bounds, kk, ksize, n_out, out);
+    else
+        resample_u8_h_kernel<<<ew_grid((long long)B * Hin * n_out * C), kEwThreads, 0, (cudaStream_t)stream>>>(
+            in, B, Hin, Win, C, bounds, kk, ksize, n_out, out);
+    LAUNCH_CHECK("resample_u8_kernel");
+    return S2S_OK;
+}
+
+int s2s_denorm_u8(const float* x, int B, int C, int HW, uint8_t* out, void* stream) {
+    if (!x || !out) return fail(S2S_ERR_INVALID, "denorm_u8: bad arguments");
+    denorm_u8_kernel<<<ew_grid((long long)B * HW), kEwThreads, 0, (cudaStream_t)stream>>>(x, B, C, HW, out);
+    LAUNCH_CHECK("denorm_u8_kernel");
     return S2S_OK;
 }
 

@@ -29,7 +29,11 @@ def denormalize(t: torch.Tensor) -> torch.Tensor:
 
 
 def to_uint8_hwc(t: torch.Tensor) -> torch.Tensor:
-    """Normalised NCHW tiles -> uint8 NHWC (what the reference hands to matplotlib / W&B)."""
+    """Normalised NCHW tiles -> uint8 NHWC (what the reference hands to matplotlib / W&B).  Device tensors go through
+    the fused `s2s_denorm_u8` kernel (data.denormalize_to_uint8); host tensors through the same formula in torch."""
+    if t.is_cuda:
+        from .data import denormalize_to_uint8
+        return denormalize_to_uint8(t)
     return (denormalize(t) * 255.0 + 0.5).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
 

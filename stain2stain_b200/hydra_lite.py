@@ -26,6 +26,14 @@ TARGET_MAP = {
         "stain2stain_b200.lit.ClassConditionalFlowMatchingLitModule",
     "src.models.conditional_flow_matching_multitask_multiclassloss.MultiTaskFlowMatchingLitModule":
         "stain2stain_b200.multitask.MultiTaskFlowMatchingLitModule",
+    "src.models.conditional_flow_matching_masked.ConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit_masked.MaskWeightedFlowMatchingLitModule",
+    "src.models.conditional_flow_matching_ROI_loss.ConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit_masked.ROILossFlowMatchingLitModule",
+    "src.models.conditional_flow_matching_conditional_mask.ConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit_masked.MaskConditionedFlowMatchingLitModule",
+    "src.models.conditional_flow_matching_conditional_toggle_mask.ConditionalFlowMatchingLitModule":
+        "stain2stain_b200.lit_masked.MaskToggleFlowMatchingLitModule",
     "src.models.components.shared_encoder.SharedEncoder": "stain2stain_b200.multitask.SharedEncoder",
     "src.models.components.task_decoders.FlowMatchingDecoder": "stain2stain_b200.multitask.FlowMatchingDecoder",
     "src.models.components.task_decoders.SegmentationDecoder": "stain2stain_b200.multitask.SegmentationDecoder",

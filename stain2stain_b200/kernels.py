@@ -438,3 +438,95 @@ def seg_loss_bwd(logits, target, ignore_index: int, sums, smooth: float, w_dice:
     check(_L().s2s_seg_loss_bwd(ptr(logits), ptr(target), B, Cc, H * W, int(ignore_index), ptr(sums), float(smooth),
                                 float(w_dice), float(w_ce), ptr(gscale), ptr(d), stream_ptr()), "seg_loss_bwd")
     return d
+
+
+# ---- image-space kernels either side of the UNet (csrc/tiles.cuh) ---------------------------
+def patch_pack(x0: torch.Tensor, x1: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None,
+               extra: Optional[torch.Tensor] = None, fmt: int = ACT) -> torch.Tensor:
+    """fp32 NCHW [B,Cx,H,W] (+ optional condition channel `extra` [B,1,H,W]) -> 16-bit NHWC [B,H,W,64] 3x3 patches,
+    column tap*CT + c; with x1/t the first Cx channels are the flow-matching interpolant."""
+    assert x0.dtype == torch.float32 and x0.is_contiguous() and x0.dim() == 4
+    B, Cx, H, W = x0.shape
+    if x1 is not None:
+        assert x1.shape == x0.shape and x1.is_contiguous() and x1.dtype == torch.float32
+        assert t.dtype == torch.float32 and t.numel() == B and t.is_contiguous()
+    if extra is not None:
+        assert extra.dtype == torch.float32 and extra.is_contiguous() and tuple(extra.shape) == (B, 1, H, W)
+    dst = torch.empty((B, H, W, 64), dtype=T16, device=x0.device)
+    ct = Cx + (1 if extra is not None else 0)
+    with _Prof("patch_pack", 0.0, (4.0 * ct * (2 if x1 is not None else 1) + 128.0) * B * H * W):
+        check(_L().s2s_patch_pack(ptr(x0), ptr(x1), ptr(t), ptr(extra), B, Cx, H, W, ptr(dst), fmt, stream_ptr()),
+              "patch_pack")
+    return dst
+
+
+def fm_loss_weighted(v, x0, x1, mask, lam: float, want_grad: bool):
+    """-> (sums fp32 [2] = (sum w d^2, sum w), dv_unscaled = 2 w d or None); w = 1 + lam * mask broadcast over channels."""
+    B, Cc, H, W = v.shape
+    for a in (v, x0, x1, mask):
+        assert a.dtype == torch.float32 and a.is_contiguous()
+    assert x0.shape == v.shape and x1.shape == v.shape and tuple(mask.shape) == (B, 1, H, W)
+    sums = torch.zeros(2, dtype=torch.float32, device=v.device)
+    dv = torch.empty_like(v) if want_grad else None
+    with _Prof("fm_loss_weighted", 0.0, (16.0 + (4.0 if want_grad else 0.0)) * v.numel()):
+        check(_L().s2s_fm_loss_weighted(ptr(v), ptr(x0), ptr(x1), ptr(mask), float(lam), B, Cc, H * W, ptr(sums), ptr(dv),
+                                        stream_ptr()), "fm_loss_weighted")
+    return sums, dv
+
+
+def roi_charbonnier(x0, x1, t, mask, eps: float = 1e-3):
+    """-> sums fp32 [2] = (sum charbonnier(xt - x1) * m, sum m) with xt = t x1 + (1-t) x0."""
+    B, Cc, H, W = x0.shape
+    for a in (x0, x1, t, mask):
+        assert a.dtype == torch.float32 and a.is_contiguous()
+    assert x1.shape == x0.shape and t.numel() == B and tuple(mask.shape) == (B, 1, H, W)
+    sums = torch.zeros(2, dtype=torch.float32, device=x0.device)
+    with _Prof("roi_charbonnier", 0.0, 8.0 * x0.numel() + 4.0 * mask.numel()):
+        check(_L().s2s_roi_charbonnier(ptr(x0), ptr(x1), ptr(t), ptr(mask), B, Cc, H * W, float(eps), ptr(sums),
+                                       stream_ptr()), "roi_charbonnier")
+    return sums
+
+
+def tile_prep(src_u8: torch.Tensor, tgt_u8: Optional[torch.Tensor], params: torch.Tensor, size: int, bgr: bool = False,
+              mask_u8: Optional[torch.Tensor] = None):
+    """uint8 HWC tiles [B,Hs,Ws,3] (+ target, + uint8 mask [B,Hs,Ws]) -> crop/flip/to_tensor/normalise -> fp32 NCHW.
+    params: int32 [B,4] = (top, left, hflip, vflip) on the device."""
+    assert src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() == 4 and src_u8.shape[3] == 3
+    B, Hs, Ws, _ = src_u8.shape
+    assert params.dtype == torch.int32 and tuple(params.shape) == (B, 4) and params.is_contiguous()
+    if tgt_u8 is not None:
+        assert tgt_u8.shape == src_u8.shape and tgt_u8.dtype == torch.uint8 and tgt_u8.is_contiguous()
+    if mask_u8 is not None:
+        assert tuple(mask_u8.shape) == (B, Hs, Ws) and mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
+    out0 = torch.empty((B, 3, size, size), dtype=torch.float32, device=src_u8.device)
+    out1 = torch.empty_like(out0) if tgt_u8 is not None else None
+    outm = torch.empty((B, 1, size, size), dtype=torch.float32, device=src_u8.device) if mask_u8 is not None else None
+    n_img = 1 + (tgt_u8 is not None)
+    with _Prof("tile_prep", 0.0, 15.0 * n_img * B * size * size):
+        check(_L().s2s_tile_prep(ptr(src_u8), ptr(tgt_u8), ptr(mask_u8), ptr(params), B, Hs, Ws, size, int(bgr), ptr(out0),
+                                 ptr(out1), ptr(outm), stream_ptr()), "tile_prep")
+    return out0, out1, outm
+
+
+def resample_u8(x: torch.Tensor, bounds: torch.Tensor, kk: torch.Tensor, vertical: bool) -> torch.Tensor:
+    """One Pillow resampling pass over uint8 [B,H,W,C]; bounds int32 [n_out,2], kk int32 [n_out,ksize] (device)."""
+    assert x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    n_out, ksize = kk.shape
+    assert bounds.dtype == torch.int32 and kk.dtype == torch.int32 and tuple(bounds.shape) == (n_out, 2)
+    assert bounds.is_contiguous() and kk.is_contiguous()
+    out = torch.empty((B, n_out, W, Cc) if vertical else (B, H, n_out, Cc), dtype=torch.uint8, device=x.device)
+    with _Prof("resample_u8", 0.0, float(x.numel() + out.numel())):
+        check(_L().s2s_resample_u8(ptr(x), B, H, W, Cc, ptr(bounds), ptr(kk), ksize, n_out, int(vertical), ptr(out),
+                                   stream_ptr()), "resample_u8")
+    return out
+
+
+def denorm_u8(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW [B,C,H,W] in [-1,1] -> uint8 NHWC [B,H,W,C]."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x.device)
+    with _Prof("denorm_u8", 0.0, 5.0 * x.numel()):
+        check(_L().s2s_denorm_u8(ptr(x), B, Cc, H * W, ptr(out), stream_ptr()), "denorm_u8")
+    return out

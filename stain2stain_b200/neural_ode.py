@@ -35,49 +35,61 @@ def _rms(x):
     return x.abs().pow(2).mean().sqrt()
 
 
-def _unwrap_vector_field(vf) -> Tuple[Optional[RawUNetModel], Optional[torch.Tensor]]:
-    """Find one of our UNets behind the reference's wrappers (`ConditionalWrapper(model, y)`,
-    class_conditional_flow_matching.py:163-174; `FlowWrapper`), returning (net, y)."""
+def _unwrap_vector_field(vf) -> Tuple[Optional[RawUNetModel], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Find one of our UNets behind the reference's wrappers -- `ConditionalWrapper(model, y)`
+    (class_conditional_flow_matching.py:163-174), `FlowWrapper`, `MaskConditionedWrapper(net, mask)`
+    (conditional_flow_matching_conditional_mask.py:170-180) -- returning (net, y, mask)."""
     if isinstance(vf, RawUNetModel):
-        return vf, None
+        return vf, None, None
     inner = getattr(vf, "model", None)
     if inner is None:
         inner = getattr(vf, "net", None)
     if isinstance(inner, RawUNetModel):
         y = getattr(vf, "y", None)
-        return inner, y if torch.is_tensor(y) else None
-    return None, None
+        mask = getattr(vf, "mask", None)
+        return inner, (y if torch.is_tensor(y) else None), (mask if torch.is_tensor(mask) else None)
+    return None, None, None
 
 
 class _EulerGraph:
     """One captured Euler step of a UNet on static buffers."""
 
-    def __init__(self, net: RawUNetModel, x: torch.Tensor, y: Optional[torch.Tensor], dt: float):
+    def __init__(self, net: RawUNetModel, x: torch.Tensor, y: Optional[torch.Tensor], dt: float,
+                 extra: Optional[torch.Tensor] = None):
+        from . import kernels as K
         self.x = torch.empty_like(x)
         self.t = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
         self.y = None if y is None else y.clone()
+        self.extra = None if extra is None else extra.float().contiguous().clone()
         self.dt = dt
         # eager warm-up on scratch data: packs weights, sets kernel attributes, warms the allocator
         self.x.copy_(x)
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            net.euler_step_(self.t, self.x, dt, y=self.y)
+            net.euler_step_(self.t, self.x, dt, y=self.y, extra=self.extra)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = K.LAUNCHES[0]
         with torch.cuda.graph(self.graph):
-            net.euler_step_(self.t, self.x, dt, y=self.y)
+            net.euler_step_(self.t, self.x, dt, y=self.y, extra=self.extra)
             self.t.add_(dt)
+        self.kernels_per_replay = K.LAUNCHES[0] - n0  # this package's kernels inside one replay
 
-    def run(self, x0: torch.Tensor, t0: float, steps: int, y: Optional[torch.Tensor], record: Optional[list]):
+    def run(self, x0: torch.Tensor, t0: float, steps: int, y: Optional[torch.Tensor], record: Optional[list],
+            extra: Optional[torch.Tensor] = None):
+        from . import kernels as K
         self.x.copy_(x0)
         self.t.fill_(t0)
         if self.y is not None:
             self.y.copy_(y)
+        if self.extra is not None:
+            self.extra.copy_(extra)
         for _ in range(steps):
             self.graph.replay()
             if record is not None:
                 record.append(self.x.clone())
+        K.LAUNCHES[0] += steps * self.kernels_per_replay
         return self.x
 
 
@@ -89,25 +101,26 @@ def _param_signature(net: nn.Module):
 
 
 def fused_euler(net: RawUNetModel, x: torch.Tensor, t_span: torch.Tensor, y: Optional[torch.Tensor] = None,
-                record: Optional[list] = None, use_graph: bool = True) -> torch.Tensor:
-    """Integrate dx/dt = net(t, x) over a UNIFORM t_span with the fused Euler step.  Returns the final state."""
+                record: Optional[list] = None, use_graph: bool = True, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Integrate dx/dt = net(t, x[, mask]) over a UNIFORM t_span with the fused Euler step.  Returns the final state."""
     assert not net.training, "sampling runs in eval mode (generate() calls self.eval())"
     steps = len(t_span) - 1
     t0 = float(t_span[0])
     dt = float(t_span[-1] - t_span[0]) / steps
     x = x.float().contiguous()
     if use_graph:
-        key = (id(net), tuple(x.shape), x.device.index, dt, y is not None, _param_signature(net))
+        key = (id(net), tuple(x.shape), x.device.index, dt, y is not None, extra is not None, _param_signature(net))
         g = _GRAPHS.get(key)
         if g is None:
             for k in [k for k in _GRAPHS if k[0] == id(net) and k[1] == tuple(x.shape)]:
                 del _GRAPHS[k]  # stale parameters / other dt: drop the old capture
-            g = _GRAPHS[key] = _EulerGraph(net, x, y, dt)
-        return g.run(x, t0, steps, y, record).clone()
+            g = _GRAPHS[key] = _EulerGraph(net, x, y, dt, extra)
+        return g.run(x, t0, steps, y, record, extra).clone()
     xs = x.clone()
+    ex = None if extra is None else extra.float().contiguous()
     t = torch.full((x.shape[0],), t0, dtype=torch.float32, device=x.device)
     for _ in range(steps):
-        net.euler_step_(t, xs, dt, y=y)
+        net.euler_step_(t, xs, dt, y=y, extra=ex)
         t += dt
         if record is not None:
             record.append(xs.clone())
@@ -192,23 +205,23 @@ class NeuralODE(nn.Module):
         self.use_cuda_graph = use_cuda_graph
 
     def _fast(self, t_span):
-        net, y = _unwrap_vector_field(self.vf)
+        net, y, mask = _unwrap_vector_field(self.vf)
         ok = net is not None and self.solver == "euler" and not net.training and _is_uniform(t_span)
-        return (net, y) if ok else (None, None)
+        return (net, y, mask) if ok else (None, None, None)
 
     @torch.no_grad()
     def final_state(self, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
         """State at t_span[-1] without materialising the trajectory (what `generate` actually needs)."""
-        net, y = self._fast(t_span)
+        net, y, mask = self._fast(t_span)
         if net is not None:
-            return fused_euler(net, x, t_span, y, None, self.use_cuda_graph)
+            return fused_euler(net, x, t_span, y, None, self.use_cuda_graph, extra=mask)
         return self.trajectory(x, t_span)[-1]
 
     def trajectory(self, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
-        net, y = self._fast(t_span)
+        net, y, mask = self._fast(t_span)
         if net is not None and not torch.is_grad_enabled():
             rec = [x.float().clone()]
-            fused_euler(net, x, t_span, y, rec, self.use_cuda_graph)
+            fused_euler(net, x, t_span, y, rec, self.use_cuda_graph, extra=mask)
             return torch.stack(rec)
         _, sol = odeint(lambda t, z: self.vf(t, z), x, t_span, solver=self.solver, atol=self.atol, rtol=self.rtol)
         return sol

@@ -261,13 +261,19 @@ def upsample2x(x):
 
 # --------------------------------------------------------------------------------------------- stem / head (3-channel ends)
 class _Stem(torch.autograd.Function):
-    """3x3 conv on the fp32 NCHW image (optionally the FM interpolant of x0, x1 at t) -> bf16 NHWC features."""
+    """3x3 conv on the fp32 NCHW image (optionally the FM interpolant of x0, x1 at t; optionally with a condition
+    channel `extra` appended, never materialised as a concat) -> 16-bit NHWC features."""
 
     @staticmethod
-    def forward(ctx, x0, x1, t, w, b, stats_box):
-        patches = K.patch27_pack(x0.contiguous(), 1, None if x1 is None else x1.contiguous(),
-                                 None if t is None else t.float().contiguous())
-        cout = w.shape[0]
+    def forward(ctx, x0, x1, t, w, b, stats_box, extra):
+        cout, cin = w.shape[0], w.shape[1]
+        x1c = None if x1 is None else x1.contiguous()
+        tc = None if t is None else t.float().contiguous()
+        if cin == 3 and extra is None:
+            patches = K.patch27_pack(x0.contiguous(), 1, x1c, tc)
+        else:
+            assert x0.shape[1] + (extra is not None) == cin, "stem: input channels do not match the conv weight"
+            patches = K.patch_pack(x0.contiguous(), x1c, tc, None if extra is None else extra.float().contiguous())
 
         def make():
             wp = torch.zeros((cout, 64), dtype=T16, device=w.device)
@@ -286,19 +292,19 @@ class _Stem(torch.autograd.Function):
     def backward(ctx, g):
         (patches,) = ctx.saved_tensors
         g = g.contiguous()
-        cout = g.shape[3]
+        cout, cin = g.shape[3], ctx.wshape[1]
         dw = torch.zeros((1, cout, 64), dtype=torch.float32, device=g.device)
         K.conv_wgrad(g, K.convert16(patches, K.ACT, K.GRAD), 1, 1, dw)
-        d_w = dw[0, :, :27].reshape(cout, 9, 3).permute(0, 2, 1).reshape(ctx.wshape).contiguous()
+        d_w = dw[0, :, :9 * cin].reshape(cout, 9, cin).permute(0, 2, 1).reshape(ctx.wshape).contiguous()
         d_b = torch.zeros(cout, dtype=torch.float32, device=g.device)
         K.channel_sum(g, d_b)
-        return None, None, None, d_w, d_b, None
+        return None, None, None, d_w, d_b, None, None
 
 
-def stem_conv(x0, w, b, x1=None, t=None):
-    assert w.shape[1] == 3 and tuple(w.shape[2:]) == (3, 3), "stem expects a 3-channel 3x3 conv"
+def stem_conv(x0, w, b, x1=None, t=None, extra=None):
+    assert w.shape[1] in (3, 4) and tuple(w.shape[2:]) == (3, 3), "stem expects a 3- or 4-channel 3x3 conv"
     box = []
-    return _tag(_Stem.apply(x0, x1, t, w, b, box), box)
+    return _tag(_Stem.apply(x0, x1, t, w, b, box, extra), box)
 
 
 class _HeadConv(torch.autograd.Function):
@@ -361,6 +367,33 @@ class _FMLoss(torch.autograd.Function):
 
 def fm_loss(v, x0, x1):
     return _FMLoss.apply(v, x0, x1)
+
+
+class _FMLossWeighted(torch.autograd.Function):
+    """sum(w (v - (x1 - x0))^2) / (sum(w) + 1e-8), w = 1 + lam * mask (conditional_flow_matching_masked.py:76-92)."""
+
+    @staticmethod
+    def forward(ctx, v, x0, x1, mask, lam):
+        sums, dv = K.fm_loss_weighted(v.contiguous(), x0.contiguous(), x1.contiguous(), mask.contiguous(), lam, True)
+        inv = 1.0 / (sums[1] + 1e-8)
+        ctx.save_for_backward(dv, inv)
+        return sums[0] * inv
+
+    @staticmethod
+    def backward(ctx, g):
+        dv, inv = ctx.saved_tensors
+        return dv * (g * inv), None, None, None, None
+
+
+def fm_loss_weighted(v, x0, x1, mask, lam: float):
+    return _FMLossWeighted.apply(v, x0, x1, mask, float(lam))
+
+
+def roi_charbonnier(x0, x1, t, mask, eps_charb: float = 1e-3, eps_area: float = 1e-8):
+    """(charb(xt - x1) * m).sum() / (m.sum() * C + eps_area) (conditional_flow_matching_ROI_loss.py:80-92); no gradient:
+    the term depends on the data only."""
+    sums = K.roi_charbonnier(x0.contiguous(), x1.contiguous(), t.float().contiguous(), mask.float().contiguous(), eps_charb)
+    return sums[0] / (sums[1] * x0.shape[1] + eps_area)
 
 
 # --------------------------------------------------------------------------------------------- opaque <-> real dtype glue

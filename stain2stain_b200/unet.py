@@ -306,11 +306,17 @@ class RawUNetModel(nn.Module):
         """x: fp32 NCHW image batch (CUDA).  Returns the velocity, fp32 NCHW, like the reference."""
         return self._run(t, x, y)
 
-    def _run(self, t, x, y=None, x1=None, axpy_a: Optional[float] = None):
+    def _run(self, t, x, y=None, x1=None, axpy_a: Optional[float] = None, extra=None):
+        """`extra`: optional fp32 [B,1,H,W] condition channel appended behind x's channels inside the stem operand
+        packing (the mask of the mask-conditioned variants; `torch.cat([x, mask], 1)` is never materialised)."""
         if not x.is_cuda:
             raise RuntimeError("stain2stain_b200.UNetModel runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if self.in_channels != 3:
-            raise NotImplementedError("the B200 stem kernel is specialised for 3-channel tiles (reference configs 1-4)")
+        if self.in_channels not in (3, 4):
+            raise NotImplementedError("the B200 stem kernel takes 3- or 4-channel tiles (reference configs 1-4 and the "
+                                      "mask-conditioned variants)")
+        if x.shape[1] + (0 if extra is None else 1) != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[1]}"
+                             + ("" if extra is None else " + 1 condition channel"))
         in_dtype = x.dtype
         x = x.float().contiguous()
         emb_act = self._embed(t, x, y)
@@ -321,7 +327,7 @@ class RawUNetModel(nn.Module):
             while tt.dim() > 1:
                 tt = tt[:, 0]
             tt = tt.to(x.device).float()
-        h = ops.stem_conv(x, stem.weight, stem.bias, x1=None if x1 is None else x1.float(), t=tt)
+        h = ops.stem_conv(x, stem.weight, stem.bias, x1=None if x1 is None else x1.float(), t=tt, extra=extra)
         a = self._trunk(h, emb_act)
         head = self.out[2]
         if axpy_a is not None:  # inference-only fused Euler update, in place on x
@@ -329,14 +335,15 @@ class RawUNetModel(nn.Module):
         return ops.head_conv(a, head.weight, head.bias).to(in_dtype)
 
     @torch.no_grad()
-    def euler_step_(self, t, x, dt: float, y=None):
+    def euler_step_(self, t, x, dt: float, y=None, extra=None):
         """x <- x + dt * v(t, x) with the update fused into the head conv's epilogue (x: fp32 NCHW contiguous)."""
         assert x.dtype == torch.float32 and x.is_contiguous()
-        return self._run(t, x, y, axpy_a=dt)
+        assert x.shape[1] == self.out_channels, "the fused Euler update needs state channels == out_channels"
+        return self._run(t, x, y, axpy_a=dt, extra=extra)
 
-    def velocity_of_interpolant(self, t, x0, x1, y=None):
+    def velocity_of_interpolant(self, t, x0, x1, y=None, extra=None):
         """v(t, (1-t) x0 + t x1) with the interpolation fused into the stem operand packing (training path)."""
-        return self._run(t, x0, y, x1=x1)
+        return self._run(t, x0, y, x1=x1, extra=extra)
 
 
 def default_channel_mult(image_size: int):

@@ -141,3 +141,79 @@ def test_reference_bridge_matches_fixtures_when_reference_is_present():
     se = rb.reference_module("src.models.components.shared_encoder")
     t = torch.rand(4)
     assert torch.equal(se.TimeEmbedding(64)(t), omt.TimeEmbedding(64)(t))
+
+
+# ---- mask / ROI variants: the four reference LitModules, executed unmodified, pinned the oracle
+_MASK_STEP = {
+    "mask_weighted": lambda net, b, t=None: oflow.model_step_mask_weighted(net, oflow.ConditionalFlowMatcher(0.0), b, t=t),
+    "roi_loss": lambda net, b, t=None: oflow.model_step_roi(net, oflow.ConditionalFlowMatcher(0.0), b, t=t),
+    "mask_conditioned": lambda net, b, t=None: oflow.model_step_mask_conditioned(net, oflow.ConditionalFlowMatcher(0.0), b, t=t),
+    "mask_toggle": lambda net, b, t=None: oflow.model_step_mask_conditioned(net, oflow.ConditionalFlowMatcher(0.0), b, t=t),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_MASK_STEP))
+def test_oracle_reproduces_reference_mask_variants(name):
+    torch.set_num_threads(1)
+    gold = load("mask_variants_small.pt")
+    rec = gold[name]
+    raw4 = name in ("mask_conditioned", "mask_toggle")
+    torch.manual_seed(gold["weight_seed"])
+    net = ounet.RawUNetModel(**gold["configs"]["raw4"]) if raw4 else ounet.UNetModel(**gold["configs"]["simple"])
+    net = ounet.dezero_(net, seed=gold["dezero_seed"]).eval()
+    check_sums(net, rec["checksums"], prefix="net.")
+    inp = inputs(gold["input_seed"], 2, 64, mask_classes=2)
+    x0, x1, mask = inp["x0"], inp["x1"], inp["mask"]
+    assert float(mask.sum()) == gold["inputs_check"]["mask"]
+    with torch.no_grad():
+        v = net(inp["t"], torch.cat([x0, mask], 1)) if raw4 else net(inp["t"], x0)
+    assert torch.allclose(v, rec["forward"], atol=1e-6)
+    ms = rec["model_step"]
+    torch.manual_seed(ms["rng_seed"])
+    loss = _MASK_STEP[name](net, (x0, x1, mask))
+    assert torch.allclose(loss, ms["loss"], rtol=1e-6)
+    net.zero_grad()
+    loss.backward()
+    for k, p in net.named_parameters():
+        ref = ms["grad_norms"]["net." + k]
+        assert abs(float(p.grad.double().norm()) - ref) <= 1e-4 * max(ref, 1e-8), k
+    if name == "mask_toggle":
+        for ts in rec["training_step"]:
+            torch.manual_seed(ts["rng_seed"])
+            lt = oflow.model_step_mask_conditioned(net, oflow.ConditionalFlowMatcher(0.0), (x0, x1, mask), use_mask_toggle=True)
+            assert torch.allclose(lt, ts["loss"], rtol=1e-6), ts["toggled"]
+    if raw4:
+        gen = oflow.generate_mask_conditioned(net, x0[:1], mask[:1], num_steps=2, zero_mask=(name == "mask_toggle"))
+    else:
+        gen = oflow.generate(net, x0[:1], num_steps=2)
+    assert torch.allclose(gen, rec["generate_num_steps2"], atol=1e-5)
+
+
+def test_mask_variant_litmodules_follow_the_reference_on_a_cpu_net():
+    """Host logic of stain2stain_b200/lit_masked.py (generic path, any nn.Module net): same losses as the reference."""
+    from stain2stain_b200.lit_masked import (MaskConditionedFlowMatchingLitModule, MaskToggleFlowMatchingLitModule,
+                                             MaskWeightedFlowMatchingLitModule, ROILossFlowMatchingLitModule)
+    torch.set_num_threads(1)
+    gold = load("mask_variants_small.pt")
+    inp = inputs(gold["input_seed"], 2, 64, mask_classes=2)
+    batch = (inp["x0"], inp["x1"], inp["mask"])
+    classes = dict(mask_weighted=MaskWeightedFlowMatchingLitModule, roi_loss=ROILossFlowMatchingLitModule,
+                   mask_conditioned=MaskConditionedFlowMatchingLitModule, mask_toggle=MaskToggleFlowMatchingLitModule)
+    for name, cls in classes.items():
+        raw4 = name in ("mask_conditioned", "mask_toggle")
+        torch.manual_seed(gold["weight_seed"])
+        net = ounet.RawUNetModel(**gold["configs"]["raw4"]) if raw4 else ounet.UNetModel(**gold["configs"]["simple"])
+        net = ounet.dezero_(net, seed=gold["dezero_seed"]).eval()
+        lit = cls(net=net, flow_matcher=oflow.ConditionalFlowMatcher(0.0),
+                  solver=functools.partial(oflow.NeuralODE, solver="dopri5"), optimizer=functools.partial(torch.optim.Adam, lr=1e-4),
+                  scheduler=None, log_images=False)
+        ms = gold[name]["model_step"]
+        torch.manual_seed(ms["rng_seed"])
+        assert torch.allclose(lit.model_step(batch), ms["loss"], rtol=1e-6), name
+        if name == "mask_toggle":
+            for ts in gold[name]["training_step"]:
+                torch.manual_seed(ts["rng_seed"])
+                assert torch.allclose(lit.training_step(batch, 0), ts["loss"], rtol=1e-6)
+        with pytest.raises(ValueError):
+            cls(net=net, flow_matcher=oflow.ConditionalFlowMatcher(0.0), solver=None).generate(
+                *((inp["x0"], inp["mask"]) if raw4 else (inp["x0"],)))
