@@ -43,6 +43,18 @@ def _peaks():
     return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
 
 
+def _conv_traffic():
+    """DRAM bytes per conv launch from the committed `ncu --set full` capture (profiles/), next to the algorithmic bytes
+    of the same launches -- `roofline.traffic`.  None if the capture is not in the tree."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d["traffic_per_launch"], {"algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "ratio": d["ratio"],
+                                     "source": "profiles/r01_conv_traffic.json (ncu --set full, kbench conv shapes at B=32)"}
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -239,8 +251,10 @@ def run_train(args, rank, world, local):
         if "conv_igemm" in prof:
             c = prof["conv_igemm"]
             ach = c["flops"] / (c["ms"] / 1e3) / 1e12
+            traffic, traffic_note = _conv_traffic()
             roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (fwd + dgrad implicit GEMM)", "achieved": ach,
-                    "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+                    "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": pk["src"] + " bf16_tflops_sustained", "launches_per_step": c["launches"],
                     "kernel_ms_per_step": c["ms"], "share_of_step": c["ms"] / step_ms,
                     "algorithmic_flops_per_step": c["flops"]}
@@ -294,6 +308,7 @@ def run_sample(args, rank, world, local):
     e1.record()
     _barrier(world)
     ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = K.LAUNCHES[0]
     clocks = sampler.stop() if rank == 0 else None
     _barrier(world)
     e0.record()
@@ -317,7 +332,8 @@ def run_sample(args, rank, world, local):
                    "l2": "activations of one evaluation (>1 GB) exceed L2"},
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
                 "d2h_bytes_per_step": B * 3 * 256 * 256 * 4},
-        "gpu_launches": "CUDA graph replays: %d x %d-kernel graph" % (evals * args.steps, 0),
+        "gpu_launches": launches,
+        "gpu_launches_note": "own kernels inside the CUDA-graph replays (%d replays per step)" % evals,
         "roofline": {"bound": "tensor", "kernel": "whole velocity evaluation (conv_igemm dominated)", "achieved": ach,
                      "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
                      "peak_source": pk["src"] + " bf16_tflops_sustained"},

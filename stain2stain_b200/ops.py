@@ -28,11 +28,17 @@ class _PackCache:
         return tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws)
 
     def get(self, key: tuple, ws: Sequence[torch.Tensor], make):
+        """`make(dst)` packs into `dst` when given (the previous operand of the same parameters: same shapes, same
+        device -- an optimizer step only changed the values, and the zero padding is never written), else allocates."""
         sig = self._sig(ws)
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
-        val = make()
+        dst = None
+        if hit is not None and len(hit[0]) == len(sig) and all(a[2] == b[2] for a, b in zip(hit[0], sig)) and \
+                hit[1].device == ws[0].device:
+            dst = hit[1]
+        val = make(dst)
         self._store[key] = (sig, val)
         return val
 
@@ -70,8 +76,9 @@ class ConvPlan:
         return sum(s.taps * ((s.ci_count + 63) // 64 * 64) for s in self.segs)
 
     def packed_fwd(self, weights: Sequence[torch.Tensor]) -> torch.Tensor:
-        def make():
-            wp = torch.zeros((K.padded_rows(self.cout), self.ktot()), dtype=T16, device=weights[0].device)
+        def make(dst):
+            wp = dst if dst is not None else \
+                torch.zeros((K.padded_rows(self.cout), self.ktot()), dtype=T16, device=weights[0].device)
             off = 0
             for s in self.segs:
                 K.pack_conv_weight(weights[s.weight].detach(), wp, k_off=off, ci_begin=s.ci_begin, ci_count=s.ci_count)
@@ -83,8 +90,8 @@ class ConvPlan:
         s = self.segs[si]
         w = weights[s.weight]
 
-        def make():
-            wd = torch.zeros((s.ci_count, s.taps * self.cout), dtype=T16, device=w.device)
+        def make(dst):
+            wd = dst if dst is not None else torch.zeros((s.ci_count, s.taps * self.cout), dtype=T16, device=w.device)
             K.pack_conv_weight(w.detach(), wd, ci_begin=s.ci_begin, ci_count=s.ci_count, transpose_flip=True,
                                fmt=K.GRAD)
             return wd
@@ -275,8 +282,8 @@ class _Stem(torch.autograd.Function):
             assert x0.shape[1] + (extra is not None) == cin, "stem: input channels do not match the conv weight"
             patches = K.patch_pack(x0.contiguous(), x1c, tc, None if extra is None else extra.float().contiguous())
 
-        def make():
-            wp = torch.zeros((cout, 64), dtype=T16, device=w.device)
+        def make(dst):
+            wp = dst if dst is not None else torch.zeros((cout, 64), dtype=T16, device=w.device)
             K.pack_conv_weight(w.detach(), wp)
             return wp
         wp = PACK_CACHE.get(("stem", id(w)), [w], make)
@@ -314,8 +321,8 @@ class _HeadConv(torch.autograd.Function):
     def forward(ctx, a, w, b, axpy_x, axpy_a):
         cout, cin = w.shape[0], w.shape[1]
 
-        def make():
-            wp = torch.zeros((16, 9 * cin), dtype=T16, device=w.device)
+        def make(dst):
+            wp = dst if dst is not None else torch.zeros((16, 9 * cin), dtype=T16, device=w.device)
             K.pack_conv_weight(w.detach(), wp)
             return wp
         wp = PACK_CACHE.get(("head", id(w)), [w], make)
@@ -539,8 +546,8 @@ class _Head1x1(torch.autograd.Function):
     def forward(ctx, a, w, b):
         cout, cin = w.shape[0], w.shape[1]
 
-        def make():
-            wp = torch.zeros((16, (cin + 63) // 64 * 64), dtype=T16, device=w.device)
+        def make(dst):
+            wp = dst if dst is not None else torch.zeros((16, (cin + 63) // 64 * 64), dtype=T16, device=w.device)
             K.pack_conv_weight(w.detach(), wp)
             return wp
         wp = PACK_CACHE.get(("head1x1", id(w)), [w], make)
