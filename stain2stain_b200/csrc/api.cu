@@ -83,7 +83,8 @@ int wgrad_pairs() {  // S2S_WGRAD_2CTA=0 forces the single-CTA wgrad kernel
     return v;
 }
 
-int conv_halo() {  // S2S_CONV_HALO: 0 = off, 1 = halo-tiled A operand (matrix base offset set), 2 = same without base offset
+int conv_halo() {  // S2S_CONV_HALO: 0 = off, 1 = halo-tiled A operand (matrix base offset set), 2 = same without base offset,
+                   // 3 = three column-shifted halo boxes per channel block (all descriptors 1024 B aligned)
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("S2S_CONV_HALO");
@@ -285,12 +286,15 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             Conv3Params q;
             memset(&q, 0, sizeof(q));
             const int BN3 = (Cout % 256 == 0) ? 256 : 128;
-            const int mt3 = (BN3 == 128 && Hout >= 2 * kHaloTH) ? 2 : 1;
+            const bool cols3 = conv_halo() == 3;
+            const int mt3 = (!cols3 && BN3 == 128 && Hout >= 2 * kHaloTH) ? 2 : 1;
+            q.cols3 = cols3 ? 1 : 0;
             q.nseg = nsrc;
             int kb3 = 0;
             for (int s = 0; s < nsrc; ++s) {
                 const s2s_conv_src& sc = srcs[s];
-                int rc = sc.taps == 9 ? make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, kHaloPitch, kHaloTH * mt3 + 2)
+                int rc = sc.taps == 9 ? make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, cols3 ? kHaloTW : kHaloPitch,
+                                                          kHaloTH * mt3 + 2)
                                       : make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, kHaloTW, kHaloTH);
                 if (rc) return rc;
                 q.seg[s].taps = sc.taps;
@@ -323,13 +327,14 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             q.bias = bias;
             q.residual = (const __nv_bfloat16*)residual;
             q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
-            const size_t halo_bytes = (size_t)(kHaloTH * mt3 + 2) * kHaloPitch * 128;
+            const size_t halo_bytes = cols3 ? (size_t)3 * (kHaloTH * mt3 + 2) * kHaloTW * 128
+                                            : (size_t)(kHaloTH * mt3 + 2) * kHaloPitch * 128;
             size_t a_slot = halo_bytes > (size_t)mt3 * kABytes ? halo_bytes : (size_t)mt3 * kABytes;
             a_slot = (a_slot + 1023) / 1024 * 1024;
             q.a_slot = (uint32_t)a_slot;
             const size_t b_bytes = (size_t)(BN3 / 2) * kBlockK * 2;
             const size_t fixed = 2 * kOutStageBytes + 1024 + 1024;
-            q.sa = 3;
+            q.sa = cols3 ? 2 : 3;
             int sb = (int)((kSmemBudget - fixed - (size_t)q.sa * a_slot) / b_bytes);
             if (sb > 8) sb = 8;
             if (sb < 2) return fail(S2S_ERR_INVALID, "conv_fwd(halo): tile does not fit in shared memory");

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // 1024 B alignment is required by the 128 B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const int BN = p.BN;
     const uint32_t b_bytes = (uint32_t)(BN < 64 ? 64 : BN) * kBlockK * 2;  // B region per stage (>= 8 KB keeps 1 KB alignment)
     const int MT = p.mt;
@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================================== TMA producer (whole warp, elected issue)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -150,11 +150,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             mbar_wait(&empty[stage], phase ^ 1);
                             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
                             uint8_t* b_dst = a_dst + a_bytes;
-                            mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)BN * kBlockK * 2);
-                            for (int h = 0; h < MT; ++h)
-                                tma_load_5d(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp,
-                                            cy + h * kTileH, b);
-                            tma_load_2d(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)BN * kBlockK * 2);
+                                for (int h = 0; h < MT; ++h)
+                                    tma_load_5d(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp,
+                                                cy + h * kTileH, b);
+                                tma_load_2d(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                            }
+                            __syncwarp();
                             if (++stage == S) {
                                 stage = 0;
                                 phase ^= 1;
@@ -165,8 +168,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (whole warp, elected issue)
+        {
             const uint32_t idesc = umma_idesc_16b(kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
             const uint32_t idesc_half = umma_idesc_16b(kTileM, (uint32_t)(BN / 2), 0, 0, p.a_fmt, p.w_fmt);
             int stage = 0;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
                                 const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                                umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                if (elect_one()) umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                         }
                     } else if (MT == 2) {
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
-                                umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                if (elect_one()) umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                         }
                     } else {
@@ -212,17 +215,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const uint64_t db = umma_smem_desc_sw128(b_addr + j * hb * 128 + k * 32, 16, 1024);
-                                umma_bf16(d_tmem + j * hb, da, db, idesc_half, (kb | k) != 0 ? 1u : 0u);
+                                if (elect_one()) umma_bf16(d_tmem + j * hb, da, db, idesc_half, (kb | k) != 0 ? 1u : 0u);
                             }
                         }
                     }
-                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    if (elect_one()) umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    __syncwarp();
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[as]);  // accumulator complete
+                if (elect_one()) umma_commit(&tfull[as]);  // accumulator complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -375,13 +380,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     conv_igemm_pair_kernel(const __grid_constant__ Conv2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform, and the role branches below stay convergent
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int BN = p.BN, HB = p.BN / 2;
     constexpr uint32_t a_bytes = (uint32_t)MT * kABytes;
     const uint32_t b_bytes = (uint32_t)HB * kBlockK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int S = p.num_stages;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = blockIdx.x & 1u;  // == %cluster_ctarank for __cluster_dims__(2,1,1) on a 1-D grid (uniform)
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
@@ -433,7 +439,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
-        if (lane == 0) {
+        // whole warp, convergent; one elected lane issues (see the MMA issuer below for why)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters) {
@@ -463,12 +470,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             mbar_wait(&empty[stage], phase ^ 1);
                             uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
                             uint8_t* b_dst = a_dst + a_bytes;
-                            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
+                            if (elect_one()) {
+                                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
 #pragma unroll
-                            for (int h = 0; h < MT; ++h)
-                                tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx, cp,
-                                                 cy + h * kTileH, b);
-                            tma_load_2d_2cta(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                                for (int h = 0; h < MT; ++h)
+                                    tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &full[stage], coff + cb * kBlockK, cx,
+                                                     cp, cy + h * kTileH, b);
+                                tma_load_2d_2cta(b_dst, &p.tmW, &full[stage], kb * kBlockK, n0);
+                            }
+                            __syncwarp();
                             if (++stage == S) {
                                 stage = 0;
                                 phase ^= 1;
@@ -480,7 +490,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (leader CTA only)
-        if (lane == 0 && leader) {
+        // The WHOLE warp runs this loop (convergent code: stage / descriptor arithmetic lives in uniform registers) and one
+        // elected lane issues each tcgen05 instruction.  Issuing from inside `if (lane == 0)` makes every operand
+        // "potentially divergent": the compiler then wraps each MMA in an elect / R2UR.BROADCAST loop of ~20
+        // instructions, and the M256 x N128 x K16 MMA (64 tensor cycles) becomes issue-bound.
+        if (leader) {
             const uint32_t idesc = umma_idesc_16b(2 * kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
             int stage = 0;
             uint32_t phase = 0;
@@ -496,22 +510,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = a_addr + a_bytes;
+                    const uint64_t da0 = umma_smem_desc_sw128(a_addr, 16, 1024);
+                    const uint64_t db0 = umma_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
 #pragma unroll
                         for (int h = 0; h < MT; ++h) {  // consecutive MMAs alternate between the sub-tiles' accumulators
-                            const uint64_t da = umma_smem_desc_sw128(a_addr + h * kABytes + k * 32, 16, 1024);
-                            umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            // start-address field is (addr >> 4): advancing by k*32 B / h*16 KB is a plain add
+                            const uint64_t da = da0 + (uint64_t)((h * kABytes + k * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)((k * 32) >> 4);
+                            if (elect_one())
+                                umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit_2cta(&empty[stage], 0x3);  // frees the slot in BOTH CTAs
+                    if (elect_one()) umma_commit_2cta(&empty[stage], 0x3);  // frees the slot in BOTH CTAs
+                    __syncwarp();
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit_2cta(&tfull[as], 0x3);
+                if (elect_one()) umma_commit_2cta(&tfull[as], 0x3);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -686,6 +706,8 @@ struct Conv3Params {
     int BN, sa, sb;            // A / B ring depths
     uint32_t a_slot, tmem_cols;
     int base_off_mode;
+    int cols3;                 // 1: three column-shifted halo boxes {64, 8, 1, 16*MT+2, 1} per channel block (dx = -1, 0, +1):
+                               // every tap's A descriptor is 1024 B aligned with an 8-row-group stride of exactly 1024 B
     const float* bias;
     const __nv_bfloat16* residual;
     int a_fmt, w_fmt, out_fmt, res_fmt;
@@ -696,12 +718,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     conv_halo_pair_kernel(const __grid_constant__ Conv3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const int BN = p.BN, HB = p.BN / 2;
     const uint32_t b_bytes = (uint32_t)HB * kBlockK * 2;
-    constexpr uint32_t halo_bytes = (uint32_t)(kHaloTH * MT + 2) * kHaloPitch * 128;
+    constexpr uint32_t box3_bytes = (uint32_t)(kHaloTH * MT + 2) * kHaloTW * 128;  // one column-shifted box (cols3)
+    const uint32_t halo_bytes = p.cols3 ? 3u * box3_bytes : (uint32_t)(kHaloTH * MT + 2) * kHaloPitch * 128;
     const int SA = p.sa, SB = p.sb;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = blockIdx.x & 1u;  // == %cluster_ctarank for __cluster_dims__(2,1,1) on a 1-D grid (uniform)
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
@@ -774,7 +797,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                         uint8_t* a_dst = ringA + (size_t)ia * p.a_slot;
                         if (sg.taps == 9) {
                             if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * halo_bytes);
-                            tma_load_5d_2cta(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
+                            if (p.cols3) {
+#pragma unroll
+                                for (int j = 0; j < 3; ++j)
+                                    tma_load_5d_2cta(a_dst + j * box3_bytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1 + j, 0,
+                                                     y0 - 1, b);
+                            } else {
+                                tma_load_5d_2cta(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
+                            }
                         } else {
                             if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * MT * kABytes);
 #pragma unroll
@@ -823,10 +853,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             mbar_wait(&fullB[ib], phb);
                             tc_fence_after();
                             const uint32_t b_addr = smem_u32(ringB + (size_t)ib * b_bytes);
-                            const uint32_t tap_off =
-                                sg.taps == 9 ? (uint32_t)(((tap / 3) * kHaloPitch + (tap % 3)) * 128) : 0u;
-                            const uint32_t a_sbo = sg.taps == 9 ? (uint32_t)(kHaloPitch * 128) : 1024u;
-                            const uint32_t a_sub = sg.taps == 9 ? (uint32_t)(kHaloTH * kHaloPitch * 128) : (uint32_t)kABytes;
+                            uint32_t tap_off = 0u, a_sbo = 1024u, a_sub = (uint32_t)kABytes;
+                            if (sg.taps == 9 && p.cols3) {
+                                tap_off = (uint32_t)(tap % 3) * box3_bytes + (uint32_t)(tap / 3) * 1024u;
+                                a_sub = (uint32_t)(kHaloTH * 1024);
+                            } else if (sg.taps == 9) {
+                                tap_off = (uint32_t)(((tap / 3) * kHaloPitch + (tap % 3)) * 128);
+                                a_sbo = (uint32_t)(kHaloPitch * 128);
+                                a_sub = (uint32_t)(kHaloTH * kHaloPitch * 128);
+                            }
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
@@ -973,7 +1008,7 @@ struct WgradParams {
 __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const int BN = p.BN;
     const uint32_t a_bytes = 2 * kABytes;                 // M = 128 -> two 64-channel atoms
     const uint32_t b_bytes = (uint32_t)(BN / 64) * kABytes;
@@ -1021,7 +1056,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {  // whole warp, convergent; one elected lane issues the TMA loads
             int sx = 0, sy = 0, cp = 0, coff = 0;
             if (p.taps == 9) {
                 const int dx = tap % 3, dy = tap / 3;
@@ -1046,11 +1081,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
                 uint8_t* b_dst = a_dst + a_bytes;
-                mbar_arrive_expect_tx(&full[stage], stage_bytes);
-                tma_load_5d(a_dst, &p.tmP, &full[stage], mt * 128, x0, 0, y0, b);
-                tma_load_5d(a_dst + kABytes, &p.tmP, &full[stage], mt * 128 + 64, x0, 0, y0, b);
-                for (int j = 0; j < BN / 64; ++j)
-                    tma_load_5d(b_dst + j * kABytes, &p.tmQ, &full[stage], coff + nt * BN + j * 64, x0 + sx, cp, y0 + sy, b);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                    tma_load_5d(a_dst, &p.tmP, &full[stage], mt * 128, x0, 0, y0, b);
+                    tma_load_5d(a_dst + kABytes, &p.tmP, &full[stage], mt * 128 + 64, x0, 0, y0, b);
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_5d(b_dst + j * kABytes, &p.tmQ, &full[stage], coff + nt * BN + j * 64, x0 + sx, cp, y0 + sy,
+                                    b);
+                }
+                __syncwarp();
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1;
@@ -1058,7 +1097,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nk > 0) {
+        if (nk > 0) {  // whole warp, convergent; one elected lane issues each tcgen05 instruction
             const uint32_t idesc = umma_idesc_16b(128, (uint32_t)BN, 1, 1, p.p_fmt, p.q_fmt);
             const uint32_t idesc_half = umma_idesc_16b(128, (uint32_t)(BN / 2), 1, 1, p.p_fmt, p.q_fmt);
             int stage = 0;
@@ -1073,7 +1112,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
                     for (int kk = 0; kk < kTileM / 16; ++kk) {  // 16 pixels per MMA
                         const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
                         const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
-                        umma_bf16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                        if (elect_one()) umma_bf16(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
                     }
                 } else {
                     const uint32_t hb = (uint32_t)(BN / 2);  // N halves = whole 64-channel atoms of the Q tile
@@ -1083,17 +1122,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint64_t db = umma_smem_desc_sw128(b_addr + j * (hb / 64) * kABytes + kk * 2048, kABytes, 1024);
-                            umma_bf16(tmem_base + j * hb, da, db, idesc_half, (k | kk) != 0 ? 1u : 0u);
+                            if (elect_one()) umma_bf16(tmem_base + j * hb, da, db, idesc_half, (k | kk) != 0 ? 1u : 0u);
                         }
                     }
                 }
-                umma_commit(&empty[stage]);
+                if (elect_one()) umma_commit(&empty[stage]);
+                __syncwarp();
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit(tfull);
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
         }
     } else if (warp >= 4 && nk > 0) {
         const int q = warp & 3;
@@ -1153,13 +1194,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     conv_wgrad_pair_kernel(const __grid_constant__ Wgrad2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const int BN = p.BN;
     const int q_atoms = BN / 128;                           // 64-channel atoms of the X half this CTA stages
     const uint32_t a_bytes = 2 * kABytes;                   // 128 dY channels
     const uint32_t stage_bytes = a_bytes + (uint32_t)q_atoms * kABytes;
     const int S = p.num_stages;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = blockIdx.x & 1u;  // == %cluster_ctarank for __cluster_dims__(2,1,1) on a 1-D grid (uniform)
     const bool leader = rank == 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
     uint64_t* full = bars;
@@ -1200,7 +1241,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {  // whole warp, convergent; one elected lane issues the TMA loads
             int sx = 0, sy = 0, cp = 0, coff = 0;
             if (p.taps == 9) {
                 const int dx = tap % 3, dy = tap / 3;
@@ -1227,11 +1268,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
                 uint8_t* b_dst = a_dst + a_bytes;
-                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
-                tma_load_5d_2cta(a_dst, &p.tmP, &full[stage], m0, x0, 0, y0, b);
-                tma_load_5d_2cta(a_dst + kABytes, &p.tmP, &full[stage], m0 + 64, x0, 0, y0, b);
-                for (int j = 0; j < q_atoms; ++j)
-                    tma_load_5d_2cta(b_dst + j * kABytes, &p.tmQ, &full[stage], n0 + j * 64, x0 + sx, cp, y0 + sy, b);
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * stage_bytes);
+                    tma_load_5d_2cta(a_dst, &p.tmP, &full[stage], m0, x0, 0, y0, b);
+                    tma_load_5d_2cta(a_dst + kABytes, &p.tmP, &full[stage], m0 + 64, x0, 0, y0, b);
+                    for (int j = 0; j < q_atoms; ++j)
+                        tma_load_5d_2cta(b_dst + j * kABytes, &p.tmQ, &full[stage], n0 + j * 64, x0 + sx, cp, y0 + sy, b);
+                }
+                __syncwarp();
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1;
@@ -1239,7 +1283,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader && nk > 0) {
+        if (leader && nk > 0) {  // whole warp, convergent; one elected lane issues each tcgen05 instruction
             const uint32_t idesc = umma_idesc_16b(256, (uint32_t)BN, 1, 1, p.p_fmt, p.q_fmt);
             int stage = 0;
             uint32_t phase = 0;
@@ -1252,15 +1296,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 for (int kk = 0; kk < kTileM / 16; ++kk) {
                     const uint64_t da = umma_smem_desc_sw128(a_addr + kk * 2048, kABytes, 1024);
                     const uint64_t db = umma_smem_desc_sw128(b_addr + kk * 2048, kABytes, 1024);
-                    umma_bf16_2cta(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                    if (elect_one()) umma_bf16_2cta(tmem_base, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
                 }
-                umma_commit_2cta(&empty[stage], 0x3);
+                if (elect_one()) umma_commit_2cta(&empty[stage], 0x3);
+                __syncwarp();
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit_2cta(tfull, 0x3);
+            if (elect_one()) umma_commit_2cta(tfull, 0x3);
+            __syncwarp();
         }
     } else if (warp >= 4 && nk > 0) {
         const int q = warp & 3;
