@@ -65,8 +65,11 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                  const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
                  void* stream);
-/* Sub-tiles per sample of the epilogue statistics for this output geometry; 0 = not available (use s2s_gn_stats). */
+/* Sub-tiles per sample of the epilogue statistics for this output geometry; 0 = not available (use s2s_gn_stats).
+ * s2s_conv_stat_tiles: the plain CTA-pair kernel's geometry; s2s_conv_stat_tiles_for: the geometry of the kernel
+ * s2s_conv_fwd will pick for these segments (the halo-tiled pair kernel takes stride-1 convs with a 3x3 segment). */
 int s2s_conv_stat_tiles(int Hout, int Wout, int Cout);
+int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout);
 
 /* Weight gradient of one conv segment (tcgen05, split-K over pixels, fp32 reductions):
  *   dw[tap][m][n_off + n] += sum_{b,y,x} dy[b,y,x,m] * x[b, y*stride+dy, x*stride+dx, n]

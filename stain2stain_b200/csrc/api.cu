@@ -88,7 +88,7 @@ int conv_halo() {  // S2S_CONV_HALO: 0 = off, 1 = halo-tiled A operand (matrix b
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("S2S_CONV_HALO");
-        v = e ? atoi(e) : 0;
+        v = e ? atoi(e) : 2;  // default: halo-tiled CTA-pair kernel for every stride-1 conv with a 3x3 segment
     }
     return v;
 }
@@ -256,18 +256,44 @@ static bool pair_geometry(int Hout, int Wout, int Cout, int* BN, int* mt, int* t
     return true;
 }
 
+// the halo-tiled CTA-pair kernel takes stride-1 convs with at least one 3x3 segment (1x1 segments ride along)
+static bool halo_eligible(const s2s_conv_src* srcs, int nsrc, int Cout) {
+    if (!conv_halo() || !conv_pairs() || Cout % 128 != 0 || !srcs) return false;
+    bool any3 = false;
+    for (int s = 0; s < nsrc; ++s) {
+        if (srcs[s].stride != 1 || (srcs[s].taps != 1 && srcs[s].taps != 9)) return false;
+        any3 = any3 || srcs[s].taps == 9;
+    }
+    return any3;
+}
+static void halo_geometry(int Hout, int Wout, int Cout, int* BN, int* mt, int* tiles_x, int* tiles_y) {
+    *BN = (Cout % 256 == 0) ? 256 : 128;
+    *mt = (conv_halo() != 3 && *BN == 128 && Hout >= 2 * kHaloTH) ? 2 : 1;
+    *tiles_x = (Wout + kHaloTW - 1) / kHaloTW;
+    *tiles_y = (Hout + kHaloTH * *mt - 1) / (kHaloTH * *mt);
+}
+
 int s2s_conv_stat_tiles(int Hout, int Wout, int Cout) {
     int BN, mt, tx, ty;
-    if (conv_halo() || !pair_geometry(Hout, Wout, Cout, &BN, &mt, &tx, &ty)) return 0;
+    if (!pair_geometry(Hout, Wout, Cout, &BN, &mt, &tx, &ty)) return 0;
     return tx * ty * mt;
+}
+
+int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout) {
+    int BN, mt, tx, ty;
+    if (halo_eligible(srcs, nsrc, Cout)) {
+        halo_geometry(Hout, Wout, Cout, &BN, &mt, &tx, &ty);
+        return tx * ty * mt;
+    }
+    return s2s_conv_stat_tiles(Hout, Wout, Cout);
 }
 
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                  const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
                  void* stream) {
-    if (stats_out && (!out_bf16 || s2s_conv_stat_tiles(Hout, Wout, Cout) == 0))
-        return fail(S2S_ERR_INVALID, "conv_fwd: epilogue statistics need the CTA-pair path (s2s_conv_stat_tiles() > 0)");
+    if (stats_out && (!out_bf16 || axpy_x || s2s_conv_stat_tiles_for(srcs, nsrc, Hout, Wout, Cout) == 0))
+        return fail(S2S_ERR_INVALID, "conv_fwd: epilogue statistics need a CTA-pair path (s2s_conv_stat_tiles_for() > 0)");
     if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
     if (a_fmt != w_fmt)
         return fail(S2S_ERR_INVALID, "conv_fwd: activations and weights must share one 16-bit format (tcgen05 kind::f16 "
@@ -276,18 +302,14 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
         return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
     // halo-tiled CTA-pair kernel: stride-1 convs with at least one 3x3 segment
     {
-        bool ok = out_bf16 && !axpy_x && Cout % 128 == 0 && conv_pairs() && conv_halo();
-        bool any3 = false;
-        for (int s = 0; s < nsrc && ok; ++s) {
-            ok = ok && srcs[s].stride == 1 && (srcs[s].taps == 1 || srcs[s].taps == 9);
-            any3 = any3 || srcs[s].taps == 9;
-        }
+        const bool ok = out_bf16 && !axpy_x && halo_eligible(srcs, nsrc, Cout);
+        const bool any3 = ok;
         if (ok && any3) {
             Conv3Params q;
             memset(&q, 0, sizeof(q));
-            const int BN3 = (Cout % 256 == 0) ? 256 : 128;
             const bool cols3 = conv_halo() == 3;
-            const int mt3 = (!cols3 && BN3 == 128 && Hout >= 2 * kHaloTH) ? 2 : 1;
+            int BN3, mt3, tx3, ty3;
+            halo_geometry(Hout, Wout, Cout, &BN3, &mt3, &tx3, &ty3);
             q.cols3 = cols3 ? 1 : 0;
             q.nseg = nsrc;
             int kb3 = 0;
@@ -316,8 +338,10 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             int rc = make_act_tmap_box(&q.tmOut, out_bf16, B, Hout, Wout, Cout, kHaloTW, kHaloTH);
             if (rc) return rc;
             q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
-            q.tiles_x = (Wout + kHaloTW - 1) / kHaloTW;
-            q.tiles_y = (Hout + kHaloTH * mt3 - 1) / (kHaloTH * mt3);
+            q.tiles_x = tx3;
+            q.tiles_y = ty3;
+            q.stats = (float2*)stats_out;
+            q.stat_tiles = tx3 * ty3 * mt3;
             q.m_tiles = B * q.tiles_x * q.tiles_y;
             q.n_tiles_n = Cout / BN3;
             q.total_pairs = ((q.m_tiles + 1) / 2) * q.n_tiles_n;
@@ -333,7 +357,7 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             a_slot = (a_slot + 1023) / 1024 * 1024;
             q.a_slot = (uint32_t)a_slot;
             const size_t b_bytes = (size_t)(BN3 / 2) * kBlockK * 2;
-            const size_t fixed = 2 * kOutStageBytes + 1024 + 1024;
+            const size_t fixed = 2 * kOutStageBytes + 1024 + 3072;  // + alignment slack + barriers / statistics scratch
             q.sa = cols3 ? 2 : 3;
             int sb = (int)((kSmemBudget - fixed - (size_t)q.sa * a_slot) / b_bytes);
             if (sb > 8) sb = 8;

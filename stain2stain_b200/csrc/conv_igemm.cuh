@@ -710,6 +710,8 @@ struct Conv3Params {
                                // every tap's A descriptor is 1024 B aligned with an 8-row-group stride of exactly 1024 B
     const float* bias;
     const __nv_bfloat16* residual;
+    float2* stats;             // optional per-sub-tile (sum, sumsq) of the stored outputs, as in Conv2Params
+    int stat_tiles;
     int a_fmt, w_fmt, out_fmt, res_fmt;
 };
 
@@ -739,6 +741,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     uint64_t* tfull = emptyB + SB;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    float2* stat_scratch = reinterpret_cast<float2*>(bars + 32);  // 4 warps x 64 channels x float2 (2 KB)
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
@@ -781,8 +784,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     };
 
     if (warp == 0) {
-        // ===================================================================== TMA producer (both CTAs)
-        if (lane == 0) {
+        // ===================================================================== TMA producer (both CTAs; whole warp, elected issue)
+        {
             int ia = 0, ib = 0;
             uint32_t pha = 0, phb = 0;
             for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters) {
@@ -795,32 +798,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     for (int cb = 0; cb < sg.cblocks; ++cb) {
                         mbar_wait(&emptyA[ia], pha ^ 1);
                         uint8_t* a_dst = ringA + (size_t)ia * p.a_slot;
-                        if (sg.taps == 9) {
-                            if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * halo_bytes);
-                            if (p.cols3) {
+                        if (elect_one()) {
+                            if (sg.taps == 9) {
+                                if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * halo_bytes);
+                                if (p.cols3) {
 #pragma unroll
-                                for (int j = 0; j < 3; ++j)
-                                    tma_load_5d_2cta(a_dst + j * box3_bytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1 + j, 0,
-                                                     y0 - 1, b);
+                                    for (int j = 0; j < 3; ++j)
+                                        tma_load_5d_2cta(a_dst + j * box3_bytes, &p.tmA[s], &fullA[ia], cb * kBlockK,
+                                                         x0 - 1 + j, 0, y0 - 1, b);
+                                } else {
+                                    tma_load_5d_2cta(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
+                                }
                             } else {
-                                tma_load_5d_2cta(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
-                            }
-                        } else {
-                            if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * MT * kABytes);
+                                if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * MT * kABytes);
 #pragma unroll
-                            for (int h = 0; h < MT; ++h)
-                                tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0, 0,
-                                                 y0 + h * kHaloTH, b);
+                                for (int h = 0; h < MT; ++h)
+                                    tma_load_5d_2cta(a_dst + h * kABytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0, 0,
+                                                     y0 + h * kHaloTH, b);
+                            }
                         }
+                        __syncwarp();
                         if (++ia == SA) {
                             ia = 0;
                             pha ^= 1;
                         }
                         for (int tap = 0; tap < sg.taps; ++tap) {
                             mbar_wait(&emptyB[ib], phb ^ 1);
-                            if (leader) mbar_arrive_expect_tx(&fullB[ib], 2 * b_bytes);
-                            tma_load_2d_2cta(ringB + (size_t)ib * b_bytes, &p.tmW, &fullB[ib],
-                                             (p.seg_kb[s] + tap * sg.cblocks + cb) * kBlockK, n0);
+                            if (elect_one()) {
+                                if (leader) mbar_arrive_expect_tx(&fullB[ib], 2 * b_bytes);
+                                tma_load_2d_2cta(ringB + (size_t)ib * b_bytes, &p.tmW, &fullB[ib],
+                                                 (p.seg_kb[s] + tap * sg.cblocks + cb) * kBlockK, n0);
+                            }
+                            __syncwarp();
                             if (++ib == SB) {
                                 ib = 0;
                                 phb ^= 1;
@@ -832,7 +841,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (leader CTA only)
-        if (lane == 0 && leader) {
+        if (leader) {  // whole warp, convergent; one elected lane issues each tcgen05 instruction
             const uint32_t idesc = umma_idesc_16b(2 * kTileM, (uint32_t)BN, 0, 0, p.a_fmt, p.w_fmt);
             int ia = 0, ib = 0;
             uint32_t pha = 0, phb = 0;
@@ -869,24 +878,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                                 for (int h = 0; h < MT; ++h) {
                                     const uint64_t da = umma_smem_desc_sw128_off(a_base + h * a_sub + tap_off + k * 32, 16,
                                                                                  a_sbo, p.base_off_mode);
-                                    umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, acc);
+                                    if (elect_one()) umma_bf16_2cta(d_tmem + (uint32_t)(h * BN), da, db, idesc, acc);
                                 }
                                 acc = 1;
                             }
-                            umma_commit_2cta(&emptyB[ib], 0x3);
+                            if (elect_one()) umma_commit_2cta(&emptyB[ib], 0x3);
+                            __syncwarp();
                             if (++ib == SB) {
                                 ib = 0;
                                 phb ^= 1;
                             }
                         }
-                        umma_commit_2cta(&emptyA[ia], 0x3);
+                        if (elect_one()) umma_commit_2cta(&emptyA[ia], 0x3);
+                        __syncwarp();
                         if (++ia == SA) {
                             ia = 0;
                             pha ^= 1;
                         }
                     }
                 }
-                umma_commit_2cta(&tfull[as], 0x3);
+                if (elect_one()) umma_commit_2cta(&tfull[as], 0x3);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -965,6 +977,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     if (et == 0) {
                         tma_store_5d(&p.tmOut, out_stage + ob * kOutStageBytes, nbase, x0, 0, ys, b);
                         tma_store_commit();
+                    }
+                    if (p.stats != nullptr) {
+                        // as in conv_igemm_pair_kernel: per-channel (sum, sumsq) of the staged (rounded) tile; here the
+                        // sub-tile is 8 px wide x 16 px high, row r = (r / 8, r % 8)
+                        const int cg = et & 7, rg = et >> 3;
+                        const uint8_t* tile = out_stage + ob * kOutStageBytes;
+                        const bool full_tile = (ys + kHaloTH <= p.Hout) && (x0 + kHaloTW <= p.Wout);
+                        float sm[8], sq[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sm[e] = sq[e] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rg * 8 + i;
+                            if (!full_tile && ((ys + r / kHaloTW >= p.Hout) || (x0 + r % kHaloTW >= p.Wout))) continue;
+                            const uint4 u = *reinterpret_cast<const uint4*>(tile + r * 128 + ((cg ^ i) << 4));
+                            float f[8];
+                            float2 t2;
+                            t2 = unpack2(u.x, p.out_fmt); f[0] = t2.x; f[1] = t2.y;
+                            t2 = unpack2(u.y, p.out_fmt); f[2] = t2.x; f[3] = t2.y;
+                            t2 = unpack2(u.z, p.out_fmt); f[4] = t2.x; f[5] = t2.y;
+                            t2 = unpack2(u.w, p.out_fmt); f[6] = t2.x; f[7] = t2.y;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                sm[e] += f[e];
+                                sq[e] = fmaf(f[e], f[e], sq[e]);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 8);
+                            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8);
+                            sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], 16);
+                            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+                        }
+                        if (lane < 8) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) stat_scratch[q * 64 + lane * 8 + e] = make_float2(sm[e], sq[e]);
+                        }
+                        named_bar_sync(3, 128);
+                        if (et < 64 && valid) {
+                            float2 o = stat_scratch[et];
+#pragma unroll
+                            for (int wq = 1; wq < 4; ++wq) {
+                                const float2 t2 = stat_scratch[wq * 64 + et];
+                                o.x += t2.x;
+                                o.y += t2.y;
+                            }
+                            const int sub = (ty * MT + h) * p.tiles_x + tx;
+                            p.stats[((size_t)b * p.stat_tiles + sub) * p.Cout + nbase + et] = o;
+                        }
                     }
                     ob ^= 1;
                 }

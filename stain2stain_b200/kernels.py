@@ -148,8 +148,8 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted)
     macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs)
     stats = None
-    if want_stats and not out_f32:
-        nt = conv_stat_tiles(hout, wout, cout)
+    if want_stats and not out_f32 and axpy_x is None and EPI_STATS:
+        nt = int(_L().s2s_conv_stat_tiles_for(arr, len(srcs), hout, wout, cout))
         if nt > 0:
             stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=dev)
     with _Prof("conv_igemm", 2.0 * macs):

@@ -388,23 +388,26 @@ def test_stored_dropout_mask_equals_rehash():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("taps", [9, 1])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 128), (3, 16, 48, 64, 256), (2, 24, 20, 128, 128),
-                                            (1, 8, 8, 256, 512)])
-def test_conv_epilogue_statistics_match_a_stats_pass(B, H, W, Cin, Cout):
-    """GroupNorm statistics emitted by the CTA-pair conv epilogue (per 128-pixel sub-tile, from the staged 16-bit tile)
-    give the same coefficients as a separate gn_stats pass over the stored tensor -- incl. ragged tiles."""
+                                            (1, 8, 8, 256, 512), (3, 40, 40, 128, 128)])
+def test_conv_epilogue_statistics_match_a_stats_pass(B, H, W, Cin, Cout, taps):
+    """GroupNorm statistics emitted by the CTA-pair conv epilogues (per 128-pixel sub-tile, from the staged 16-bit tile)
+    give the same coefficients as a separate gn_stats pass over the stored tensor -- incl. ragged tiles.  taps = 9 runs
+    the halo-tiled pair kernel (8 x 16 pixel tiles), taps = 1 the plain pair kernel (16 x 8 pixel tiles)."""
     k = K()
     g = torch.Generator(device=DEV).manual_seed(21)
     x = nhwc(rb(torch.randn(B, Cin, H, W, device=DEV, generator=g)))
     w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (3 * Cin ** 0.5)
+    if taps == 1:
+        w = w[:, :, 1:2, 1:2].contiguous() * 3
     wp = pack_fwd(k, [(w, 0, Cin)], Cout)
     bias = torch.randn(Cout, device=DEV, generator=g)
-    res = k.conv_fwd([(x, 9, 1)], wp, Cout, H, W, bias=bias, want_stats=True)
+    res = k.conv_fwd([(x, taps, 1)], wp, Cout, H, W, bias=bias, want_stats=True)
     y, st = res
-    if k.conv_stat_tiles(H, W, Cout) == 0:
-        assert st is None
-        pytest.skip("CTA-pair path not selected for this geometry")
-    assert st.shape == (B, k.conv_stat_tiles(H, W, Cout), Cout, 2)
+    if st is None:
+        pytest.skip("no CTA-pair path for this geometry")
+    assert st.shape[0] == B and tuple(st.shape[2:]) == (Cout, 2) and st.shape[1] * 128 >= H * W
     gamma = 1 + 0.1 * torch.randn(Cout, device=DEV, generator=g)
     beta = 0.1 * torch.randn(Cout, device=DEV, generator=g)
     coef_e, mr_e = k.gn_coef_parts([st], gamma, beta, None, H * W)
@@ -414,7 +417,7 @@ def test_conv_epilogue_statistics_match_a_stats_pass(B, H, W, Cin, Cout):
     assert torch.allclose(mr_e, mr_s, rtol=2e-4, atol=2e-5), float((mr_e - mr_s).abs().max())
     assert torch.allclose(coef_e, coef_s, rtol=2e-4, atol=2e-5)
     # two-source fold == fold of the concatenation
-    y2, st2 = k.conv_fwd([(x, 9, 1)], wp, Cout, H, W, bias=bias * 0.5, want_stats=True)
+    y2, st2 = k.conv_fwd([(x, taps, 1)], wp, Cout, H, W, bias=bias * 0.5, want_stats=True)
     g2 = torch.cat([gamma, gamma]); b2 = torch.cat([beta, beta])
     coef_2, mr_2 = k.gn_coef_parts([st, st2], g2, b2, None, H * W)
     stats_c = k.gn_partial_buffer(B, H * W, 2 * Cout, DEV)
