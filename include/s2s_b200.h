@@ -65,6 +65,24 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                  const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
                  void* stream);
+/* s2s_conv_fwd with the normalisation that PRECEDES the conv fused into its operand path (inference): segment i with
+ * norms[i].coef != NULL is the RAW tensor, and the kernel rewrites every landed shared-memory tile in place as
+ * act(x * A + Bc) with coef = fp32 [B][ld][2] (A, Bc) as produced by s2s_gn_coef / s2s_gn_coef_parts (GroupNorm32 +
+ * FiLM folded), channel c of the segment at coef[b][off + c]; act must be 1 (SiLU) and a_fmt fp16: the prologue
+ * evaluates silu(z) = z/2 + z/2*tanh(z/2) with one tanh.approx.f16x2 per channel pair (|error| <= |z|/2 * 2^-11).  Replaces, for the conv that follows:
+ * torchcfm ResBlock `in_layers[0:2]` / `out_layers[0:2]` (GroupNorm32 -> (FiLM) -> SiLU) in eval mode, i.e. the whole
+ * s2s_gn_apply pass.  Only for geometries where s2s_conv_norm_fusable() != 0 (halo-tiled CTA-pair kernel, 3x3 stride-1
+ * normalised segments); everything else about the call is s2s_conv_fwd's. */
+typedef struct {
+    const float* coef;
+    int ld;
+    int off;
+} s2s_conv_norm;
+int s2s_conv_norm_fusable(const s2s_conv_src* srcs, int nsrc, int Cout);
+int s2s_conv_fwd_norm(const s2s_conv_src* srcs, const s2s_conv_norm* norms, int act, int nsrc, int B, int Hout, int Wout,
+                      const void* w_packed, int Ktot, int Cout, const float* bias, const void* residual, void* out_bf16,
+                      float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream);
+
 /* Sub-tiles per sample of the epilogue statistics for this output geometry; 0 = not available (use s2s_gn_stats).
  * s2s_conv_stat_tiles: the plain CTA-pair kernel's geometry; s2s_conv_stat_tiles_for: the geometry of the kernel
  * s2s_conv_fwd will pick for these segments (the halo-tiled pair kernel takes stride-1 convs with a 3x3 segment). */

@@ -23,6 +23,10 @@ class ConvSrc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("C", C.c_int), ("taps", C.c_int), ("stride", C.c_int)]
 
 
+class ConvNorm(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("ld", C.c_int), ("off", C.c_int)]
+
+
 _vp, _i, _f, _d, _u64, _ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must mirror include/s2s_b200.h exactly.
@@ -32,6 +36,9 @@ SIGNATURES = {
     "s2s_num_sms": [],
     "s2s_pack_conv_weight": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
     "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
+    "s2s_conv_norm_fusable": [C.POINTER(ConvSrc), _i, _i],
+    "s2s_conv_fwd_norm": [C.POINTER(ConvSrc), C.POINTER(ConvNorm), _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i,
+                          _i, _i, _vp],
     "s2s_conv_stat_tiles": [_i, _i, _i],
     "s2s_conv_stat_tiles_for": [C.POINTER(ConvSrc), _i, _i, _i, _i],
     "s2s_gn_coef_parts": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],

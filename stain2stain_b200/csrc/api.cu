@@ -288,10 +288,41 @@ int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wo
     return s2s_conv_stat_tiles(Hout, Wout, Cout);
 }
 
+static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
+                         int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
+                         const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt,
+                         int res_fmt, void* stream, const s2s_conv_norm* norms, int act);
+
 int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                  int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                  const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt,
                  void* stream) {
+    return conv_fwd_impl(srcs, nsrc, B, Hout, Wout, w_packed, Ktot, Cout, bias, residual, out_bf16, out_f32, axpy_x, axpy_a,
+                         stats_out, a_fmt, w_fmt, out_fmt, res_fmt, stream, nullptr, 0);
+}
+
+int s2s_conv_norm_fusable(const s2s_conv_src* srcs, int nsrc, int Cout) {
+    return (conv_halo() == 1 || conv_halo() == 2) && halo_eligible(srcs, nsrc, Cout) ? 1 : 0;
+}
+
+int s2s_conv_fwd_norm(const s2s_conv_src* srcs, const s2s_conv_norm* norms, int act, int nsrc, int B, int Hout, int Wout,
+                      const void* w_packed, int Ktot, int Cout, const float* bias, const void* residual, void* out_bf16,
+                      float* stats_out, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream) {
+    if (!norms || act != 1 || a_fmt != S2S_FMT_F16)
+        return fail(S2S_ERR_INVALID, "conv_fwd_norm: the fused prologue is built for SiLU on fp16 activations");
+    if (!s2s_conv_norm_fusable(srcs, nsrc, Cout))
+        return fail(S2S_ERR_INVALID, "conv_fwd_norm: this geometry does not run on the halo-tiled CTA-pair kernel");
+    for (int s = 0; s < nsrc; ++s)
+        if (norms[s].coef && (srcs[s].taps != 9 || norms[s].ld % 8 || norms[s].off % 8))
+            return fail(S2S_ERR_INVALID, "conv_fwd_norm: a normalised segment must be 3x3 with 8-aligned coefficient offsets");
+    return conv_fwd_impl(srcs, nsrc, B, Hout, Wout, w_packed, Ktot, Cout, bias, residual, out_bf16, nullptr, nullptr, 0.f,
+                         stats_out, a_fmt, w_fmt, out_fmt, res_fmt, stream, norms, act);
+}
+
+static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
+                         int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
+                         const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt,
+                         int res_fmt, void* stream, const s2s_conv_norm* norms, int act) {
     if (stats_out && (!out_bf16 || axpy_x || s2s_conv_stat_tiles_for(srcs, nsrc, Hout, Wout, Cout) == 0))
         return fail(S2S_ERR_INVALID, "conv_fwd: epilogue statistics need a CTA-pair path (s2s_conv_stat_tiles_for() > 0)");
     if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
@@ -342,6 +373,16 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             q.tiles_y = ty3;
             q.stats = (float2*)stats_out;
             q.stat_tiles = tx3 * ty3 * mt3;
+            if (norms) {
+                q.prologue = 1;
+                q.act = act;
+                for (int s = 0; s < nsrc; ++s) {
+                    q.seg_coef[s] = (const float2*)norms[s].coef;
+                    q.seg_x[s] = (const uint16_t*)srcs[s].x;
+                    q.seg_coef_ld[s] = norms[s].ld;
+                    q.seg_coef_off[s] = norms[s].off;
+                }
+            }
             q.m_tiles = B * q.tiles_x * q.tiles_y;
             q.n_tiles_n = Cout / BN3;
             q.total_pairs = ((q.m_tiles + 1) / 2) * q.n_tiles_n;
@@ -366,15 +407,19 @@ int s2s_conv_fwd(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, 
             const size_t smem = (size_t)q.sa * a_slot + (size_t)sb * b_bytes + fixed;
             int clusters = num_sms() / 2;
             if (clusters > q.total_pairs) clusters = q.total_pairs;
-            if (mt3 == 2) {
-                rc = set_smem(conv_halo_pair_kernel<2>, smem);
-                if (rc) return rc;
-                conv_halo_pair_kernel<2><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
-            } else {
-                rc = set_smem(conv_halo_pair_kernel<1>, smem);
-                if (rc) return rc;
-                conv_halo_pair_kernel<1><<<2 * clusters, kConvThreads, smem, (cudaStream_t)stream>>>(q);
-            }
+            const dim3 grid3(2 * clusters);
+            cudaStream_t st3 = (cudaStream_t)stream;
+#define S2S_HALO_LAUNCH(MTV, PROV)                                                          \
+    do {                                                                                    \
+        rc = set_smem(conv_halo_pair_kernel<MTV, PROV>, smem);                              \
+        if (rc) return rc;                                                                  \
+        conv_halo_pair_kernel<MTV, PROV><<<grid3, kConvThreads, smem, st3>>>(q);            \
+    } while (0)
+            if (mt3 == 2 && q.prologue) S2S_HALO_LAUNCH(2, true);
+            else if (mt3 == 2) S2S_HALO_LAUNCH(2, false);
+            else if (q.prologue) S2S_HALO_LAUNCH(1, true);
+            else S2S_HALO_LAUNCH(1, false);
+#undef S2S_HALO_LAUNCH
             LAUNCH_CHECK("conv_halo_pair_kernel");
             return S2S_OK;
         }

@@ -713,9 +713,18 @@ struct Conv3Params {
     float2* stats;             // optional per-sub-tile (sum, sumsq) of the stored outputs, as in Conv2Params
     int stat_tiles;
     int a_fmt, w_fmt, out_fmt, res_fmt;
+    // Fused normalisation prologue (inference): a segment with seg_coef != nullptr is NOT the activated tensor but the
+    // raw one; warps 2-3 rewrite each landed halo box in place as act(x * A + Bc) with the per-(sample, channel)
+    // coefficients of the GroupNorm (+FiLM) that precedes this conv, so the norm-apply pass over the tensor disappears.
+    const float2* seg_coef[kMaxSeg];  // [B][seg_coef_ld] (A, Bc), or nullptr = segment is used as it is
+    const uint16_t* seg_x[kMaxSeg];   // the segment's tensor (NHWC 16-bit): normalised segments are loaded by the transform
+                                      // warps straight from global memory (no TMA, no second pass over shared memory)
+    int seg_coef_ld[kMaxSeg], seg_coef_off[kMaxSeg];
+    int prologue;                     // 1: A boxes go TMA -> own full barrier -> transform warps -> leader's ready barrier
+    int act;                          // 0 none, 1 SiLU
 };
 
-template <int MT>
+template <int MT, bool PRO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     conv_halo_pair_kernel(const __grid_constant__ Conv3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -740,7 +749,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     uint64_t* emptyB = fullB + SB;
     uint64_t* tfull = emptyB + SB;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* readyA = tempty + 2;  // prologue mode: 2 transform warps x 2 CTAs arrive on the leader's copy
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(readyA + SA);
     float2* stat_scratch = reinterpret_cast<float2*>(bars + 32);  // 4 warps x 64 channels x float2 (2 KB)
 
     if (warp == 0 && lane == 0) {
@@ -752,6 +762,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
         for (int i = 0; i < SA; ++i) {
             mbar_init(&fullA[i], 1);
             mbar_init(&emptyA[i], 1);
+            mbar_init(&readyA[i], 4);
         }
         for (int i = 0; i < SB; ++i) {
             mbar_init(&fullB[i], 1);
@@ -798,7 +809,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     for (int cb = 0; cb < sg.cblocks; ++cb) {
                         mbar_wait(&emptyA[ia], pha ^ 1);
                         uint8_t* a_dst = ringA + (size_t)ia * p.a_slot;
-                        if (elect_one()) {
+                        if (PRO && p.seg_coef[s] != nullptr) {
+                            // normalised segment: the transform warps fill this slot themselves (they wait on emptyA);
+                            // only the weights of its taps are fetched here
+                        } else if (PRO) {
+                            // each CTA's box completes on its OWN barrier (its transform warps wait on it)
+                            if (elect_one()) {
+                                if (sg.taps == 9) {
+                                    mbar_arrive_expect_tx(&fullA[ia], halo_bytes);
+                                    tma_load_5d(a_dst, &p.tmA[s], &fullA[ia], cb * kBlockK, x0 - 1, 0, y0 - 1, b);
+                                } else {
+                                    mbar_arrive_expect_tx(&fullA[ia], MT * kABytes);
+#pragma unroll
+                                    for (int h = 0; h < MT; ++h)
+                                        tma_load_5d(a_dst + h * kABytes, &p.tmA[s], &fullA[ia], cb * kBlockK, x0, 0,
+                                                    y0 + h * kHaloTH, b);
+                                }
+                            }
+                        } else if (elect_one()) {
                             if (sg.taps == 9) {
                                 if (leader) mbar_arrive_expect_tx(&fullA[ia], 2 * halo_bytes);
                                 if (p.cols3) {
@@ -856,7 +884,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 for (int s = 0; s < p.nseg; ++s) {
                     const ConvSeg sg = p.seg[s];
                     for (int cb = 0; cb < sg.cblocks; ++cb) {
-                        mbar_wait(&fullA[ia], pha);
+                        if (PRO)
+                            mbar_wait_cluster(&readyA[ia], pha);
+                        else
+                            mbar_wait(&fullA[ia], pha);
                         const uint32_t a_base = smem_u32(ringA + (size_t)ia * p.a_slot);
                         for (int tap = 0; tap < sg.taps; ++tap) {
                             mbar_wait(&fullB[ib], phb);
@@ -899,6 +930,122 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 }
                 if (elect_one()) umma_commit_2cta(&tfull[as], 0x3);
                 __syncwarp();
+            }
+        }
+    } else if (warp < 4) {
+        // ===================================================================== norm prologue (warps 2-3, both CTAs)
+        if (PRO) {
+            const int t = (int)threadIdx.x - 64;   // 0..63
+            const int j = t & 7, rr = t >> 3;      // physical 16-byte chunk of the 128-byte row; row index mod 8
+            const int c16 = j ^ rr;                // logical channel chunk behind the 128-byte swizzle (slots are 1 KB aligned)
+            constexpr int rows9 = (kHaloTH * MT + 2) * kHaloPitch;
+            int ia = 0;
+            uint32_t pha = 0, full_bits = 0;
+            for (int pair = cluster_id; pair < p.total_pairs; pair += num_clusters) {
+                int b, ty, tx, nt;
+                bool valid;
+                decode(pair, b, ty, tx, nt, valid);
+                const int x0 = tx * kHaloTW, y0 = ty * kHaloTH * MT;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    const float2* cf = p.seg_coef[s];
+                    for (int cb = 0; cb < sg.cblocks; ++cb) {
+                        const int c0 = cb * kBlockK + c16 * 8;
+                        if (cf == nullptr) {
+                            // raw segment (1x1 skip conv): TMA filled the slot; hand it on unchanged.  fullA[ia] completes only
+                            // in the rounds in which the slot holds a raw segment, so its parity is tracked per slot.
+                            mbar_wait(&fullA[ia], (full_bits >> ia) & 1u);
+                            full_bits ^= 1u << ia;
+                        } else {
+                            // normalised 3x3 segment: global -> registers -> silu(x*A + Bc) -> swizzled shared memory.
+                            // (Rewriting a TMA-filled tile in place was measured first: the extra shared-memory read + write
+                            // competes with the MMAs' operand reads, which already run near the port's limit -- conv 22.9 ->
+                            // 27 ms per evaluation even with the arithmetic removed.)
+                            float Ah[8], Bh[8];
+                            const bool chan_ok = valid && c0 + 8 <= sg.C;
+                            if (chan_ok) {
+                                const float4* src = reinterpret_cast<const float4*>(
+                                    cf + (size_t)b * p.seg_coef_ld[s] + p.seg_coef_off[s] + c0);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 v = __ldg(src + e);
+                                    Ah[2 * e] = 0.5f * v.x; Bh[2 * e] = 0.5f * v.y;
+                                    Ah[2 * e + 1] = 0.5f * v.z; Bh[2 * e + 1] = 0.5f * v.w;
+                                }
+                            }
+                            const uint16_t* gx = p.seg_x[s] + (size_t)b * p.Hout * p.Wout * sg.C + c0;
+                            const uint32_t sbase = smem_u32(ringA + (size_t)ia * p.a_slot) + (uint32_t)(j * 16);
+                            constexpr int U = 8;                              // rows per group and thread
+                            constexpr int G = (rows9 + 8 * U - 1) / (8 * U);  // groups per box
+                            int h = 0, w = rr;                                // box row / column of the next row to load
+                            // two register buffers: the loads of group g+1 are in flight while group g is transformed and
+                            // stored, and group 0 is requested BEFORE waiting for the slot (loads do not touch it)
+                            auto load_group = [&](int g, uint4 (&v)[U], uint32_t& okm) {
+                                okm = 0;
+#pragma unroll
+                                for (int i = 0; i < U; ++i) {
+                                    const int r = rr + 8 * (g * U + i);
+                                    const int yy = y0 - 1 + h, xx = x0 - 1 + w;
+                                    const bool ok = chan_ok && r < rows9 && yy >= 0 && yy < p.Hout && xx >= 0 && xx < p.Wout;
+                                    v[i] = make_uint4(0, 0, 0, 0);  // conv padding / channel tail / dummy tile: zeros
+                                    if (ok) v[i] = ldg_nc16(gx + ((size_t)yy * p.Wout + xx) * sg.C);
+                                    okm |= (uint32_t)ok << i;
+                                    w += 8;
+                                    if (w >= kHaloPitch) {
+                                        w -= kHaloPitch;
+                                        ++h;
+                                    }
+                                }
+                            };
+                            auto finish_group = [&](int g, uint4 (&v)[U], uint32_t okm) {
+#pragma unroll
+                                for (int i = 0; i < U; ++i) {
+                                    if (!((okm >> i) & 1u)) continue;
+                                    uint32_t in[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        // silu(z) = z/2 + z/2 * tanh(z/2): hz in fp32, one tanh.approx.f16x2 + one HFMA2 per pair
+                                        const float2 xf = unpack_f16x2(in[e]);
+                                        const uint32_t hz = pack_f16x2(fmaf(xf.x, Ah[2 * e], Bh[2 * e]),
+                                                                       fmaf(xf.y, Ah[2 * e + 1], Bh[2 * e + 1]));
+                                        uint32_t th;
+                                        asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(hz));
+                                        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(in[e]) : "r"(hz), "r"(th));
+                                    }
+                                    v[i] = make_uint4(in[0], in[1], in[2], in[3]);
+                                }
+#pragma unroll
+                                for (int i = 0; i < U; ++i) {
+                                    const int r = rr + 8 * (g * U + i);
+                                    if (r < rows9)
+                                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)r * 128u),
+                                                     "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
+                                                     : "memory");
+                                }
+                            };
+                            uint4 va[U], vb[U];
+                            uint32_t oka, okb;
+                            load_group(0, va, oka);
+                            mbar_wait(&emptyA[ia], pha ^ 1);  // the MMAs that read this slot last have completed
+#pragma unroll 1
+                            for (int g = 0; g < G; g += 2) {
+                                if (g + 1 < G) load_group(g + 1, vb, okb);
+                                finish_group(g, va, oka);
+                                if (g + 1 < G) {
+                                    if (g + 2 < G) load_group(g + 2, va, oka);
+                                    finish_group(g + 1, vb, okb);
+                                }
+                            }
+                        }
+                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader_release(&readyA[ia]);
+                        if (++ia == SA) {
+                            ia = 0;
+                            pha ^= 1;
+                        }
+                    }
+                }
             }
         }
     } else if (warp >= 4) {

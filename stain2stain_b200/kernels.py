@@ -16,7 +16,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvSrc, ptr, stream_ptr
+from ._lib import ConvNorm, ConvSrc, ptr, stream_ptr
 from ._lib import check as _check
 
 T16 = torch.bfloat16  # declared dtype of every 16-bit engine tensor (see module docstring)
@@ -109,6 +109,19 @@ def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begi
 
 
 EPI_STATS = os.environ.get("S2S_EPI_STATS", "1") != "0"  # GroupNorm statistics from the producing conv's epilogue
+# inference: GroupNorm(+FiLM)+SiLU applied inside the consuming conv (s2s_conv_fwd_norm).  OFF by default: with two helper
+# warps per CTA the prologue does not hide behind the MMAs (measured) -- the separate norm-apply pass is faster.
+NORM_FUSE = os.environ.get("S2S_NORM_FUSE", "0") != "0"
+
+
+def conv_norm_fusable(srcs: Sequence[Tuple[torch.Tensor, int, int]], cout: int, force: bool = False) -> bool:
+    """True when `conv_fwd(..., norms=...)` can run for these segments (halo-tiled CTA-pair kernel)."""
+    if not (NORM_FUSE or force) or ACT != FMT_F16:
+        return False
+    arr = (ConvSrc * len(srcs))()
+    for i, (x, taps, stride) in enumerate(srcs):
+        arr[i].x, arr[i].C, arr[i].taps, arr[i].stride = x.data_ptr(), x.shape[3], taps, stride
+    return bool(_L().s2s_conv_norm_fusable(arr, len(srcs), cout))
 
 
 def conv_stat_tiles(hout: int, wout: int, cout: int) -> int:
@@ -119,8 +132,11 @@ def conv_stat_tiles(hout: int, wout: int, cout: int) -> int:
 def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tensor, cout: int, hout: int, wout: int,
              bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out_f32: bool = False,
              axpy_x: Optional[torch.Tensor] = None, axpy_a: float = 0.0, out: Optional[torch.Tensor] = None,
-             a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT, want_stats: bool = False):
+             a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT, want_stats: bool = False,
+             norms: Optional[Sequence[Optional[Tuple[torch.Tensor, int]]]] = None, norm_act: int = 1):
     """srcs: [(x NHWC 16-bit, taps, stride)].  Returns 16-bit NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32.
+    norms (inference): per segment `(coef fp32 [B, Ctot, 2], channel offset)` or None -- the segment is then the RAW
+    tensor and act(x * A + Bc) is applied to its tiles inside the kernel (no norm-apply pass); norm_act: 0 none, 1 SiLU.
     want_stats: returns (out, stats) with stats = fp32 [B, tiles, cout, 2] per-sub-tile (sum, sumsq) of the stored
     output (the consumer's GroupNorm statistics, produced by the conv epilogue) or None when that path is unavailable."""
     arr = (ConvSrc * len(srcs))()
@@ -152,6 +168,19 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
         nt = int(_L().s2s_conv_stat_tiles_for(arr, len(srcs), hout, wout, cout))
         if nt > 0:
             stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=dev)
+    if norms is not None:
+        assert not out_f32 and axpy_x is None and len(norms) == len(srcs)
+        narr = (ConvNorm * len(srcs))()
+        for i, nm in enumerate(norms):
+            if nm is not None:
+                cf, off = nm
+                assert cf.dtype == torch.float32 and cf.is_contiguous() and cf.shape[0] == B and cf.shape[2] == 2
+                narr[i].coef, narr[i].ld, narr[i].off = cf.data_ptr(), cf.shape[1], off
+        with _Prof("conv_igemm", 2.0 * macs):
+            check(_L().s2s_conv_fwd_norm(arr, narr, int(norm_act), len(srcs), B, hout, wout, ptr(w_packed),
+                                         w_packed.shape[1], cout, ptr(bias), ptr(residual), o16, ptr(stats), a_fmt, w_fmt,
+                                         out_fmt, res_fmt, stream_ptr()), "conv_fwd_norm")
+        return (out, stats) if want_stats else out
     with _Prof("conv_igemm", 2.0 * macs):
         check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
                                 ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), ptr(stats), a_fmt, w_fmt, out_fmt,

@@ -618,6 +618,7 @@ class ResBlockCfg:
     has_skip_conv: bool
     groups: int = 32
     eps: float = 1e-5
+    plan1_multi: Optional[ConvPlan] = None  # inference: conv 1 over the RAW sources, one 3x3 segment per source
 
 
 def _wgrad_to(d_out, x_g, taps: int, stride: int, d_w_view, n_begin: int):
@@ -637,7 +638,8 @@ class _ResBlockFn(torch.autograd.Function):
     over the block input."""
 
     @staticmethod
-    def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, src_stats, stats_box, *tensors):
+    def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, src_stats, stats_box, grad_mode: bool,
+                *tensors):
         srcs = tensors[:n_src]
         emb_act = tensors[n_src]
         gn1w, gn1b, c1w, c1b, ew, eb, gn2w, gn2b, c2w, c2b = tensors[n_src + 1:n_src + 11]
@@ -646,8 +648,10 @@ class _ResBlockFn(torch.autograd.Function):
         ctot = sum(s.shape[3] for s in srcs)
         cout = c1w.shape[0]
         dev = srcs[0].device
-        train = any(ctx.needs_input_grad)
+        # `needs_input_grad` is True for parameters even under torch.no_grad(); the caller passes the grad mode
+        train = grad_mode and any(ctx.needs_input_grad)
         dual = train and K.ACT != K.GRAD
+        mask = None
         # ---- norm 1 (+SiLU) over the concatenated input
         if usable_stats(src_stats):  # statistics written by the producing convs' epilogues: no pass over the inputs
             coef1, mr1 = K.gn_coef_parts(list(src_stats), gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
@@ -658,13 +662,26 @@ class _ResBlockFn(torch.autograd.Function):
                 K.gn_stats(s, stats, off)
                 off += s.shape[3]
             coef1, mr1 = K.gn_coef(stats, gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
-        a1 = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
-        a1g = torch.empty_like(a1) if dual else None
-        off = 0
-        for s in srcs:
-            K.gn_apply(s, coef1, a1, off, True, y2=a1g)
-            off += s.shape[3]
-        h, h_stats = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach(), want_stats=True)
+        # inference: the norm-apply passes disappear -- the convs read the RAW tensors and apply silu(x * A + Bc) to
+        # their shared-memory tiles (s2s_conv_fwd_norm); the concat is then one GEMM segment per source
+        fuse = (not train) and cfg.plan1_multi is not None and \
+            K.conv_norm_fusable([(s, 9, 1) for s in srcs], cout)
+        if fuse:
+            offs, off = [], 0
+            for s in srcs:
+                offs.append(off)
+                off += s.shape[3]
+            h, h_stats = K.conv_fwd([(s, 9, 1) for s in srcs], cfg.plan1_multi.packed_fwd([c1w]), cout, H, W,
+                                    bias=c1b.detach(), want_stats=True, norms=[(coef1, o) for o in offs], norm_act=1)
+        else:
+            a1 = torch.empty((B, H, W, ctot), dtype=T16, device=dev)
+            a1g = torch.empty_like(a1) if dual else None
+            off = 0
+            for s in srcs:
+                K.gn_apply(s, coef1, a1, off, True, y2=a1g)
+                off += s.shape[3]
+            h, h_stats = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach(),
+                                    want_stats=True)
         # ---- FiLM from the (already SiLU'd) embedding, norm 2 (+SiLU, dropout)
         film = torch.addmm(eb.detach(), emb_act.detach().float(), ew.detach().t()).contiguous()
         if h_stats is not None:
@@ -673,21 +690,26 @@ class _ResBlockFn(torch.autograd.Function):
             stats2 = K.gn_partial_buffer(B, H * W, cout, dev)
             K.gn_stats(h, stats2, 0)
             coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
-        a2 = torch.empty((B, H, W, cout), dtype=T16, device=dev)
-        a2g = torch.empty_like(a2) if dual else None
-        mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if (train and drop_p > 0) else None
-        K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g, mask=mask)
+        if fuse:
+            a2, norms2 = h, [(coef2, 0)]
+        else:
+            a2 = torch.empty((B, H, W, cout), dtype=T16, device=dev)
+            a2g = torch.empty_like(a2) if dual else None
+            mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if (train and drop_p > 0) else None
+            K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g, mask=mask)
+            norms2 = None
         # ---- conv 2 with the skip path in the same accumulator
         if cfg.has_skip_conv:
             sw, sb = skip
             wp = cfg.plan2.packed_fwd([c2w, sw])
             bias = (c2b.detach() + sb.detach()).contiguous()
             out, out_stats = K.conv_fwd([(a2, 9, 1)] + [(s, 1, 1) for s in srcs], wp, cout, H, W, bias=bias,
-                                        want_stats=True)
+                                        want_stats=True,
+                                        norms=None if norms2 is None else norms2 + [None] * len(srcs))
         else:
             assert n_src == 1 and ctot == cout
             out, out_stats = K.conv_fwd([(a2, 9, 1)], cfg.plan2.packed_fwd([c2w]), cout, H, W, bias=c2b.detach(),
-                                        residual=srcs[0], want_stats=True)
+                                        residual=srcs[0], want_stats=True, norms=norms2)
         stats_box.append(out_stats)
         if train:
             ctx.cfg, ctx.n_src, ctx.drop = cfg, n_src, (drop_p, seed)
@@ -766,7 +788,7 @@ class _ResBlockFn(torch.autograd.Function):
             K.gn_bwd_apply(s, d_a1, coef1, pqr1, off, d_skip[i], dx, True)
             d_srcs.append(dx)
             off += s.shape[3]
-        grads = [None, None, None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
+        grads = [None, None, None, None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
                  d_gn2w, d_gn2b, d_c2w, d_b2]
         if cfg.has_skip_conv:
             grads += [d_sw, d_b2]
@@ -776,4 +798,5 @@ class _ResBlockFn(torch.autograd.Function):
 def res_block(cfg: ResBlockCfg, srcs, emb_act, params, drop_p: float, seed: int):
     box = []
     src_stats = tuple(stats_of(t) for t in srcs)
-    return _tag(_ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), src_stats, box, *srcs, emb_act, *params), box)
+    return _tag(_ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), src_stats, box, torch.is_grad_enabled(),
+                                  *srcs, emb_act, *params), box)

@@ -160,8 +160,12 @@ class ResBlock(TimestepBlock):
         widths = tuple(s.shape[3] for s in srcs)
         cfg = self._cfgs.get(widths)
         if cfg is None:
+            segs, off = [], 0
+            for i, w in enumerate(widths):
+                segs.append(Seg(i, 0, off, w, 9, 1))
+                off += w
             cfg = self._cfgs[widths] = ops.ResBlockCfg(self._plan1, self._plan2_skip(widths) if has_skip else self._plan2,
-                                                       has_skip)
+                                                       has_skip, plan1_multi=ConvPlan(tuple(segs), self.out_channels))
         params = [gn1.weight, gn1.bias, conv1.weight, conv1.bias, lin.weight, lin.bias, gn2.weight, gn2.bias,
                   conv2.weight, conv2.bias]
         if has_skip:
