@@ -97,6 +97,18 @@ int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wo
 int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int stride, int B, int Hout, int Wout,
                    float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream);
 
+/* s2s_pack_conv_weight for many weights in ONE launch (every cached GEMM operand is stale after an optimizer step).
+ * jobs_dev: device table of jobs; work_dev: device list of (job index, chunk index) int pairs, one CTA each, a chunk
+ * being s2s_pack_chunk() destination elements of the job (total = Cout * ci_count * taps).  The zero padding of the
+ * destinations is not touched. */
+typedef struct {
+    const float* w;
+    void* dst16;
+    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, pad;
+} s2s_pack_job;
+int s2s_pack_chunk(void);
+int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev, int n_work, void* stream);
+
 /* dw fp32 [taps][M][ldn] -> grad_oihw[m][n_begin + n][tap] = beta * grad + dw[tap][m][n_off + n] */
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad_oihw,
                      int Cin_total, int n_begin, float beta, void* stream);

@@ -648,6 +648,17 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     return S2S_OK;
 }
 
+int s2s_pack_chunk(void) { return kPackChunk; }
+
+int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev, int n_work, void* stream) {
+    static_assert(sizeof(s2s_pack_job) == sizeof(PackJob), "ABI struct drifted from the kernel's");
+    if (n_work <= 0) return S2S_OK;
+    if (!jobs_dev || !work_dev) return fail(S2S_ERR_INVALID, "pack_conv_weight_multi: bad arguments");
+    pack_conv_weight_multi_kernel<<<n_work, 256, 0, (cudaStream_t)stream>>>((const PackJob*)jobs_dev, (const int2*)work_dev);
+    LAUNCH_CHECK("pack_conv_weight_multi_kernel");
+    return S2S_OK;
+}
+
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad, int Cin_total,
                      int n_begin, float beta, void* stream) {
     const long long total = (long long)M * n_count * taps;

@@ -115,6 +115,39 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
     }
 }
 
+// The same packing for MANY weights in one launch (after an optimizer step every cached GEMM operand is stale: 158
+// tensors per training step).  Host uploads a job table + (job, chunk) work list, as for the multi-tensor Adam.
+constexpr int kPackChunk = 16384;
+struct PackJob {
+    const float* w;
+    uint16_t* dst;
+    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, pad;
+};
+__global__ void __launch_bounds__(256) pack_conv_weight_multi_kernel(const PackJob* __restrict__ jobs,
+                                                                     const int2* __restrict__ work) {
+    const int2 wi = work[blockIdx.x];
+    const PackJob jb = jobs[wi.x];
+    const long long total = (long long)jb.Cout * jb.ci_count * jb.taps;
+    const long long beg = (long long)wi.y * kPackChunk;
+    const long long end = min(total, beg + kPackChunk);
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        int row, tap, inner;
+        if (!jb.transpose_flip) {
+            inner = (int)(i % jb.ci_count);
+            tap = (int)((i / jb.ci_count) % jb.taps);
+            row = (int)(i / ((long long)jb.ci_count * jb.taps));
+            const float v = jb.w[((size_t)row * jb.Cin + jb.ci_begin + inner) * jb.taps + tap];
+            jb.dst[(size_t)row * jb.ld_k + jb.k_off + (size_t)tap * jb.ci_count + inner] = pack1(v, jb.fmt);
+        } else {
+            inner = (int)(i % jb.Cout);
+            tap = (int)((i / jb.Cout) % jb.taps);
+            row = (int)(i / ((long long)jb.Cout * jb.taps));
+            const float v = jb.w[((size_t)inner * jb.Cin + jb.ci_begin + row) * jb.taps + (jb.taps - 1 - tap)];
+            jb.dst[(size_t)row * jb.ld_k + jb.k_off + (size_t)tap * jb.Cout + inner] = pack1(v, jb.fmt);
+        }
+    }
+}
+
 // [taps][M][ldn] fp32 wgrad buffer -> += into OIHW fp32 gradient.  dst[m][n_begin + n][tap] += src[tap][m][n_off + n]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int taps, int M, int ldn, int n_off, int n_count,
                                     float* __restrict__ grad, int Cin_total, int n_begin, float beta) {

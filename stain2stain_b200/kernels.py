@@ -108,6 +108,39 @@ def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begi
                                         int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
 
 
+def pack_conv_weight_multi(jobs, table_cache: dict):
+    """jobs: [(w fp32, dst 16-bit, k_off, ci_begin, ci_count, transpose_flip, fmt)] on ONE device -> one launch.
+    The device job table / work list are cached in `table_cache` by the job set (pointers are stable across steps)."""
+    if not jobs:
+        return
+    dev = jobs[0][0].device
+    sig = tuple((w.data_ptr(), dst.data_ptr(), k_off, cb, cc, tf, fmt) for (w, dst, k_off, cb, cc, tf, fmt) in jobs)
+    hit = table_cache.get(sig)
+    if hit is None:
+        chunk = int(_L().s2s_pack_chunk())
+        arr = (_lib.PackJob * len(jobs))()
+        work = []
+        total_bytes = 0.0
+        for i, (w, dst, k_off, cb, cc, tf, fmt) in enumerate(jobs):
+            assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == T16 and dst.is_contiguous()
+            assert w.device == dev and dst.device == dev
+            cout, cin = w.shape[0], w.shape[1]
+            taps = w[0, 0].numel() if w.dim() > 2 else 1
+            arr[i] = _lib.PackJob(w.data_ptr(), dst.data_ptr(), cout, cin, taps, cb, cc, dst.shape[1], k_off, int(tf), fmt, 0)
+            n = cout * cc * taps
+            total_bytes += 6.0 * n
+            work.extend((i, c) for c in range((n + chunk - 1) // chunk))
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().pin_memory()
+        w_host = torch.tensor(work, dtype=torch.int32).pin_memory()
+        hit = (raw.to(dev, non_blocking=True), w_host.to(dev, non_blocking=True), len(work), total_bytes, (raw, w_host))
+        if len(table_cache) > 16:
+            table_cache.clear()
+        table_cache[sig] = hit
+    with _Prof("pack_conv_weight", 0.0, hit[3]):
+        check(_L().s2s_pack_conv_weight_multi(hit[0].data_ptr(), hit[1].data_ptr(), hit[2], stream_ptr()),
+              "pack_conv_weight_multi")
+
+
 EPI_STATS = os.environ.get("S2S_EPI_STATS", "1") != "0"  # GroupNorm statistics from the producing conv's epilogue
 # inference: GroupNorm(+FiLM)+SiLU applied inside the consuming conv (s2s_conv_fwd_norm).  OFF by default: with two helper
 # warps per CTA the prologue does not hide behind the MMAs (measured, DESIGN.md 2.1) -- the separate norm-apply pass is faster.
@@ -291,13 +324,16 @@ def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0
                                      x_fmt, g_fmt, stream_ptr()), "gn_bwd_reduce")
 
 
-def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool):
+def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool, want_red: bool = False):
+    """-> (pqr [B,C,4], dfilm or None[, red [B,C,2] = folded (sum dz, sum dz*xhat) when want_red])."""
     B, _, Cc, _ = red_part.shape
     red = torch.empty((B, Cc, 2), dtype=torch.float32, device=red_part.device)
     pqr = torch.empty((B, Cc, 4), dtype=torch.float32, device=red_part.device)
     dfilm = torch.empty((B, 2 * Cc), dtype=torch.float32, device=red_part.device) if want_dfilm else None
     check(_L().s2s_gn_bwd_coef(ptr(red_part), ptr(red), ptr(mr), ptr(gamma), ptr(beta), ptr(film), B, Cc, mr.shape[1],
                                HW, ptr(pqr), ptr(dgamma), ptr(dbeta), ptr(dfilm), stream_ptr()), "gn_bwd_coef")
+    if want_red:
+        return pqr, dfilm, red
     return pqr, dfilm
 
 

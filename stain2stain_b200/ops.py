@@ -6,6 +6,7 @@ to bf16 GEMM operands on the fly (cached while the parameter is unchanged).
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -18,32 +19,74 @@ T16 = K.T16
 
 # --------------------------------------------------------------------------------------------- packed-weight cache
 class _PackCache:
-    """bf16 GEMM operands derived from fp32 parameters, keyed by (purpose, parameter identity and version)."""
+    """16-bit GEMM operands derived from fp32 parameters, keyed by (purpose, parameter identity and version).
+
+    `make(dst)` returns `(operand, jobs)`: the destination tensor (allocated zero-filled when `dst` is None, else the
+    previous operand of the same parameters -- an optimizer step only changed the values, the zero padding is never
+    written) and the pack jobs `(index of the weight in ws, k_off, ci_begin, ci_count, transpose_flip, fmt)` that fill it.  When a stale
+    operand is requested, EVERY stale operand of the cache is re-packed by one multi-tensor launch
+    (`s2s_pack_conv_weight_multi`): after an optimizer step that is all 158 operands of the model at once."""
 
     def __init__(self):
-        self._store: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
+        self._store: Dict[tuple, list] = {}   # key -> [sig, operand, weakrefs to the weights, jobs]
+        self._tables: Dict[tuple, tuple] = {}  # job-set signature -> (device job table, device work list, n_work, keep-alive)
 
     @staticmethod
     def _sig(ws: Sequence[torch.Tensor]):
         return tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws)
 
     def get(self, key: tuple, ws: Sequence[torch.Tensor], make):
-        """`make(dst)` packs into `dst` when given (the previous operand of the same parameters: same shapes, same
-        device -- an optimizer step only changed the values, and the zero padding is never written), else allocates."""
         sig = self._sig(ws)
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
-        dst = None
-        if hit is not None and len(hit[0]) == len(sig) and all(a[2] == b[2] for a, b in zip(hit[0], sig)) and \
-                hit[1].device == ws[0].device:
-            dst = hit[1]
-        val = make(dst)
-        self._store[key] = (sig, val)
+        if hit is not None and self._reusable(hit, sig, ws[0].device):
+            self._refresh_stale(ws[0].device)
+            hit = self._store.get(key)
+            if hit is not None and hit[0] == sig:
+                return hit[1]
+        val, jobs = make(None)
+        self._run_jobs(val, jobs, ws)
+        self._store[key] = [sig, val, [weakref.ref(w) for w in ws], jobs]  # jobs name weights by index: no strong refs
         return val
+
+    @staticmethod
+    def _reusable(hit, sig, device) -> bool:
+        return len(hit[0]) == len(sig) and all(a[0] == b[0] and a[2] == b[2] for a, b in zip(hit[0], sig)) and \
+            hit[1].device == device
+
+    @staticmethod
+    def _run_jobs(dst, jobs, ws):
+        for (wi, k_off, ci_begin, ci_count, tf, fmt) in jobs:
+            K.pack_conv_weight(ws[wi].detach(), dst, k_off=k_off, ci_begin=ci_begin, ci_count=ci_count, transpose_flip=tf,
+                               fmt=fmt)
+
+    def _refresh_stale(self, device):
+        """Re-pack, in one launch, every operand on `device` whose parameters changed in place (same storage, new version)."""
+        stale, dead = [], []
+        for key, ent in self._store.items():
+            ws = [r() for r in ent[2]]
+            if any(w is None for w in ws):
+                dead.append(key)
+                continue
+            sig = self._sig(ws)
+            if sig != ent[0] and ent[1].device == device and self._reusable(ent, sig, device):
+                stale.append((key, ent, ws, sig))
+        for key in dead:
+            del self._store[key]
+        if not stale:
+            return
+        jobs = []
+        for key, ent, ws, sig in stale:
+            for (wi, k_off, ci_begin, ci_count, tf, fmt) in ent[3]:
+                jobs.append((ws[wi].detach(), ent[1], k_off, ci_begin, ci_count, tf, fmt))
+        K.pack_conv_weight_multi(jobs, self._tables)
+        for key, ent, ws, sig in stale:
+            ent[0] = sig
 
     def clear(self):
         self._store.clear()
+        self._tables.clear()
 
 
 PACK_CACHE = _PackCache()
@@ -79,11 +122,11 @@ class ConvPlan:
         def make(dst):
             wp = dst if dst is not None else \
                 torch.zeros((K.padded_rows(self.cout), self.ktot()), dtype=T16, device=weights[0].device)
-            off = 0
+            jobs, off = [], 0
             for s in self.segs:
-                K.pack_conv_weight(weights[s.weight].detach(), wp, k_off=off, ci_begin=s.ci_begin, ci_count=s.ci_count)
+                jobs.append((s.weight, off, s.ci_begin, s.ci_count, False, K.ACT))
                 off += s.taps * ((s.ci_count + 63) // 64 * 64)
-            return wp
+            return wp, jobs
         return PACK_CACHE.get(("fwd", self.uid), weights, make)
 
     def packed_dgrad(self, si: int, weights: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -92,9 +135,7 @@ class ConvPlan:
 
         def make(dst):
             wd = dst if dst is not None else torch.zeros((s.ci_count, s.taps * self.cout), dtype=T16, device=w.device)
-            K.pack_conv_weight(w.detach(), wd, ci_begin=s.ci_begin, ci_count=s.ci_count, transpose_flip=True,
-                               fmt=K.GRAD)
-            return wd
+            return wd, [(0, 0, s.ci_begin, s.ci_count, True, K.GRAD)]
         return PACK_CACHE.get(("dgrad", self.uid, si), [w], make)
 
 
@@ -284,8 +325,7 @@ class _Stem(torch.autograd.Function):
 
         def make(dst):
             wp = dst if dst is not None else torch.zeros((cout, 64), dtype=T16, device=w.device)
-            K.pack_conv_weight(w.detach(), wp)
-            return wp
+            return wp, [(0, 0, 0, w.shape[1], False, K.ACT)]
         wp = PACK_CACHE.get(("stem", id(w)), [w], make)
         B, _, H, W = x0.shape
         out, st = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach(), want_stats=True)
@@ -323,8 +363,7 @@ class _HeadConv(torch.autograd.Function):
 
         def make(dst):
             wp = dst if dst is not None else torch.zeros((16, 9 * cin), dtype=T16, device=w.device)
-            K.pack_conv_weight(w.detach(), wp)
-            return wp
+            return wp, [(0, 0, 0, cin, False, K.ACT)]
         wp = PACK_CACHE.get(("head", id(w)), [w], make)
         B, H, W, _ = a.shape
         out = K.conv_fwd([(a, 9, 1)], wp, cout, H, W, bias=b.detach(), out_f32=True, axpy_x=axpy_x, axpy_a=axpy_a,
@@ -548,8 +587,7 @@ class _Head1x1(torch.autograd.Function):
 
         def make(dst):
             wp = dst if dst is not None else torch.zeros((16, (cin + 63) // 64 * 64), dtype=T16, device=w.device)
-            K.pack_conv_weight(w.detach(), wp)
-            return wp
+            return wp, [(0, 0, 0, cin, False, K.ACT)]
         wp = PACK_CACHE.get(("head1x1", id(w)), [w], make)
         B, H, W, _ = a.shape
         out = K.conv_fwd([(a, 1, 1)], wp, cout, H, W, bias=b.detach(), out_f32=True)
@@ -686,10 +724,14 @@ class _ResBlockFn(torch.autograd.Function):
         film = torch.addmm(eb.detach(), emb_act.detach().float(), ew.detach().t()).contiguous()
         if h_stats is not None:
             coef2, mr2 = K.gn_coef_parts([h_stats], gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
+            part2 = h_stats
         else:
             stats2 = K.gn_partial_buffer(B, H * W, cout, dev)
             K.gn_stats(h, stats2, 0)
             coef2, mr2 = K.gn_coef(stats2, gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
+            part2 = stats2
+        # sum over pixels of h per (sample, channel): lets backward write conv 1's bias gradient in closed form
+        sum_h = part2[..., 0].sum(dim=1) if train else None
         if fuse:
             a2, norms2 = h, [(coef2, 0)]
         else:
@@ -716,7 +758,7 @@ class _ResBlockFn(torch.autograd.Function):
             ctx.dual = dual
             ctx.mask = mask  # uint8 keep bits of the dropout (1 bit / element), read by the two norm-backward passes
             ctx.save_for_backward(*srcs, emb_act, h, a1g if dual else a1, a2g if dual else a2, coef1, mr1, coef2, mr2,
-                                  film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, *skip[:1])
+                                  film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, sum_h, *skip[:1])
         return out
 
     @staticmethod
@@ -725,8 +767,9 @@ class _ResBlockFn(torch.autograd.Function):
         drop_p, seed = ctx.drop
         sv = ctx.saved_tensors
         srcs = sv[:n_src]
-        emb_act, h, a1s, a2s, coef1, mr1, coef2, mr2, film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w = sv[n_src:n_src + 16]
-        sw = sv[n_src + 16] if cfg.has_skip_conv else None
+        emb_act, h, a1s, a2s, coef1, mr1, coef2, mr2, film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, sum_h = \
+            sv[n_src:n_src + 17]
+        sw = sv[n_src + 17] if cfg.has_skip_conv else None
         a1g = a1s if ctx.dual else K.convert16(a1s, K.ACT, K.GRAD)
         a2g = a2s if ctx.dual else K.convert16(a2s, K.ACT, K.GRAD)
         d_out = d_out.contiguous()
@@ -758,7 +801,7 @@ class _ResBlockFn(torch.autograd.Function):
         red2 = K.gn_partial_buffer(B, H * W, cout, dev)
         K.gn_bwd_reduce(h, d_a2, coef2, mr2, red2, 0, True, drop_p, seed, mask=ctx.mask)
         d_gn2w, d_gn2b = torch.zeros(cout, **f32), torch.zeros(cout, **f32)
-        pqr2, dfilm = K.gn_bwd_coef(red2, mr2, gn2w, gn2b, film, H * W, d_gn2w, d_gn2b, True)
+        pqr2, dfilm, red2f = K.gn_bwd_coef(red2, mr2, gn2w, gn2b, film, H * W, d_gn2w, d_gn2b, True, want_red=True)
         d_h = torch.empty_like(h)
         K.gn_bwd_apply(h, d_a2, coef2, pqr2, 0, None, d_h, True, drop_p, seed, mask=ctx.mask)
         # ---- FiLM linear
@@ -769,8 +812,9 @@ class _ResBlockFn(torch.autograd.Function):
         # ---- conv 1
         d_c1w = torch.empty_like(c1w, dtype=torch.float32)
         _wgrad_to(d_h, a1g, 9, 1, d_c1w.view(cout, ctot, -1), 0)
-        d_b1 = torch.zeros(cout, **f32)
-        K.channel_sum(d_h, d_b1)
+        # bias gradient of conv 1 = sum over pixels of d_h = sum_b (P * sum dz + Q * sum h + HW * R): closed form from
+        # per-(sample, channel) quantities that exist already -- no pass over d_h
+        d_b1 = (pqr2[..., 0] * red2f[..., 0] + pqr2[..., 1] * sum_h + float(H * W) * pqr2[..., 2]).sum(dim=0)
         d_a1 = K.conv_fwd([(d_h, 9, 1)], cfg.plan1.packed_dgrad(0, [c1w]), ctot, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD,
                           out_fmt=K.GRAD)
         # ---- norm 1 backward; the skip-path gradient is added in the same pass
