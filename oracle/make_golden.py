@@ -221,10 +221,54 @@ def paired_dataset():
     return out
 
 
+def any2any_dataset():
+    """The reference's PairedAnyToAnyDataset / ClassConditionalAnyToAnyDataModule (src/data/class_conditional_he_amyloid.py),
+    unmodified, on a tiny synthetic three-domain PNG tree."""
+    import random
+    import tempfile
+
+    import numpy as np
+    from PIL import Image
+    mod = rb.reference_module("src.data.class_conditional_he_amyloid")
+    rng = np.random.RandomState(9)
+    mapping = {0: "he", 1: "amyloid", 2: "tau"}
+    names = [f"t{k}.png" for k in range(5)]
+    imgs = {(c, n): rng.randint(0, 256, (80, 88, 3)).astype(np.uint8) for c in mapping for n in names}
+    del imgs[(2, "t4.png")]  # one file is missing in one domain: intersection drops it, union keeps it
+    out = dict(mapping=mapping, names=names, images={f"{c}/{n}": v for (c, n), v in imgs.items()})
+    with tempfile.TemporaryDirectory() as d:
+        for c, folder in mapping.items():
+            os.makedirs(os.path.join(d, folder))
+        for (c, n), v in imgs.items():
+            Image.fromarray(v).save(os.path.join(d, mapping[c], n))
+        for tag, kw in (("intersection_same_crop", dict()),
+                        ("union_separate_crops_fixed_source", dict(filename_mode="union", same_crop_for_pair=False,
+                                                                   source_domain_mode=1))):
+            ds = mod.PairedAnyToAnyDataset(d, mapping, crop_size=64, **kw)
+            torch.manual_seed(321)
+            random.seed(321)
+            items = [ds[i] for i in (0, 3, len(ds) - 1, 1)]
+            out[tag] = dict(kwargs=kw, torch_seed=321, python_seed=321, filenames=list(ds.filenames), indices=(0, 3, len(ds) - 1, 1),
+                            items=[(a, b, int(c)) for a, b, c in items])
+        dm = mod.ClassConditionalAnyToAnyDataModule(d, mapping, crop_size=64, batch_size=6, val_split=0.4, split_seed=7)
+        dm.prepare_data()
+        with open(os.path.join(d, "train_val_split.json")) as f:
+            out["split_json"] = f.read()
+
+        class _T:
+            world_size = 3
+        dm.trainer = _T()
+        dm.setup()
+        out["per_device_batch_6_over_3"] = dm.batch_size_per_device
+        out["train_len"], out["val_len"] = len(dm.data_train), len(dm.data_val)
+    torch.save(out, os.path.join(OUT, "any2any_dataset_small.pt"))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order on the CPU
-    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask, mask_variants, paired_dataset):
+    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask, mask_variants, paired_dataset, any2any_dataset):
         o = fn()
         print({k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__) for k, v in o.items()})
     for f in sorted(os.listdir(OUT)):

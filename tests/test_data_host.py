@@ -134,3 +134,58 @@ def test_png_writer_round_trip(tmp_path):
     w.submit([str(tmp_path / "b0.png"), str(tmp_path / "b1.png")], torch.from_numpy(np.stack([img, img[::-1].copy()])))
     w.wait()
     assert np.array_equal(cv2.imread(str(tmp_path / "b1.png"))[:, :, ::-1], img[::-1])
+
+
+# ---- any-to-any (class-conditional) data module: src/data/class_conditional_he_amyloid.py ------------------------------
+def _any2any_tree(tmp_path, g):
+    from PIL import Image
+    for c, folder in g["mapping"].items():
+        os.makedirs(tmp_path / folder, exist_ok=True)
+    for key, v in g["images"].items():
+        c, n = key.split("/")
+        Image.fromarray(v).save(str(tmp_path / g["mapping"][int(c)] / n))
+
+
+@pytest.mark.parametrize("tag", ["intersection_same_crop", "union_separate_crops_fixed_source"])
+def test_any2any_dataset_follows_the_reference(tmp_path, tag):
+    """Same domain choices, same crops (RNG calls in the reference's order), same normalised tiles (host statement of the
+    crop + to_tensor + normalise kernel) as the reference's PairedAnyToAnyDataset produced."""
+    from stain2stain_b200.data_any2any import PairedAnyToAnyDataset
+    g = torch.load(os.path.join(GOLD, "any2any_dataset_small.pt"), map_location="cpu", weights_only=False)
+    _any2any_tree(tmp_path, g)
+    rec = g[tag]
+    ds = PairedAnyToAnyDataset(str(tmp_path), g["mapping"], crop_size=64, **rec["kwargs"])
+    assert ds.filenames == rec["filenames"] and ds.num_classes == 3
+    torch.manual_seed(rec["torch_seed"])
+    random.seed(rec["python_seed"])
+    for idx, (want_s, want_t, want_label) in zip(rec["indices"], rec["items"]):
+        src, tgt, params, label = ds[idx]
+        assert label == want_label
+        (i, j, _, _), (i2, j2, _, _) = params.tolist()
+        assert torch.equal(_to_tensor_norm(src[i:i + 64, j:j + 64]), want_s)
+        assert torch.equal(_to_tensor_norm(tgt[i2:i2 + 64, j2:j2 + 64]), want_t)
+    with pytest.raises(ValueError):
+        PairedAnyToAnyDataset(str(tmp_path), {0: "he", 1: "missing"}, crop_size=64)
+    with pytest.raises(ValueError):
+        PairedAnyToAnyDataset(str(tmp_path), g["mapping"], crop_size=64, filename_mode="bogus")
+
+
+def test_any2any_datamodule_split_and_batch_rule(tmp_path):
+    from stain2stain_b200.data_any2any import ClassConditionalAnyToAnyDataModule
+    g = torch.load(os.path.join(GOLD, "any2any_dataset_small.pt"), map_location="cpu", weights_only=False)
+    _any2any_tree(tmp_path, g)
+    dm = ClassConditionalAnyToAnyDataModule(str(tmp_path), g["mapping"], crop_size=64, batch_size=6, val_split=0.4, split_seed=7)
+    with pytest.raises(RuntimeError):
+        dm.setup()  # no split file yet
+    dm.prepare_data()
+    assert open(tmp_path / "train_val_split.json").read() == g["split_json"]
+
+    class T:
+        world_size = 3
+    dm.trainer = T()
+    dm.setup()
+    assert dm.batch_size_per_device == g["per_device_batch_6_over_3"] == 2
+    assert (len(dm.data_train), len(dm.data_val)) == (g["train_len"], g["val_len"])
+    T.world_size = 4
+    with pytest.raises(RuntimeError):
+        dm.setup()

@@ -165,3 +165,29 @@ def test_paired_dataset_and_loader_reproduce_the_reference_items(tmp_path):
     batches = list(loader)
     assert len(batches) == 1 and batches[0][0].shape == (2, 3, 64, 64) and batches[0][0].is_cuda
     assert torch.equal(batches[0][0][0].cpu(), rec["items"][0][0]) and torch.equal(batches[0][1][1].cpu(), rec["items"][1][1])
+
+
+@pytest.mark.parametrize("tag", ["intersection_same_crop", "union_separate_crops_fixed_source"])
+def test_any2any_dataset_reproduces_the_reference_items(tmp_path, tag):
+    """src/data/class_conditional_he_amyloid.py through the device kernel: bit-identical tiles, same labels."""
+    from PIL import Image
+    from stain2stain_b200.data_any2any import AnyToAnyBatchLoader, PairedAnyToAnyDataset
+    g = torch.load(os.path.join(GOLD, "any2any_dataset_small.pt"), map_location="cpu", weights_only=False)
+    for c, folder in g["mapping"].items():
+        os.makedirs(tmp_path / folder, exist_ok=True)
+    for key, v in g["images"].items():
+        c, n = key.split("/")
+        Image.fromarray(v).save(str(tmp_path / g["mapping"][int(c)] / n))
+    rec = g[tag]
+    ds = PairedAnyToAnyDataset(str(tmp_path), g["mapping"], crop_size=64, **rec["kwargs"])
+    torch.manual_seed(rec["torch_seed"])
+    random.seed(rec["python_seed"])
+    for idx, (want_s, want_t, want_label) in zip(rec["indices"], rec["items"]):
+        s, t, label = ds.get_reference_item(idx)
+        assert label == want_label and torch.equal(s.cpu(), want_s) and torch.equal(t.cpu(), want_t)
+    loader = AnyToAnyBatchLoader(ds, batch_size=3, shuffle=False, num_workers=2)
+    batches = list(loader)
+    assert len(batches) == len(loader) == (len(ds) + 2) // 3
+    x0, x1, y = batches[0]
+    assert x0.shape == (3, 3, 64, 64) and x1.shape == x0.shape and x0.is_cuda and y.dtype == torch.int64 and y.shape == (3,)
+    assert float(x0.min()) >= -1.0 and float(x0.max()) <= 1.0
