@@ -157,6 +157,11 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
 int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
                       const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
                       uint64_t seed, const void* mask_in, int x_fmt, int g_fmt, void* stream);
+/* s2s_gn_bwd_reduce that additionally stores x as bf16 NHWC [B,HW,C] (x_bf16_out, may be NULL): the weight-gradient
+ * operand of a 1x1 skip conv over the raw block input, for +2 B/element instead of an s2s_convert16 pass. */
+int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
+                         const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
+                         uint64_t seed, const void* mask_in, void* x_bf16_out, int x_fmt, int g_fmt, void* stream);
 int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,
                     const float* film, int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta,
                     float* dfilm, void* stream);

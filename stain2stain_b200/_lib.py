@@ -57,6 +57,7 @@ SIGNATURES = {
     "s2s_gn_coef": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "s2s_gn_apply": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _vp, _i, _i, _vp],
     "s2s_gn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _vp, _i, _i, _vp],
+    "s2s_gn_bwd_reduce_x2": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _u64, _vp, _vp, _i, _i, _vp],
     "s2s_gn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "s2s_gn_chunks": [_i, _i],
     "s2s_gn_bwd_apply": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _u64, _vp, _i, _i, _vp],

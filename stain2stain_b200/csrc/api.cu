@@ -733,9 +733,9 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
     return S2S_OK;
 }
 
-int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
-                      const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
-                      uint64_t seed, const void* mask_in, int x_fmt, int g_fmt, void* stream) {
+int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
+                         const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
+                         uint64_t seed, const void* mask_in, void* x_bf16_out, int x_fmt, int g_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_bwd_reduce");
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
@@ -743,9 +743,17 @@ int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
-            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in))))));
+            (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in,
+            (__nv_bfloat16*)x_bf16_out))))));
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
+}
+
+int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int C, const float* coef,
+                      const float* mean_rstd, int G, int Ctot, int c_off, float* red, int silu, float drop_p,
+                      uint64_t seed, const void* mask_in, int x_fmt, int g_fmt, void* stream) {
+    return s2s_gn_bwd_reduce_x2(x, g, ld_g, B, HW, C, coef, mean_rstd, G, Ctot, c_off, red, silu, drop_p, seed, mask_in,
+                                nullptr, x_fmt, g_fmt, stream);
 }
 
 int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,

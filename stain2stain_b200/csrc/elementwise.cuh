@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
                                                                       const float2* __restrict__ mean_rstd, int G,
                                                                       int Ctot, int c_off, float2* __restrict__ red_out,
                                                                       float drop_p, unsigned long long seed,
-                                                                      const uint8_t* __restrict__ mask_in) {
+                                                                      const uint8_t* __restrict__ mask_in,
+                                                                      __nv_bfloat16* __restrict__ x_bf16_out) {
     constexpr int U = 2;
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
@@ -563,6 +564,10 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
         }
         float xf[8], dz[8];
         gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
+        // optional side product: x in bf16 (the weight-gradient operand of a 1x1 skip conv over the raw block input) --
+        // +2 B/element here instead of a 4 B/element conversion pass
+        if (x_bf16_out != nullptr)
+            stg_stream(reinterpret_cast<uint4*>(x_bf16_out + ((size_t)b * HW + p) * C + slot * 8), cvt8_out_t<kFmtBF16>(xf));
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s1[e] += dz[e];

@@ -316,12 +316,16 @@ def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int 
 
 
 def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
-                  g_fmt: int = GRAD, mask=None):
+                  g_fmt: int = GRAD, mask=None, x_bf16_out=None):
+    """x_bf16_out (optional, same shape as x): receives x stored as bf16 (side product for a later weight gradient)."""
     B, H, W, Cc = x.shape
-    with _Prof("gn_bwd_reduce_dropout" if drop_p > 0 else "gn_bwd_reduce", 0.0, 4.0 * x.numel()):  # reads x and g
-        check(_L().s2s_gn_bwd_reduce(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
-                                     coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), ptr(mask),
-                                     x_fmt, g_fmt, stream_ptr()), "gn_bwd_reduce")
+    if x_bf16_out is not None:
+        assert x_bf16_out.shape == x.shape and x_bf16_out.dtype == T16 and x_bf16_out.is_contiguous()
+    nbytes = (4.0 + (2.0 if x_bf16_out is not None else 0.0)) * x.numel()  # reads x and g (+ writes the bf16 copy)
+    with _Prof("gn_bwd_reduce_dropout" if drop_p > 0 else "gn_bwd_reduce", 0.0, nbytes):
+        check(_L().s2s_gn_bwd_reduce_x2(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(mr), mr.shape[1],
+                                        coef.shape[1], c_off, ptr(red), int(silu), float(drop_p), int(seed), ptr(mask),
+                                        ptr(x_bf16_out), x_fmt, g_fmt, stream_ptr()), "gn_bwd_reduce")
 
 
 def gn_bwd_coef(red_part, mr, gamma, beta, film, HW: int, dgamma, dbeta, want_dfilm: bool, want_red: bool = False):

@@ -787,14 +787,11 @@ class _ResBlockFn(torch.autograd.Function):
         d_skip: List[torch.Tensor] = []
         d_sw = None
         if cfg.has_skip_conv:
-            d_sw = torch.empty_like(sw, dtype=torch.float32)
-            off = 0
+            # data gradient of the 1x1 skip conv now; its weight gradient needs the raw inputs in bf16, which the first
+            # norm's backward reduce pass (it reads them anyway) writes as a side product further down
             for i, s in enumerate(srcs):
-                ci = s.shape[3]
-                _wgrad_to(d_out, K.convert16(s, K.ACT, K.GRAD), 1, 1, d_sw.view(cout, ctot, -1), off)
-                d_skip.append(K.conv_fwd([(d_out, 1, 1)], cfg.plan2.packed_dgrad(1 + i, [c2w, sw]), ci, H, W,
+                d_skip.append(K.conv_fwd([(d_out, 1, 1)], cfg.plan2.packed_dgrad(1 + i, [c2w, sw]), s.shape[3], H, W,
                                          a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD))
-                off += ci
         else:
             d_skip.append(d_out)
         # ---- norm 2 backward
@@ -820,8 +817,14 @@ class _ResBlockFn(torch.autograd.Function):
         # ---- norm 1 backward; the skip-path gradient is added in the same pass
         red1 = K.gn_partial_buffer(B, H * W, ctot, dev)
         off = 0
+        need_raw = cfg.has_skip_conv and ctx.dual
+        if cfg.has_skip_conv:
+            d_sw = torch.empty_like(sw, dtype=torch.float32)
         for s in srcs:
-            K.gn_bwd_reduce(s, d_a1, coef1, mr1, red1, off, True)
+            s_g = torch.empty_like(s) if need_raw else None
+            K.gn_bwd_reduce(s, d_a1, coef1, mr1, red1, off, True, x_bf16_out=s_g)
+            if cfg.has_skip_conv:
+                _wgrad_to(d_out, s_g if need_raw else K.convert16(s, K.ACT, K.GRAD), 1, 1, d_sw.view(cout, ctot, -1), off)
             off += s.shape[3]
         d_gn1w, d_gn1b = torch.zeros(ctot, **f32), torch.zeros(ctot, **f32)
         pqr1, _ = K.gn_bwd_coef(red1, mr1, gn1w, gn1b, None, H * W, d_gn1w, d_gn1b, False)

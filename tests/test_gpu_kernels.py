@@ -472,3 +472,25 @@ def test_conv_with_fused_norm_prologue_matches_apply_then_conv(B, H, W, C0, C1, 
     assert rel_l2(a, b) <= 1e-3, rel_l2(a, b)
     assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max())
     assert torch.allclose(st, st_w, rtol=2e-2, atol=2e-2 * float(st_w.abs().max()))
+
+
+def test_gn_bwd_reduce_bf16_side_copy_equals_convert16():
+    """The norm backward reduce pass can store its input as bf16 on the way (the skip conv's weight-gradient operand):
+    same bits as s2s_convert16, same reduction result as without the side product."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(41)
+    B, H, W, C = 2, 24, 20, 192
+    x = nhwc(rb(torch.randn(B, C, H, W, device=DEV, generator=g)))
+    gy = nhwc(rb(torch.randn(B, C, H, W, device=DEV, generator=g), "grad"), "grad")
+    gamma = 1 + 0.1 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(C, device=DEV, generator=g)
+    stats = k.gn_partial_buffer(B, H * W, C, DEV)
+    k.gn_stats(x, stats, 0)
+    coef, mr = k.gn_coef(stats, gamma, beta, None, H * W)
+    red_a = k.gn_partial_buffer(B, H * W, C, DEV)
+    red_b = k.gn_partial_buffer(B, H * W, C, DEV)
+    k.gn_bwd_reduce(x, gy, coef, mr, red_a, 0, True)
+    side = torch.full_like(x, float("nan"))
+    k.gn_bwd_reduce(x, gy, coef, mr, red_b, 0, True, x_bf16_out=side)
+    assert torch.equal(red_a, red_b)
+    assert torch.equal(side.view(torch.int16), k.convert16(x, k.ACT, k.GRAD).view(torch.int16))
