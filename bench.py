@@ -530,11 +530,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "sample", "multitask"])
-    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 32)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 64; 4096 tiles on 8 GPUs = 8 micro-batches per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = {"train": 64, "sample": 32, "multitask": 16}[args.mode]
+        args.batch = {"train": 64, "sample": 64, "multitask": 16}[args.mode]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
