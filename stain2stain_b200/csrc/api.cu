@@ -711,9 +711,18 @@ int s2s_gn_coef_parts(const float* stats0, int C0, const float* stats1, int C1, 
     if (G > 64 || C % G || !stats0 || C0 <= 0 || (C1 > 0 && !stats1))
         return fail(S2S_ERR_INVALID, "gn_coef_parts: G = %d, C = %d + %d unsupported", G, C0, C1);
     if (C > 4096) return fail(S2S_ERR_INVALID, "gn_coef_parts: C = %d unsupported (<= 4096)", C);
-    gn_coef_parts_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    if ((C0 | C1) & 1) return fail(S2S_ERR_INVALID, "gn_coef_parts: channel counts must be even");
+    const int threads = 1024;
+    int slices = threads / (C / 2);
+    if (slices < 1) slices = 1;
+    if (slices > 16) slices = 16;
+    if (slices > nchunks) slices = nchunks;
+    const size_t smem = (size_t)(2 * C) * (1 + slices) * sizeof(float);  // <= 2 * 4096 * 2 * 4 = 64 KB at slices = 1
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(gn_coef_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gn_coef_parts_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(
         (const float2*)stats0, C0, (const float2*)stats1, C1, nchunks, gamma, beta, film, G, HW, eps, (float2*)coef,
-        (float2*)mean_rstd);
+        (float2*)mean_rstd, slices);
     LAUNCH_CHECK("gn_coef_parts_kernel");
     return S2S_OK;
 }

@@ -390,7 +390,7 @@ def test_stored_dropout_mask_equals_rehash():
 
 @pytest.mark.parametrize("taps", [9, 1])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 128), (3, 16, 48, 64, 256), (2, 24, 20, 128, 128),
-                                            (1, 8, 8, 256, 512), (3, 40, 40, 128, 128)])
+                                            (1, 8, 8, 256, 512), (3, 40, 40, 128, 128), (1, 128, 144, 64, 128)])
 def test_conv_epilogue_statistics_match_a_stats_pass(B, H, W, Cin, Cout, taps):
     """GroupNorm statistics emitted by the CTA-pair conv epilogues (per 128-pixel sub-tile, from the staged 16-bit tile)
     give the same coefficients as a separate gn_stats pass over the stored tensor -- incl. ragged tiles.  taps = 9 runs
