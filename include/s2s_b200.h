@@ -203,10 +203,11 @@ int s2s_roi_charbonnier(const float* x0, const float* x1, const float* t, const 
 
 /* Input side (src/data/paired_data_module.py:171-199): uint8 HWC tile pair [B,Hs,Ws,3] (+ optional uint8 mask
  * [B,Hs,Ws]) -> crop(top,left,S,S) -> hflip -> vflip -> to_tensor -> Normalize(0.5,0.5) -> fp32 NCHW [B,3,S,S],
- * bit-identical to the torchvision chain.  params: int32 [B][4] = (top, left, hflip, vflip); bgr != 0 if the bytes are
- * in cv2.imread order.  tgt/out1 and mask/outm may be NULL. */
+ * bit-identical to the torchvision chain.  params: int32 [B][4] = (top, left, hflip, vflip); flags bit 0: the colour
+ * bytes are in cv2.imread (BGR) order; flags bit 1: the mask is written as its raw byte value (class ids,
+ * src/data/paired_data_multiclassmask.py:113-128) instead of mask / 255.  tgt/out1 and mask/outm may be NULL. */
 int s2s_tile_prep(const uint8_t* src, const uint8_t* tgt, const uint8_t* mask, const int* params, int B, int Hs, int Ws,
-                  int S, int bgr, float* out0, float* out1, float* outm, void* stream);
+                  int S, int flags, float* out0, float* out1, float* outm, void* stream);
 
 /* One pass of Pillow's antialiased 8-bit resampling (TF.resize on a PIL image, paired_data_module.py:201-203):
  * out = clip8((2^21 + sum_k in[first+k]*kk[k]) >> 22).  bounds int32 [n_out][2] = (first, count), kk int32

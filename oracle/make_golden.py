@@ -265,10 +265,55 @@ def any2any_dataset():
     return out
 
 
+def mask_datasets():
+    """The reference's mask-carrying datasets, unmodified: src/data/paired_data_multiclassmask.py (config M's data: class-id
+    mask, same crop / flips as the tiles, Pillow NEAREST on the eval path) and src/data/paired_data_mask_he_amyloid.py
+    (binarised mask, cv2 INTER_NEAREST)."""
+    import random
+    import tempfile
+
+    import cv2
+    import numpy as np
+    mc = rb.reference_module("src.data.paired_data_multiclassmask")
+    ha = rb.reference_module("src.data.paired_data_mask_he_amyloid")
+    rng = np.random.RandomState(13)
+    n, h, w = 2, 90, 100
+    imgs = {}
+    rows = []
+    for k in range(n):
+        imgs[f"i{k}_he.png"] = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        imgs[f"i{k}_ihc.png"] = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        imgs[f"i{k}_gw.png"] = rng.randint(0, 5, (h, w)).astype(np.uint8)          # class ids 0..4
+        imgs[f"i{k}_am.png"] = (rng.randint(0, 4, (h, w)) * 85).astype(np.uint8)   # 0, 85, 170, 255
+        rows.append((f"i{k}_he.png", f"i{k}_ihc.png", f"i{k}_gw.png", f"i{k}_am.png", "train"))
+    out = dict(images=imgs, rows=rows)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "train"))
+        with open(os.path.join(d, "meta.csv"), "w") as f:
+            f.write("image_id,he_filepath,ihc_filepath,graywhite_filepath,amyloid_filepath,split\n")
+            for k, r in enumerate(rows):
+                f.write(f"{k},{','.join(r)}\n")
+        for name, v in imgs.items():
+            cv2.imwrite(os.path.join(d, "train", name), v if v.ndim == 2 else cv2.cvtColor(v, cv2.COLOR_RGB2BGR))
+        kw = dict(data_dir=d, csv_file_name="meta.csv", source_column="he_filepath", target_column="ihc_filepath", folder="train")
+        ds = mc.PairedDataset(image_size=64, use_augmentation=True, **kw)
+        torch.manual_seed(55)
+        random.seed(55)
+        out["multiclass_train_aug"] = dict(torch_seed=55, python_seed=55, image_size=64, items=[ds[0], ds[1], ds[1]])
+        ds = mc.PairedDataset(image_size=48, use_augmentation=False, direction="T2S", **kw)
+        out["multiclass_eval48_T2S"] = ds[1]
+        ds = ha.PairedHEIHCDataset(image_size=48, **kw)
+        out["he_amyloid_eval48"] = ds[0]
+        ds = ha.PairedHEIHCDataset(image_size=64, direction="IHC_to_HE", **kw)
+        out["he_amyloid_eval64_reverse"] = ds[1]
+    torch.save(out, os.path.join(OUT, "mask_datasets_small.pt"))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order on the CPU
-    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask, mask_variants, paired_dataset, any2any_dataset):
+    for fn in (lambda: simple_fm(False), lambda: simple_fm(True), multitask, mask_variants, paired_dataset, any2any_dataset, mask_datasets):
         o = fn()
         print({k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__) for k, v in o.items()})
     for f in sorted(os.listdir(OUT)):

@@ -870,11 +870,11 @@ int s2s_roi_charbonnier(const float* x0, const float* x1, const float* t, const 
 }
 
 int s2s_tile_prep(const uint8_t* src, const uint8_t* tgt, const uint8_t* mask, const int* params, int B, int Hs, int Ws,
-                  int S, int bgr, float* out0, float* out1, float* outm, void* stream) {
+                  int S, int flags, float* out0, float* out1, float* outm, void* stream) {
     if (!src || !params || !out0 || (tgt && !out1) || (mask && !outm) || S <= 0 || S > Hs || S > Ws)
         return fail(S2S_ERR_INVALID, "tile_prep: bad arguments");
     tile_prep_kernel<<<ew_grid((long long)B * S * S), kEwThreads, 0, (cudaStream_t)stream>>>(src, tgt, mask, params, B, Hs, Ws,
-                                                                                          S, bgr, out0, out1, outm);
+                                                                                          S, flags, out0, out1, outm);
     LAUNCH_CHECK("tile_prep_kernel");
     return S2S_OK;
 }

@@ -135,12 +135,15 @@ __global__ void __launch_bounds__(kEwThreads) roi_charbonnier_kernel(
 //   out[b,c,y,x] = (u8[b, top + (vflip ? S-1-y : y), left + (hflip ? S-1-x : x), c] / 255 - 0.5) / 0.5
 // i.e. TF.crop -> TF.hflip -> TF.vflip -> TF.to_tensor -> Normalize(0.5, 0.5) (paired_data_module.py:171-199), with
 // IEEE division / subtraction so that the result is bit-identical to the torchvision chain.
-// mask (optional): uint8 [B,Hs,Ws] -> outm fp32 [B,1,S,S] = mask / 255 (to_tensor of a single-channel PIL image).
+// mask (optional): uint8 [B,Hs,Ws] -> outm fp32 [B,1,S,S] = mask / 255 (to_tensor of a single-channel PIL image), or the
+// raw byte value as a float when flags bit 1 is set (class-id masks: `torch.from_numpy(np.array(mask)).float()`,
+// src/data/paired_data_multiclassmask.py:113-128).  flags bit 0: the colour bytes are BGR.
 __global__ void __launch_bounds__(kEwThreads) tile_prep_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ tgt,
                                                                const uint8_t* __restrict__ mask,
                                                                const int* __restrict__ params, int B, int Hs, int Ws, int S,
-                                                               int bgr, float* __restrict__ out0, float* __restrict__ out1,
+                                                               int flags, float* __restrict__ out0, float* __restrict__ out1,
                                                                float* __restrict__ outm) {
+    const int bgr = flags & 1, mask_raw = flags & 2;
     const long long n = (long long)B * S * S;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % S);
@@ -159,8 +162,10 @@ __global__ void __launch_bounds__(kEwThreads) tile_prep_kernel(const uint8_t* __
             out0[oo + c * plane] = a;
             if (tgt != nullptr) out1[oo + c * plane] = __fsub_rn(__fdiv_rn((float)tgt[so + sc], 255.f), 0.5f) * 2.f;
         }
-        if (mask != nullptr)
-            outm[(size_t)b * plane + (size_t)y * S + x] = __fdiv_rn((float)mask[((size_t)b * Hs + sy) * Ws + sx], 255.f);
+        if (mask != nullptr) {
+            const float mv = (float)mask[((size_t)b * Hs + sy) * Ws + sx];
+            outm[(size_t)b * plane + (size_t)y * S + x] = mask_raw ? mv : __fdiv_rn(mv, 255.f);
+        }
     }
 }
 

@@ -119,7 +119,8 @@ def draw_augment_params(n: int, src_h: int, src_w: int, size: int) -> torch.Tens
 
 
 def prepare_tiles(src_u8: torch.Tensor, tgt_u8: Optional[torch.Tensor], size: int, use_augmentation: bool,
-                  bgr: bool = False, params: Optional[torch.Tensor] = None, mask_u8: Optional[torch.Tensor] = None):
+                  bgr: bool = False, params: Optional[torch.Tensor] = None, mask_u8: Optional[torch.Tensor] = None,
+                  mask_raw: bool = False):
     """uint8 NHWC device batches -> fp32 NCHW normalised tiles (x0, x1[, mask]) exactly as the reference's dataset
     produces them: train = crop/flip, eval = antialiased resize (paired_data_module.py:171-210)."""
     from . import kernels as K
@@ -132,11 +133,41 @@ def prepare_tiles(src_u8: torch.Tensor, tgt_u8: Optional[torch.Tensor], size: in
     else:
         src_u8 = resize_u8(src_u8, size, size)
         tgt_u8 = None if tgt_u8 is None else resize_u8(tgt_u8, size, size)
-        if mask_u8 is not None and (H != size or W != size):
-            raise NotImplementedError("mask resizing follows another interpolation rule; give masks at the tile size")
+        if mask_u8 is not None and tuple(mask_u8.shape[1:]) != (size, size):
+            raise ValueError("eval path: resize the mask on the host first (nearest_resize_pil / nearest_resize_cv2): it "
+                             "follows another interpolation rule than the images")
         params = torch.zeros((B, 4), dtype=torch.int32, device=dev)
-    x0, x1, m = K.tile_prep(src_u8, tgt_u8, params, size, bgr=bgr, mask_u8=mask_u8)
+    x0, x1, m = K.tile_prep(src_u8, tgt_u8, params, size, bgr=bgr, mask_u8=mask_u8, mask_raw=mask_raw)
     return (x0, x1) if mask_u8 is None else (x0, x1, m)
+
+
+# ------------------------------------------------------------------------------------------------ nearest-neighbour mask resizing
+def _pil_nearest_index(in_size: int, out_size: int) -> np.ndarray:
+    """Pillow's ImagingScaleAffine: xo = a/2, then `xo += a` per output pixel (ACCUMULATED in double, which is what
+    decides the ties of non-integer ratios), index = (int) xo."""
+    a = float(in_size) / out_size
+    idx = np.empty(out_size, dtype=np.int64)
+    xo = a * 0.5
+    for o in range(out_size):
+        idx[o] = min(int(xo), in_size - 1)
+        xo += a
+    return idx
+
+
+def nearest_resize_pil(mask: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """`TF.resize(pil_mask, (h, w), interpolation=NEAREST)` (src/data/paired_data_multiclassmask.py:121): Pillow samples the
+    pixel under the centre of each output pixel."""
+    h, w = mask.shape[:2]
+    return mask[_pil_nearest_index(h, out_h)][:, _pil_nearest_index(w, out_w)]
+
+
+def nearest_resize_cv2(mask: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """`cv2.resize(mask, (w, h), interpolation=cv2.INTER_NEAREST)` (src/data/paired_data_mask_he_amyloid.py:89): OpenCV
+    samples at the output pixel's ORIGIN, index = min(floor(o * in / out), in - 1)."""
+    h, w = mask.shape[:2]
+    ys = np.minimum(np.floor(np.arange(out_h) * (h / out_h)).astype(np.int64), h - 1)
+    xs = np.minimum(np.floor(np.arange(out_w) * (w / out_w)).astype(np.int64), w - 1)
+    return mask[ys][:, xs]
 
 
 # ------------------------------------------------------------------------------------------------ dataset / datamodule mirrors
@@ -186,6 +217,65 @@ class PairedDataset:
         if self.return_filename:
             return (a, b, sf, tf) if self.direction == "S2T" else (a, b, tf, sf)
         return a, b
+
+
+class PairedMulticlassMaskDataset(PairedDataset):
+    """`src.data.paired_data_multiclassmask.PairedDataset` (the multitask model's data, config M): tile pair + a
+    class-id mask.  Train: the SAME crop / flips for all three (one kernel); eval: antialiased resize for the images,
+    Pillow NEAREST for the mask (:119-123).  The mask comes back as fp32 [1, S, S] holding the raw class ids."""
+
+    def __init__(self, data_dir, csv_file_name, source_column, target_column, folder, mask_column='graywhite_filepath',
+                 image_size=512, direction="S2T", use_augmentation=False):
+        super().__init__(data_dir, csv_file_name, source_column, target_column, folder, image_size, direction,
+                         use_augmentation)
+        self.mask_dir = os.path.join(data_dir, folder)
+        self.mask_column = mask_column
+
+    def __getitem__(self, idx):
+        import cv2
+        s, t, sf, tf = super().__getitem__(idx)
+        mp = os.path.join(self.mask_dir, self.metadata.iloc[idx][self.mask_column])
+        assert os.path.exists(mp), f"Mask image not found: {mp}"
+        return s, t, cv2.imread(mp, cv2.IMREAD_GRAYSCALE)
+
+    def get_reference_item(self, idx, device="cuda"):
+        s, t, m = self[idx]
+        S = self.image_size
+        if not self.use_augmentation:
+            m = nearest_resize_pil(m, S, S)
+        su = torch.from_numpy(s).unsqueeze(0).to(device)
+        tu = torch.from_numpy(t).unsqueeze(0).to(device)
+        mu = torch.from_numpy(np.ascontiguousarray(m)).unsqueeze(0).to(device)
+        x0, x1, mask = prepare_tiles(su, tu, S, self.use_augmentation, bgr=True, mask_u8=mu, mask_raw=True)
+        return (x0[0], x1[0], mask[0]) if self.direction == "S2T" else (x1[0], x0[0], mask[0])
+
+
+class PairedHEIHCMaskDataset(PairedDataset):
+    """`src.data.paired_data_mask_he_amyloid.PairedHEIHCDataset` (the mask / ROI LitModules' data): resized tile pair +
+    a binarised uint8 mask [1, S, S]: `cv2.resize(..., INTER_NEAREST)` then `> 1` (:88-91)."""
+
+    def __init__(self, data_dir, csv_file_name, source_column, target_column, folder, image_size=512,
+                 direction="HE_to_IHC"):
+        super().__init__(data_dir, csv_file_name, source_column, target_column, folder, image_size, "S2T", False)
+        self.he_ihc_direction = direction
+        self.mask_dir = os.path.join(data_dir, folder)
+        self.mask_column = 'amyloid_filepath'
+
+    def __getitem__(self, idx):
+        import cv2
+        s, t, sf, tf = super().__getitem__(idx)
+        mp = os.path.join(self.mask_dir, self.metadata.iloc[idx][self.mask_column])
+        assert os.path.exists(mp), f"Mask image not found: {mp}"
+        m = nearest_resize_cv2(cv2.imread(mp, cv2.IMREAD_GRAYSCALE), self.image_size, self.image_size)
+        return s, t, np.where(m > 1, 1, 0).astype(np.uint8)
+
+    def get_reference_item(self, idx, device="cuda"):
+        s, t, m = self[idx]
+        su = torch.from_numpy(s).unsqueeze(0).to(device)
+        tu = torch.from_numpy(t).unsqueeze(0).to(device)
+        x0, x1 = prepare_tiles(su, tu, self.image_size, False, bgr=True)
+        mask = torch.from_numpy(m).unsqueeze(0).to(device)
+        return (x0[0], x1[0], mask) if self.he_ihc_direction == "HE_to_IHC" else (x1[0], x0[0], mask)
 
 
 class TileBatchLoader:

@@ -557,9 +557,10 @@ def roi_charbonnier(x0, x1, t, mask, eps: float = 1e-3):
 
 
 def tile_prep(src_u8: torch.Tensor, tgt_u8: Optional[torch.Tensor], params: torch.Tensor, size: int, bgr: bool = False,
-              mask_u8: Optional[torch.Tensor] = None):
+              mask_u8: Optional[torch.Tensor] = None, mask_raw: bool = False):
     """uint8 HWC tiles [B,Hs,Ws,3] (+ target, + uint8 mask [B,Hs,Ws]) -> crop/flip/to_tensor/normalise -> fp32 NCHW.
-    params: int32 [B,4] = (top, left, hflip, vflip) on the device."""
+    params: int32 [B,4] = (top, left, hflip, vflip) on the device.  mask_raw: the mask output is the byte value as a
+    float (class ids) instead of byte / 255."""
     assert src_u8.dtype == torch.uint8 and src_u8.is_contiguous() and src_u8.dim() == 4 and src_u8.shape[3] == 3
     B, Hs, Ws, _ = src_u8.shape
     assert params.dtype == torch.int32 and tuple(params.shape) == (B, 4) and params.is_contiguous()
@@ -572,7 +573,8 @@ def tile_prep(src_u8: torch.Tensor, tgt_u8: Optional[torch.Tensor], params: torc
     outm = torch.empty((B, 1, size, size), dtype=torch.float32, device=src_u8.device) if mask_u8 is not None else None
     n_img = 1 + (tgt_u8 is not None)
     with _Prof("tile_prep", 0.0, 15.0 * n_img * B * size * size):
-        check(_L().s2s_tile_prep(ptr(src_u8), ptr(tgt_u8), ptr(mask_u8), ptr(params), B, Hs, Ws, size, int(bgr), ptr(out0),
+        check(_L().s2s_tile_prep(ptr(src_u8), ptr(tgt_u8), ptr(mask_u8), ptr(params), B, Hs, Ws, size,
+                                 int(bool(bgr)) | (2 if mask_raw else 0), ptr(out0),
                                  ptr(out1), ptr(outm), stream_ptr()), "tile_prep")
     return out0, out1, outm
 

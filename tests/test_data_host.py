@@ -189,3 +189,62 @@ def test_any2any_datamodule_split_and_batch_rule(tmp_path):
     T.world_size = 4
     with pytest.raises(RuntimeError):
         dm.setup()
+
+
+# ---- mask-carrying datasets: src/data/paired_data_multiclassmask.py, src/data/paired_data_mask_he_amyloid.py -------------
+@pytest.mark.parametrize("src,dst", [((96, 96), (48, 48)), ((90, 100), (64, 64)), ((50, 70), (64, 64)), ((100, 100), (37, 53)),
+                                     ((333, 217), (100, 300)), ((7, 5), (64, 33))])
+def test_nearest_mask_resize_rules_match_pillow_and_opencv(src, dst):
+    import cv2
+    from PIL import Image
+    m = np.random.RandomState(src[0] + dst[0]).randint(0, 6, src).astype(np.uint8)
+    assert np.array_equal(D.nearest_resize_pil(m, *dst), np.asarray(Image.fromarray(m).resize((dst[1], dst[0]), Image.NEAREST)))
+    assert np.array_equal(D.nearest_resize_cv2(m, *dst), cv2.resize(m, (dst[1], dst[0]), interpolation=cv2.INTER_NEAREST))
+
+
+def _mask_tree(tmp_path, g):
+    import cv2
+    os.makedirs(tmp_path / "train", exist_ok=True)
+    with open(tmp_path / "meta.csv", "w") as f:
+        f.write("image_id,he_filepath,ihc_filepath,graywhite_filepath,amyloid_filepath,split\n")
+        for k, r in enumerate(g["rows"]):
+            f.write(f"{k},{','.join(r)}\n")
+    for name, v in g["images"].items():
+        cv2.imwrite(str(tmp_path / "train" / name), v if v.ndim == 2 else cv2.cvtColor(v, cv2.COLOR_RGB2BGR))
+    return dict(data_dir=str(tmp_path), csv_file_name="meta.csv", source_column="he_filepath", target_column="ihc_filepath",
+                folder="train")
+
+
+def test_mask_datasets_follow_the_reference_host_side(tmp_path):
+    """Decode + mask rules + RNG protocol of the two mask datasets against the items the reference's own datasets returned
+    (the tile arithmetic is the host statement of the device kernel; the GPU tier runs the kernel itself)."""
+    g = torch.load(os.path.join(GOLD, "mask_datasets_small.pt"), map_location="cpu", weights_only=False)
+    kw = _mask_tree(tmp_path, g)
+    rec = g["multiclass_train_aug"]
+    ds = D.PairedMulticlassMaskDataset(image_size=rec["image_size"], use_augmentation=True, **kw)
+    torch.manual_seed(rec["torch_seed"])
+    random.seed(rec["python_seed"])
+    params = D.draw_augment_params(3, 90, 100, rec["image_size"])
+    S = rec["image_size"]
+    for (top, left, hf, vf), idx, want in zip(params.tolist(), (0, 1, 1), rec["items"]):
+        s, t, m = ds[idx]
+        outs = []
+        for a in (s[:, :, ::-1], t[:, :, ::-1], m):
+            a = a[top:top + S, left:left + S]
+            a = a[:, ::-1] if hf else a
+            a = a[::-1] if vf else a
+            outs.append(np.ascontiguousarray(a))
+        assert torch.equal(_to_tensor_norm(outs[0]), want[0]) and torch.equal(_to_tensor_norm(outs[1]), want[1])
+        assert torch.equal(torch.from_numpy(outs[2]).float().unsqueeze(0), want[2])
+    # eval: Pillow NEAREST for the class-id mask
+    ds = D.PairedMulticlassMaskDataset(image_size=48, use_augmentation=False, direction="T2S", **kw)
+    s, t, m = ds[1]
+    want = g["multiclass_eval48_T2S"]
+    assert torch.equal(torch.from_numpy(D.nearest_resize_pil(m, 48, 48)).float().unsqueeze(0), want[2])
+    assert torch.equal(_to_tensor_norm(_resize_numpy(t[:, :, ::-1], 48, 48)), want[0])  # T2S: target first
+    # binarised amyloid mask: cv2 INTER_NEAREST, then > 1
+    ds = D.PairedHEIHCMaskDataset(image_size=48, **kw)
+    s, t, m = ds[0]
+    want = g["he_amyloid_eval48"]
+    assert m.dtype == np.uint8 and torch.equal(torch.from_numpy(m).unsqueeze(0), want[2])
+    assert torch.equal(_to_tensor_norm(_resize_numpy(s[:, :, ::-1], 48, 48)), want[0])

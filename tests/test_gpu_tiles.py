@@ -191,3 +191,34 @@ def test_any2any_dataset_reproduces_the_reference_items(tmp_path, tag):
     x0, x1, y = batches[0]
     assert x0.shape == (3, 3, 64, 64) and x1.shape == x0.shape and x0.is_cuda and y.dtype == torch.int64 and y.shape == (3,)
     assert float(x0.min()) >= -1.0 and float(x0.max()) <= 1.0
+
+
+def test_mask_datasets_reproduce_the_reference_items(tmp_path):
+    """src/data/paired_data_multiclassmask.py and paired_data_mask_he_amyloid.py through the device kernels (raw class-id
+    mask path of tile_prep included): bit-identical to the items the reference's datasets returned."""
+    import cv2
+    from stain2stain_b200 import data as D
+    g = torch.load(os.path.join(GOLD, "mask_datasets_small.pt"), map_location="cpu", weights_only=False)
+    os.makedirs(tmp_path / "train", exist_ok=True)
+    with open(tmp_path / "meta.csv", "w") as f:
+        f.write("image_id,he_filepath,ihc_filepath,graywhite_filepath,amyloid_filepath,split\n")
+        for k, r in enumerate(g["rows"]):
+            f.write(f"{k},{','.join(r)}\n")
+    for name, v in g["images"].items():
+        cv2.imwrite(str(tmp_path / "train" / name), v if v.ndim == 2 else cv2.cvtColor(v, cv2.COLOR_RGB2BGR))
+    kw = dict(data_dir=str(tmp_path), csv_file_name="meta.csv", source_column="he_filepath", target_column="ihc_filepath",
+              folder="train")
+    rec = g["multiclass_train_aug"]
+    ds = D.PairedMulticlassMaskDataset(image_size=rec["image_size"], use_augmentation=True, **kw)
+    torch.manual_seed(rec["torch_seed"])
+    random.seed(rec["python_seed"])
+    for idx, want in zip((0, 1, 1), rec["items"]):
+        got = ds.get_reference_item(idx)
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(got, want))
+    ds = D.PairedMulticlassMaskDataset(image_size=48, use_augmentation=False, direction="T2S", **kw)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(ds.get_reference_item(1), g["multiclass_eval48_T2S"]))
+    ds = D.PairedHEIHCMaskDataset(image_size=48, **kw)
+    got = ds.get_reference_item(0)
+    assert got[2].dtype == torch.uint8 and all(torch.equal(a.cpu(), b) for a, b in zip(got, g["he_amyloid_eval48"]))
+    ds = D.PairedHEIHCMaskDataset(image_size=64, direction="IHC_to_HE", **kw)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(ds.get_reference_item(1), g["he_amyloid_eval64_reverse"]))
