@@ -33,16 +33,32 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library in-tree.  Safe when several ranks of one node call it at once (torchrun): one process builds
+    under a file lock, into a temporary file that is renamed into place; the others wait and find it fresh."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another rank built it while we waited
+                return LIB_PATH
+            tmp = LIB_PATH + f".tmp.{os.getpid()}"
+            cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                   "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd), file=sys.stderr)
+            try:
+                subprocess.run(cmd, check=True, cwd=CSRC)
+                os.replace(tmp, LIB_PATH)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
