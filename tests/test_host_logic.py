@@ -158,3 +158,45 @@ def test_conv_plan_bookkeeping():
     assert p.ktot() == 9 * 128 + 256 + 128  # channel counts are padded to 64-wide k-blocks per segment
     q = ConvPlan((Seg(0, 0, 0, 64, 9, 2),), 64)
     assert q.uid != p.uid and q.ktot() == 576
+
+
+def test_pack_cache_refreshes_every_stale_operand_in_one_launch(monkeypatch):
+    """The packed-operand cache: first use packs one operand, an in-place parameter update (optimizer step: same storage,
+    new version) makes ALL operands of those parameters stale and the next request re-packs them with ONE multi-tensor
+    launch into the SAME buffers; dead parameters drop out.  (A cache that missed the version bump served the initial
+    weights for ever -- the bug the entry-point test found.)"""
+    import gc
+
+    import torch
+
+    from stain2stain_b200 import kernels as K
+    from stain2stain_b200 import ops
+    calls = []
+    monkeypatch.setattr(K, "pack_conv_weight", lambda w, dst, **kw: calls.append(("one", w.data_ptr())))
+    monkeypatch.setattr(K, "pack_conv_weight_multi", lambda jobs, tc: calls.append(("multi", sorted(j[0].data_ptr() for j in jobs))))
+    pc = ops._PackCache()
+    w1 = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))
+    w2 = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))
+
+    def make(dst):
+        return (dst if dst is not None else torch.zeros(8, 64, dtype=K.T16)), [(0, 0, 0, 4, False, K.ACT)]
+    a = pc.get(("a",), [w1], make)
+    b = pc.get(("b",), [w2], make)
+    assert pc.get(("a",), [w1], make) is a and len(calls) == 2          # fresh hit: nothing packed
+    with torch.no_grad():
+        w1.add_(1)
+        w2.add_(1)
+    assert pc.get(("a",), [w1], make) is a                                # same buffer, refreshed in place ...
+    assert calls[-1] == ("multi", sorted([w1.data_ptr(), w2.data_ptr()]))  # ... together with every other stale operand
+    assert pc.get(("b",), [w2], make) is b and len(calls) == 3            # already fresh
+    torch.autograd.graph.increment_version(w1)                            # what FusedAdam does after its raw-pointer update
+    assert pc.get(("a",), [w1], make) is a and calls[-1] == ("multi", [w1.data_ptr()])
+    w3 = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))                      # replaced parameter (other storage): new operand
+    a3 = pc.get(("a",), [w3], make)
+    assert a3 is not a and calls[-1] == ("one", w3.data_ptr())
+    del w2, b
+    gc.collect()
+    with torch.no_grad():
+        w3.add_(1)
+    pc.get(("a",), [w3], make)
+    assert ("b",) not in pc._store                                        # entries of dead parameters are dropped
