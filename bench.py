@@ -169,7 +169,11 @@ def run_train(args, rank, world, local):
     lit.train()
     step_mod = _StepModule(lit)
     if world > 1:
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True)
+        # ONE bucket: a single flat fp32 all-reduce (284 MB, < 1 ms over NVSwitch) right after backward.  The default
+        # 25 MB buckets put ~12 ncclAllReduce kernels next to persistent 148-CTA tcgen05 kernels whose static tile
+        # schedule turns every SM NCCL holds into a second wave (round 1: +9.4 ms per step at 8 GPUs).
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True,
+                                                             bucket_cap_mb=args.bucket_mb)
     opt = lit.configure_optimizers()["optimizer"]
     g = torch.Generator(device=dev).manual_seed(1984 + rank)
     # inputs larger than L2 (2 x 50 MB per step at B=64) and a fresh pair per step: no L2 reuse between steps
@@ -239,6 +243,7 @@ def run_train(args, rank, world, local):
         "config": {"workload": "configs[1]: simple flow-matching UNet training, 256x256 tiles, batch 64/GPU, DDP",
                    "per_gpu_batch": B, "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()),
                    "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "Adam lr 1e-4 (fused, own kernel)",
+                   "ddp_bucket_mb": args.bucket_mb if world > 1 else None,
                    "l2": "inputs larger than L2 (2 x %.0f MB per step, 4 rotating sets)" % (B * 3 * 256 * 256 * 4 / 1e6)},
         "loss": last_loss,
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": 2 * B * 3 * 256 * 256 * 4,
@@ -275,27 +280,45 @@ def run_train(args, rank, world, local):
         out["model_flops_utilisation"] = (FLOP_TRAIN_PER_TILE * B / (step_ms / 1e3)) / 1e12 / pk["tf"]
         out["clocks"] = clocks
         out["cpu_baseline"] = cpu_baseline(sample_steps=1) if (world == 1 and not args.no_cpu) else None
+    # ---- the metric's second half in the same line: 50-evaluation Euler sampling (configs[2]), tiles sharded by rank
+    if not args.no_sample:
+        del x0s, x1s, host0, host1
+        opt.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        rec = sample_record(args, lit, rank, world, local, micro_batch=args.sample_batch)
+        if rank == 0:
+            out["sample"] = rec
     return out
 
 
-def run_sample(args, rank, world, local):
+def sample_record(args, lit, rank, world, local, micro_batch=64):
+    """configs[2]: 50-step Euler ODE sampling (`infer_simple_flowmatching`: lit.generate) of synthetic 256x256 tiles,
+    the tile index range cut across ranks with `parallel.shard_range` (no collective on the data path).
+
+    One "step" = one micro-batch of tiles taken through 50 velocity evaluations + state updates.  Two passes over this
+    rank's shard: first half with the tiles resident in HBM (`value`), second half through the public API with each
+    micro-batch copied from pinned host memory and the sampled tiles copied back to the host (`e2e`)."""
     from stain2stain_b200 import kernels as K
+    from stain2stain_b200.parallel import shard_range
     dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    B = args.batch
-    lit = build_lit(dev)
-    lit.eval()
-    g = torch.Generator(device=dev).manual_seed(1984 + rank)
-    n_sets = 3
-    xs = [torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
-    hosts = [x.cpu().pin_memory() for x in xs[:2]]
     evals = 50
+    n_tiles = args.sample_tiles if args.sample_tiles else 512 * world   # 4096 tiles on 8 GPUs = configs[2]
+    lo, hi = shard_range(n_tiles, rank, world)
+    mine = hi - lo
+    mb = min(micro_batch, mine)
+    n_mb = max(2, mine // mb)            # micro-batches of this rank (ragged tails are not part of the synthetic workload)
+    n_dev, n_e2e = (n_mb + 1) // 2, n_mb // 2
+    lit.eval()
+    g = torch.Generator(device=dev).manual_seed(1984 + 7919 * rank)
+    n_sets = 3  # rotating input sets; one evaluation streams > 1 GB of activations, far beyond L2
+    xs = [torch.rand(mb, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
+    hosts = [x.cpu().pin_memory() for x in xs[:2]]
+    out_host = torch.empty((mb, 3, 256, 256), dtype=torch.float32).pin_memory()
 
     def step(x):
         return lit.generate(x, num_steps=evals + 1)  # 51 grid points = 50 Euler evaluations, dt = 1/50
 
-    for i in range(max(args.warmup, 1)):
-        step(xs[i % n_sets])
+    step(xs[0])  # warm-up: packs the eval-mode operands, captures the CUDA graph
     _barrier(world)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -303,43 +326,57 @@ def run_sample(args, rank, world, local):
     K.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(n_dev):
         out_img = step(xs[i % n_sets])
     e1.record()
     _barrier(world)
     ms = _max_over_ranks(e0.elapsed_time(e1), world, dev)
     launches = K.LAUNCHES[0]
     clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(out_img).all())
     _barrier(world)
     e0.record()
-    for i in range(args.steps):
-        res = step(hosts[i % 2].to(dev, non_blocking=True)).cpu()
+    for i in range(n_e2e):
+        out_host.copy_(step(hosts[i % 2].to(dev, non_blocking=True)), non_blocking=True)
     e1.record()
     _barrier(world)
     ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
-    tiles = B * world * args.steps
     pk = _peaks()
-    step_ms = ms / args.steps
-    ach = FLOP_FWD_PER_TILE * evals * B / (step_ms / 1e3) / 1e12
+    step_ms = ms / n_dev
+    ach = FLOP_FWD_PER_TILE * evals * mb / (step_ms / 1e3) / 1e12
     return {
         "metric": "256x256 tiles/s, 50-evaluation Euler ODE sampling (CUDA-graph fused velocity eval + update)",
-        "value": tiles / (ms / 1e3), "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "value": mb * n_dev * world / (ms / 1e3), "unit": "tiles/s", "n_gpus": world, "steps": n_dev, "warmup": 1,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands, fp32 accumulate, fp32 ODE state" if K.ACT == K.FMT_F16 else "bf16 operands, fp32 state",
         "data": "synthetic U(-1,1) 3x256x256 tiles, random-init (de-zeroed) config-A UNet, seed 1984",
-        "config": {"workload": "configs[2]: 50-step Euler ODE sampling of synthetic 256x256 tiles, sharded by tile",
-                   "micro_batch": B, "evaluations": evals, "parallelism": f"replicas x{world} (no collective)",
-                   "l2": "activations of one evaluation (>1 GB) exceed L2"},
-        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
-                "d2h_bytes_per_step": B * 3 * 256 * 256 * 4},
+        "config": {"workload": "configs[2]: 50-step Euler ODE sampling (generate(num_steps=51)) of %d synthetic 256x256 "
+                               "tiles sharded across %d GPU(s) by parallel.shard_range; rank 0 holds tiles [%d, %d)"
+                               % (n_tiles, world, lo, hi),
+                   "tiles_total": n_tiles, "tiles_per_gpu": mine, "micro_batch": mb, "evaluations": evals,
+                   "micro_batches_timed_resident": n_dev, "micro_batches_timed_e2e": n_e2e,
+                   "parallelism": f"tile shards x{world} (no collective)",
+                   "l2": "activations of one evaluation (>1 GB) exceed L2; 3 rotating input sets"},
+        "e2e": {"value": mb * n_e2e * world / (ms_e2e / 1e3), "unit": "tiles/s", "steps": n_e2e,
+                "h2d_bytes_per_step": mb * 3 * 256 * 256 * 4, "d2h_bytes_per_step": mb * 3 * 256 * 256 * 4},
         "gpu_launches": launches,
         "gpu_launches_note": "own kernels inside the CUDA-graph replays (%d replays per step)" % evals,
         "roofline": {"bound": "tensor", "kernel": "whole velocity evaluation (conv_igemm dominated)", "achieved": ach,
                      "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
-                     "peak_source": pk["src"] + " bf16_tflops_sustained"},
+                     "peak_source": pk["src"] + " bf16_tflops_sustained",
+                     "algorithmic_flops_per_step": FLOP_FWD_PER_TILE * evals * mb},
+        "finite": finite,
         "clocks": clocks,
-        "cpu_baseline": None,
     }
+
+
+def run_sample(args, rank, world, local):
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lit = build_lit(dev)
+    rec = sample_record(args, lit, rank, world, local, micro_batch=args.batch)
+    rec["cpu_baseline"] = None
+    return rec
 
 
 def run_multitask(args, rank, world, local):
@@ -472,11 +509,12 @@ def _oracle_step_fn(batch=4):
         loss = oflow.model_step(net, fm, (x0, x1))
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
 def cpu_baseline(sample_steps=1, batch=4):
+    _use_all_host_threads()
     step = _oracle_step_fn(batch)
     t0 = time.perf_counter()
     for _ in range(sample_steps):
@@ -487,9 +525,17 @@ def cpu_baseline(sample_steps=1, batch=4):
                       f"fwd+bwd+Adam) on the host CPU, {os.cpu_count()} logical cores"}
 
 
+def _use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arm is allowed all the host's cores."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return None
+    _use_all_host_threads()
     batch = 4
     step = _oracle_step_fn(batch)
     for _ in range(min(args.warmup, 1)):
@@ -508,7 +554,10 @@ def run_reference(args, rank, world):
             "value": v, "unit": "tiles/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic U(-1,1) 3x256x256 tile pairs, seed 1984",
-            "config": {"workload": "configs[1] model on the reference's CPU path, bounded sample: batch 4 per step"},
+            "config": {"workload": "configs[1] model on the reference's CPU path (fp32 oracle port), bounded sample: batch 4 "
+                                   "per step on rank 0's host cores whatever --gpus is (the CPU path does not use the GPUs; "
+                                   "tiles/s of this arm does not depend on N)",
+                       "per_step_batch": batch, "threads": torch.get_num_threads()},
             "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -532,6 +581,12 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "sample", "multitask"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 64; 4096 tiles on 8 GPUs = 8 micro-batches per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sample", action="store_true", help="train mode: skip the 50-step sampling record")
+    ap.add_argument("--sample-tiles", type=int, default=0,
+                    help="tiles of the sampling record over ALL ranks (default 512 per GPU: 4096 on 8 GPUs = configs[2])")
+    ap.add_argument("--sample-batch", type=int, default=64, help="sampling micro-batch inside the train-mode run")
+    ap.add_argument("--bucket-mb", type=int, default=512,
+                    help="DDP gradient bucket size; 512 = ONE flat all-reduce of the 284 MB of fp32 gradients")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {"train": 64, "sample": 64, "multitask": 16}[args.mode]

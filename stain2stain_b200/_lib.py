@@ -103,9 +103,14 @@ def load(build_if_missing: bool = True):
     if build_if_missing and _build.needs_build():
         try:
             _build.build()
-        except Exception as e:  # stale-but-present is still usable; absent is fatal
+        except Exception as e:
+            # a library older than its sources must never run silently: the kernels would not be the ones in the tree.
+            # S2S_ALLOW_STALE_LIB=1 is the explicit override (e.g. a box without nvcc holding a deliberately prebuilt .so)
             if not os.path.exists(path):
                 raise S2SError(f"libs2s_b200.so is missing and could not be built: {e}") from e
+            if os.environ.get("S2S_ALLOW_STALE_LIB", "0") != "1":
+                raise S2SError(f"{path} is older than csrc/ and the rebuild failed ({e}); fix the build or set "
+                               f"S2S_ALLOW_STALE_LIB=1 to run the stale library knowingly") from e
     if not os.path.exists(path):
         raise S2SError(f"{path} not found: run `python -m stain2stain_b200._build` (there is no CPU fallback)")
     lib = C.CDLL(path)

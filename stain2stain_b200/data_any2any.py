@@ -38,66 +38,95 @@ def _crop_params(h: int, w: int, size: int) -> Tuple[int, int]:
     return i, j
 
 
+class _DomainTable:
+    """Which tile names exist in which stain domain: one directory scan per domain, then name sets combined by
+    `intersection` (tiles present in every domain) or `union` (present in at least one)."""
+
+    def __init__(self, root: str, folders: Dict[int, str], exts: Sequence[str]):
+        self.dirs: Dict[int, Path] = {label: Path(root) / sub for label, sub in folders.items()}
+        exts = tuple(e.lower() for e in exts)
+        self.names: Dict[int, frozenset] = {}
+        for label, d in self.dirs.items():
+            if not d.is_dir():
+                raise ValueError(f"Folder not found: {d}")
+            self.names[label] = frozenset(e.name for e in os.scandir(d) if e.name.lower().endswith(exts))
+
+    def combined(self, mode: str) -> List[str]:
+        if mode not in ("intersection", "union"):
+            raise ValueError("filename_mode must be 'intersection' or 'union'")
+        pools = list(self.names.values())
+        if not pools:
+            return []
+        acc = pools[0]
+        for pool in pools[1:]:
+            acc = (acc & pool) if mode == "intersection" else (acc | pool)
+        return sorted(acc)
+
+    def has(self, label: int, name: str) -> bool:
+        return name in self.names[label]
+
+
 class PairedAnyToAnyDataset:
+    """Mirror of the reference's any-to-any dataset (`src/data/class_conditional_he_amyloid.py:12-145`): same keywords,
+    same item semantics, same consumption of the Python / torch RNG streams (so a seeded run picks the same domains and
+    crops), with decode on the host and crop + to_tensor + normalise on the device."""
+
+    _MAX_UNION_RETRIES = 50  # the reference gives up after 50 resamples in `union` mode (:121-131)
+
     def __init__(self, root_dir, class_folder_mapping, crop_size=256, transform=None, same_crop_for_pair=True,
                  source_domain_mode="random", filename_mode="intersection",
                  allowed_exts=(".png", ".jpg", ".jpeg", ".tif", ".tiff"), valid_filenames: Optional[List[str]] = None):
         if transform is not None:
             raise NotImplementedError("custom post-crop transforms run on the host; the B200 pipeline fuses the default one")
-        self.root_dir = root_dir
+        self.root_dir, self.crop_size, self.same_crop_for_pair = root_dir, crop_size, same_crop_for_pair
+        self.source_domain_mode, self.filename_mode = source_domain_mode, filename_mode
         self.class_folder_mapping = dict(class_folder_mapping)
-        self.crop_size = crop_size
-        self.same_crop_for_pair = same_crop_for_pair
-        self.source_domain_mode = source_domain_mode
-        self.filename_mode = filename_mode
         self.allowed_exts = tuple(allowed_exts)
-        self.num_classes = len(self.class_folder_mapping)
-        self.class_indices = sorted(self.class_folder_mapping.keys())
-        self.class_to_dir = {c: os.path.join(root_dir, folder) for c, folder in self.class_folder_mapping.items()}
-        self.class_to_filenames = {}
-        for c, d in self.class_to_dir.items():
-            if not os.path.isdir(d):
-                raise ValueError(f"Folder not found: {d}")
-            self.class_to_filenames[c] = set(f for f in os.listdir(d) if f.lower().endswith(self.allowed_exts))
-        sets = list(self.class_to_filenames.values())
-        if filename_mode == "intersection":
-            all_filenames = sorted(set.intersection(*sets) if sets else set())
-        elif filename_mode == "union":
-            all_filenames = sorted(set.union(*sets) if sets else set())
-        else:
-            raise ValueError("filename_mode must be 'intersection' or 'union'")
-        self.filenames = sorted(f for f in all_filenames if f in valid_filenames) if valid_filenames is not None \
-            else all_filenames
-        if len(self.filenames) == 0:
+        self.class_indices = sorted(self.class_folder_mapping)
+        self.num_classes = len(self.class_indices)
+        self._table = _DomainTable(root_dir, self.class_folder_mapping, self.allowed_exts)
+        names = self._table.combined(filename_mode)
+        if valid_filenames is not None:  # train / val split: keep the listed names only (order stays sorted)
+            keep = set(valid_filenames)
+            names = [n for n in names if n in keep]
+        if not names:
             raise ValueError("No filenames found (check folders / extensions).")
+        self.filenames = names
+        # reference-named views of the same table (read by code written against the reference class)
+        self.class_to_dir = {c: str(d) for c, d in self._table.dirs.items()}
+        self.class_to_filenames = {c: set(v) for c, v in self._table.names.items()}
 
     def __len__(self):
         return len(self.filenames)
 
     def _load_rgb(self, class_idx, filename) -> np.ndarray:
         from PIL import Image
-        return np.asarray(Image.open(os.path.join(self.class_to_dir[class_idx], filename)).convert("RGB"))
+        return np.asarray(Image.open(self._table.dirs[class_idx] / filename).convert("RGB"))
+
+    def _pick_source(self) -> int:
+        mode = self.source_domain_mode
+        if mode == "random":
+            return random.choice(self.class_indices)
+        if isinstance(mode, int):
+            return mode
+        raise ValueError("source_domain_mode must be 'random' or an int class index")
 
     def draw(self, idx) -> Tuple[str, int, int]:
-        """The domain choice of `__getitem__` (reference :109-131), same RNG calls in the same order."""
-        fname = self.filenames[idx]
-        if self.source_domain_mode == "random":
-            source_label = random.choice(self.class_indices)
-        elif isinstance(self.source_domain_mode, int):
-            source_label = self.source_domain_mode
-        else:
-            raise ValueError("source_domain_mode must be 'random' or an int class index")
-        target_label = random.choice(self.class_indices)
-        if self.filename_mode == "union":
-            tries = 0
-            while (fname not in self.class_to_filenames[source_label]) or (fname not in self.class_to_filenames[target_label]):
-                source_label = random.choice(self.class_indices) if self.source_domain_mode == "random" else source_label
-                target_label = random.choice(self.class_indices)
-                tries += 1
-                if tries > 50:
-                    raise RuntimeError(f"Could not find paired file '{fname}' across sampled domains. "
-                                       "Consider using intersection mode.")
-        return fname, source_label, target_label
+        """(file name, source domain, target domain) of item `idx`.  RNG protocol of the reference's `__getitem__`
+        (:109-131): one `random.choice` for the source (random mode only), one for the target; in `union` mode the pair is
+        redrawn -- source first, then target -- until both domains hold the file, at most 50 times."""
+        name = self.filenames[idx]
+        src = self._pick_source()
+        tgt = random.choice(self.class_indices)
+        if self.filename_mode != "union":
+            return name, src, tgt
+        for _ in range(self._MAX_UNION_RETRIES + 1):
+            if self._table.has(src, name) and self._table.has(tgt, name):
+                return name, src, tgt
+            src = self._pick_source()
+            tgt = random.choice(self.class_indices)
+        raise RuntimeError(f"Could not find paired file '{name}' across sampled domains. "
+                           "Consider using intersection mode.")
 
     def __getitem__(self, idx):
         """-> (src uint8 HWC RGB, tgt uint8 HWC RGB, crop params int32 [2, 4] (src, tgt), target_label)."""

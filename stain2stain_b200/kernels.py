@@ -166,7 +166,8 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
              bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out_f32: bool = False,
              axpy_x: Optional[torch.Tensor] = None, axpy_a: float = 0.0, out: Optional[torch.Tensor] = None,
              a_fmt: int = ACT, w_fmt: int = ACT, out_fmt: int = ACT, res_fmt: int = ACT, want_stats: bool = False,
-             norms: Optional[Sequence[Optional[Tuple[torch.Tensor, int]]]] = None, norm_act: int = 1):
+             norms: Optional[Sequence[Optional[Tuple[torch.Tensor, int]]]] = None, norm_act: int = 1,
+             alg_macs: Optional[float] = None):
     """srcs: [(x NHWC 16-bit, taps, stride)].  Returns 16-bit NHWC [B,hout,wout,cout], or fp32 NCHW when out_f32.
     norms (inference): per segment `(coef fp32 [B, Ctot, 2], channel offset)` or None -- the segment is then the RAW
     tensor and act(x * A + Bc) is applied to its tiles inside the kernel (no norm-apply pass); norm_act: 0 none, 1 SiLU.
@@ -194,8 +195,11 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout and bias.is_contiguous()
     assert w_packed.dtype == T16 and w_packed.is_contiguous() and w_packed.shape[0] >= padded_rows(cout)
-    # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted)
-    macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs)
+    # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted).  `alg_macs`: the caller's
+    # figure when the launch executes more than the algorithm needs (dgrad of a stride-2 conv through zero insertion
+    # runs at 4x its algorithmic MACs) -- rooflines are reported against the algorithm, never against executed work
+    macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs) if alg_macs is None \
+        else float(alg_macs)
     stats = None
     if want_stats and not out_f32 and axpy_x is None and EPI_STATS:
         nt = int(_L().s2s_conv_stat_tiles_for(arr, len(srcs), hout, wout, cout))
@@ -222,7 +226,7 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: torch.Tensor, n_off: int = 0,
-               fmt: int = GRAD):
+               fmt: int = GRAD, alg_macs: Optional[float] = None):
     """dw[tap][m][n_off+n] += sum dy[..., m] * x[shifted, n].  dw: fp32 [taps, Cm, ldn].
     Both operands must be stored in `fmt` (one MMA, one operand format: mixed fp16 x bf16 is an illegal instruction)."""
     dy_fmt = x_fmt = fmt
@@ -231,7 +235,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, taps: int, stride: int, dw: to
     B, ho, wo, cm = dy.shape
     assert x.shape[1] == ho * stride and x.shape[2] == wo * stride
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == taps and dw.shape[1] == cm
-    with _Prof("conv_wgrad", 2.0 * B * ho * wo * cm * x.shape[3] * taps):
+    macs = float(B) * ho * wo * cm * x.shape[3] * taps if alg_macs is None else float(alg_macs)
+    with _Prof("conv_wgrad", 2.0 * macs):
         check(_L().s2s_conv_wgrad(ptr(dy), cm, ptr(x), x.shape[3], taps, stride, B, ho, wo, ptr(dw), dw.shape[2],
                                   n_off, dy_fmt, x_fmt, stream_ptr()), "conv_wgrad")
 

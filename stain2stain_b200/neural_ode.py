@@ -10,6 +10,7 @@ Every other (solver, vector field) combination runs the generic stepping code be
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
@@ -93,7 +94,14 @@ class _EulerGraph:
         return self.x
 
 
-_GRAPHS: Dict[tuple, _EulerGraph] = {}
+# captured Euler steps per net: a WeakKeyDictionary, so a freed model releases its graphs (and their memory pools) and a
+# new model that happens to reuse the old one's id() can never replay another model's capture
+_GRAPHS: "weakref.WeakKeyDictionary[nn.Module, Dict[tuple, _EulerGraph]]" = weakref.WeakKeyDictionary()
+
+
+def clear_graphs():
+    """Drop every captured sampler step (call after writing parameters through `.data`, which bumps no version)."""
+    _GRAPHS.clear()
 
 
 def _param_signature(net: nn.Module):
@@ -109,12 +117,13 @@ def fused_euler(net: RawUNetModel, x: torch.Tensor, t_span: torch.Tensor, y: Opt
     dt = float(t_span[-1] - t_span[0]) / steps
     x = x.float().contiguous()
     if use_graph:
-        key = (id(net), tuple(x.shape), x.device.index, dt, y is not None, extra is not None, _param_signature(net))
-        g = _GRAPHS.get(key)
+        key = (tuple(x.shape), x.device.index, dt, y is not None, extra is not None, _param_signature(net))
+        per_net = _GRAPHS.setdefault(net, {})
+        g = per_net.get(key)
         if g is None:
-            for k in [k for k in _GRAPHS if k[0] == id(net) and k[1] == tuple(x.shape)]:
-                del _GRAPHS[k]  # stale parameters / other dt: drop the old capture
-            g = _GRAPHS[key] = _EulerGraph(net, x, y, dt, extra)
+            for k in [k for k in per_net if k[0] == tuple(x.shape)]:
+                del per_net[k]  # stale parameters / other dt: drop the old capture
+            g = per_net[key] = _EulerGraph(net, x, y, dt, extra)
         return g.run(x, t0, steps, y, record, extra).clone()
     xs = x.clone()
     ex = None if extra is None else extra.float().contiguous()

@@ -38,6 +38,11 @@ class _PackCache:
     def get(self, key: tuple, ws: Sequence[torch.Tensor], make):
         sig = self._sig(ws)
         hit = self._store.get(key)
+        if hit is not None and not all(r() is w for r, w in zip(hit[2], ws)):
+            # same key, other tensor objects: a freed model's id / allocator address / version count can all recur, so a
+            # hit is only ever accepted for the very parameters it was packed from
+            del self._store[key]
+            hit = None
         if hit is not None and hit[0] == sig:
             return hit[1]
         if hit is not None and self._reusable(hit, sig, ws[0].device):
@@ -204,7 +209,7 @@ class _FusedConv(torch.autograd.Function):
                 wd = plan.packed_dgrad(si, weights)
                 g = d_out if s.stride == 1 else K.zero_insert2x(d_out)
                 dx = K.conv_fwd([(g, s.taps, 1)], wd, s.ci_count, g.shape[1], g.shape[2], a_fmt=K.GRAD, w_fmt=K.GRAD,
-                                out_fmt=K.GRAD)
+                                out_fmt=K.GRAD, alg_macs=float(B) * hout * wout * cout * s.ci_count * s.taps)
                 d_srcs[s.src] = dx if d_srcs[s.src] is None else d_srcs[s.src] + dx
         d_biases = [d_bias if (present and n) else None
                     for present, n in zip(ctx.bias_present, need[4 + n_src + n_w:])]
@@ -328,7 +333,8 @@ class _Stem(torch.autograd.Function):
             return wp, [(0, 0, 0, w.shape[1], False, K.ACT)]
         wp = PACK_CACHE.get(("stem", id(w)), [w], make)
         B, _, H, W = x0.shape
-        out, st = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach(), want_stats=True)
+        out, st = K.conv_fwd([(patches, 1, 1)], wp, cout, H, W, bias=b.detach(), want_stats=True,
+                             alg_macs=float(B) * H * W * cout * 9 * cin)  # the operand is padded 9*cin -> 64 columns
         if stats_box is not None:
             stats_box.append(st)
         ctx.save_for_backward(patches)
@@ -341,7 +347,8 @@ class _Stem(torch.autograd.Function):
         g = g.contiguous()
         cout, cin = g.shape[3], ctx.wshape[1]
         dw = torch.zeros((1, cout, 64), dtype=torch.float32, device=g.device)
-        K.conv_wgrad(g, K.convert16(patches, K.ACT, K.GRAD), 1, 1, dw)
+        K.conv_wgrad(g, K.convert16(patches, K.ACT, K.GRAD), 1, 1, dw,
+                     alg_macs=float(g.shape[0]) * g.shape[1] * g.shape[2] * cout * 9 * cin)
         d_w = dw[0, :, :9 * cin].reshape(cout, 9, cin).permute(0, 2, 1).reshape(ctx.wshape).contiguous()
         d_b = torch.zeros(cout, dtype=torch.float32, device=g.device)
         K.channel_sum(g, d_b)
@@ -382,10 +389,11 @@ class _HeadConv(torch.autograd.Function):
         wd = torch.zeros((cin, 64), dtype=torch.bfloat16, device=w.device)
         wd[:, :27] = w.detach().permute(1, 2, 3, 0).reshape(cin, 27).to(torch.bfloat16)
         B, H, W, _ = a.shape
-        da = K.conv_fwd([(dcol, 1, 1)], wd, cin, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD)
+        da = K.conv_fwd([(dcol, 1, 1)], wd, cin, H, W, a_fmt=K.GRAD, w_fmt=K.GRAD, out_fmt=K.GRAD,
+                        alg_macs=float(B) * H * W * cin * 27)
         # wgrad: D[ci][tap*3+co] = sum_q a[q][ci] * dcol[q][tap*3+co]
         dw = torch.zeros((1, cin, 64), dtype=torch.float32, device=w.device)
-        K.conv_wgrad(K.convert16(a, K.ACT, K.GRAD), dcol, 1, 1, dw)
+        K.conv_wgrad(K.convert16(a, K.ACT, K.GRAD), dcol, 1, 1, dw, alg_macs=float(B) * H * W * cin * 27)
         d_w = dw[0, :, :27].reshape(cin, 9, 3).permute(2, 0, 1).reshape(cout, cin, 3, 3).contiguous()
         d_b = dv.sum(dim=(0, 2, 3))
         return da, d_w, d_b, None, None
@@ -659,6 +667,11 @@ class ResBlockCfg:
     plan1_multi: Optional[ConvPlan] = None  # inference: conv 1 over the RAW sources, one 3x3 segment per source
 
 
+# test hook: when a list, every training-mode ResBlock appends its dropout keep bits (uint8 [B,H,W,C/8], bit j of byte
+# c8 = channel 8*c8 + j) in execution order, so a parity test can replay the SAME masks into the fp32 oracle
+DROPOUT_TAP: Optional[list] = None
+
+
 def _wgrad_to(d_out, x_g, taps: int, stride: int, d_w_view, n_begin: int):
     """d_w_view[m][n_begin + n][tap] = sum_pixels d_out[., m] * x_g[. + tap, n]   (x_g: bf16 NHWC, all its channels)."""
     cout, cq = d_out.shape[3], x_g.shape[3]
@@ -702,8 +715,8 @@ class _ResBlockFn(torch.autograd.Function):
             coef1, mr1 = K.gn_coef(stats, gn1w.detach(), gn1b.detach(), None, H * W, cfg.groups, cfg.eps)
         # inference: the norm-apply passes disappear -- the convs read the RAW tensors and apply silu(x * A + Bc) to
         # their shared-memory tiles (s2s_conv_fwd_norm); the concat is then one GEMM segment per source
-        fuse = (not train) and cfg.plan1_multi is not None and \
-            K.conv_norm_fusable([(s, 9, 1) for s in srcs], cout)
+        fuse = (not train) and drop_p == 0 and cfg.plan1_multi is not None and \
+            K.conv_norm_fusable([(s, 9, 1) for s in srcs], cout)  # (the fused prologue has no dropout)
         if fuse:
             offs, off = [], 0
             for s in srcs:
@@ -739,6 +752,8 @@ class _ResBlockFn(torch.autograd.Function):
             a2g = torch.empty_like(a2) if dual else None
             mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if (train and drop_p > 0) else None
             K.gn_apply(h, coef2, a2, 0, True, drop_p, seed, y2=a2g, mask=mask)
+            if DROPOUT_TAP is not None and mask is not None:
+                DROPOUT_TAP.append(mask)
             norms2 = None
         # ---- conv 2 with the skip path in the same accumulator
         if cfg.has_skip_conv:

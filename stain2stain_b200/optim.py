@@ -34,7 +34,10 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables = {}  # group index -> (signature, device tensor table, device work list, n_work, keep-alive)
 
     def _table(self, gi: int, ps: List[torch.Tensor]):
-        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        # every pointer the device table holds is part of the signature: `load_state_dict` / a state reset swaps the moment
+        # tensors while parameters and gradients stay where they are
+        sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == sig:
             return hit
@@ -54,6 +57,18 @@ class FusedAdam(torch.optim.Optimizer):
         hit = (sig, t_dev, w_dev, len(work), (raw, w_host))
         self._tables[gi] = hit
         return hit
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()
+        for st in self.state.values():  # torch casts `step` to the parameter's device; the host-side count stays on the CPU
+            if torch.is_tensor(st.get("step")) and st["step"].is_cuda:
+                st["step"] = st["step"].detach().cpu()
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._tables.clear()
 
     @torch.no_grad()
     def step(self, closure=None):

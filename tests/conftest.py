@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # every "fp32 reference" in this suite (F.conv2d, matmul, the oracle on the GPU) must be TRUE fp32: on B200 the
+    # library defaults would silently run TF32 (10-bit significand) and the parity gates would compare two rounded paths
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.set_float32_matmul_precision("highest")
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -356,6 +356,41 @@ def test_fused_adam_matches_torch_adam(wd):
         assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-8)
 
 
+def test_fused_adam_resume_uses_the_loaded_moments():
+    """step -> load_state_dict (in-process resume swaps the moment tensors) -> step: the device pointer table must be
+    rebuilt, the loaded moments used and the new ones written back (optim.py:37)."""
+    from stain2stain_b200.optim import FusedAdam
+    g = torch.Generator(device=DEV).manual_seed(4)
+    shapes = [(64, 32, 3, 3), (513,), (20000,)]
+    pa = [torch.randn(s, device=DEV, generator=g).requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    oa, ob = FusedAdam(pa, lr=1e-3, weight_decay=1e-5), torch.optim.Adam(pb, lr=1e-3, weight_decay=1e-5)
+
+    def both_step():
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device=DEV, generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step(), ob.step()
+    both_step()
+    both_step()
+    import copy
+    ckpt_a, ckpt_b = copy.deepcopy(oa.state_dict()), copy.deepcopy(ob.state_dict())
+    w_a = [p.detach().clone() for p in pa]
+    both_step()  # moves on past the checkpoint ...
+    with torch.no_grad():  # ... then resume from it in-process: same parameter / gradient storage, NEW moment tensors
+        for a, b, w in zip(pa, pb, w_a):
+            a.copy_(w), b.copy_(w)
+    oa.load_state_dict(ckpt_a), ob.load_state_dict(ckpt_b)
+    old_m = [oa.state[p]["exp_avg"] for p in pa]
+    both_step()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
+    for p, q, m in zip(pa, pb, old_m):
+        assert oa.state[p]["exp_avg"] is m and float(oa.state[p]["step"]) == 3.0
+        assert torch.allclose(oa.state[p]["exp_avg"], ob.state[q]["exp_avg"], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(oa.state[p]["exp_avg_sq"], ob.state[q]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
 def test_stored_dropout_mask_equals_rehash():
     """The keep bits written by gn_apply (1 bit / element) are exactly the Philox mask, and the backward kernels give
     bit-identical results whether they read the stored bits or re-evaluate the hash."""

@@ -200,3 +200,44 @@ def test_pack_cache_refreshes_every_stale_operand_in_one_launch(monkeypatch):
         w3.add_(1)
     pc.get(("a",), [w3], make)
     assert ("b",) not in pc._store                                        # entries of dead parameters are dropped
+
+
+def test_pack_cache_never_serves_another_tensors_operand(monkeypatch):
+    """ADVICE round 1 (ops.py:329): stem / head operands are keyed by a Python id.  A model built after another was freed
+    can reuse the same id, the same caching-allocator address and the same construction version count; the hit must
+    still be refused because the weak references of the entry do not point at THIS tensor."""
+    import torch
+
+    from stain2stain_b200 import kernels as K
+    from stain2stain_b200 import ops
+    calls = []
+    monkeypatch.setattr(K, "pack_conv_weight", lambda w, dst, **kw: calls.append(id(w)))
+    pc = ops._PackCache()
+
+    def make(dst):
+        return (dst if dst is not None else torch.zeros(8, 64, dtype=K.T16)), [(0, 0, 0, 4, False, K.ACT)]
+    w1 = torch.nn.Parameter(torch.zeros(8, 4, 3, 3))
+    a = pc.get(("stem", 1234), [w1], make)
+    # an impostor with the SAME storage address, version and shape under the same key (what id()/address reuse produces)
+    w2 = torch.nn.Parameter(w1.detach())
+    assert w2.data_ptr() == w1.data_ptr() and w2._version == w1._version and w2 is not w1
+    b = pc.get(("stem", 1234), [w2], make)
+    assert b is not a and len(calls) == 2, "the cache served an operand packed from a different tensor object"
+    assert pc.get(("stem", 1234), [w2], make) is b and len(calls) == 2
+
+
+def test_euler_graph_registry_is_weak():
+    import gc
+
+    import torch
+
+    from stain2stain_b200 import neural_ode as node
+    net = torch.nn.Linear(2, 2)
+    node._GRAPHS.setdefault(net, {})["k"] = object()
+    assert len(node._GRAPHS) >= 1
+    n0 = len(node._GRAPHS)
+    del net
+    gc.collect()
+    assert len(node._GRAPHS) == n0 - 1
+    node.clear_graphs()
+    assert len(node._GRAPHS) == 0
