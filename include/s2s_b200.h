@@ -104,10 +104,37 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
 typedef struct {
     const float* w;
     void* dst16;
-    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, pad;
+    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, mode; /* mode: see s2s_pack_conv_weight_mode */
 } s2s_pack_job;
 int s2s_pack_chunk(void);
 int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev, int n_work, void* stream);
+
+/* s2s_pack_conv_weight with a tap-combination mode.  mode 0: plain.  mode 1 + phase (phase = py*2 + px; 3x3 weights):
+ * operand of the phase-decomposed Upsample conv -- 4 logical taps ti = ai*2 + bi, each the fp32 SUM of the 3x3 taps
+ * (rows R(py, ai) x columns R(px, bi), R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2}) that read the same
+ * low-resolution pixel:  forward  dst[co][k_off + ti*ci_count + ci] ; transpose_flip = 1  dst[ci][k_off + ti*Cout + co]. */
+int s2s_pack_conv_weight_mode(const float* w_oihw, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst16,
+                              int ld_k, int k_off, int transpose_flip, int fmt, int mode, void* stream);
+
+/* Upsample(nearest x2) -> conv3x3(pad 1) WITHOUT the upsampled tensor (torchcfm unet.py Upsample.forward:
+ * F.interpolate(x, scale_factor=2, mode="nearest"); self.conv(x) -- SURVEY.md A.2, row a12).  Four phase launches of the
+ * halo-tiled CTA-pair conv over the LOW-resolution input x [B,H,W,C], each a 2x2 conv with tap-summed weights writing the
+ * pixels (2y+py, 2x+px) of out [B,2H,2W,Cout] through a strided TMA store map: 4/9 of the reference's MACs.
+ *   w_packed (fwd)   16-bit [Cout][16*C]: phase p at columns [p*4*C, (p+1)*4*C)   (s2s_pack_conv_weight_mode, mode 1+p)
+ *   w_packed (dgrad) 16-bit [Cin][16*Cm]: same column layout, transpose_flip = 1
+ *   dw16             fp32 [16 = phase*4 + ti][Cm][Cq], zero-initialised by the caller; s2s_upconv_unpack_wgrad folds it
+ *                    into the OIHW gradient [Cm][Cq][3][3] (every 3x3 tap belongs to exactly one logical tap per phase)
+ *   stats_out        optional fp32 [B][s2s_upconv_stat_tiles(H,W,Cout)][Cout][2], as in s2s_conv_fwd
+ * s2s_upconv_supported: 1 when both channel counts are multiples of 128 (else use s2s_upsample2x + s2s_conv_fwd). */
+int s2s_upconv_supported(int C, int Cout);
+int s2s_upconv_stat_tiles(int H, int W, int Cout);
+int s2s_upconv_fwd(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, const float* bias, void* out,
+                   float* stats_out, int a_fmt, int w_fmt, int out_fmt, void* stream);
+int s2s_upconv_dgrad(const void* dy, int B, int H, int W, int Cm, const void* w_packed, int Cin, void* dx, int a_fmt,
+                     int w_fmt, int out_fmt, void* stream);
+int s2s_upconv_wgrad(const void* dy, int Cm, const void* x, int Cq, int B, int H, int W, float* dw16, int dy_fmt, int x_fmt,
+                     void* stream);
+int s2s_upconv_unpack_wgrad(const float* dw16, int M, int N, float* grad_oihw, void* stream);
 
 /* dw fp32 [taps][M][ldn] -> grad_oihw[m][n_begin + n][tap] = beta * grad + dw[tap][m][n_off + n] */
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad_oihw,

@@ -26,7 +26,7 @@ class ConvSrc(C.Structure):
 class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("taps", C.c_int),
                 ("ci_begin", C.c_int), ("ci_count", C.c_int), ("ld_k", C.c_int), ("k_off", C.c_int),
-                ("transpose_flip", C.c_int), ("fmt", C.c_int), ("pad", C.c_int)]
+                ("transpose_flip", C.c_int), ("fmt", C.c_int), ("mode", C.c_int)]
 
 
 class ConvNorm(C.Structure):
@@ -41,6 +41,13 @@ SIGNATURES = {
     "s2s_abi_version": [],
     "s2s_num_sms": [],
     "s2s_pack_conv_weight": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
+    "s2s_pack_conv_weight_mode": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "s2s_upconv_supported": [_i, _i],
+    "s2s_upconv_stat_tiles": [_i, _i, _i],
+    "s2s_upconv_fwd": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "s2s_upconv_dgrad": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp],
+    "s2s_upconv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "s2s_upconv_unpack_wgrad": [_vp, _i, _i, _vp, _vp],
     "s2s_pack_chunk": [],
     "s2s_pack_conv_weight_multi": [_vp, _vp, _i, _vp],
     "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],

@@ -133,15 +133,6 @@ int make_act_tmap(CUtensorMap* m, const void* x, int B, int H, int W, int C, int
     return make_tmap(m, x, 5, dims, str, box);
 }
 
-// stride-1 activation view {C, W, 1, H, B} with a custom pixel box (halo-tiled conv)
-int make_act_tmap_box(CUtensorMap* m, const void* x, int B, int H, int W, int C, int box_w, int box_h) {
-    if (C % 8) return fail(S2S_ERR_INVALID, "activation channels (%d) must be a multiple of 8", C);
-    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 1, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
-    return make_tmap(m, x, 5, dims, str, box);
-}
-
 uint32_t pow2_cols(int n) {
     uint32_t c = 32;
     while ((int)c < n) c <<= 1;
@@ -237,11 +228,20 @@ int s2s_num_sms(void) { return num_sms(); }
 
 int s2s_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst, int ld_k,
                          int k_off, int transpose_flip, int fmt, void* stream) {
+    return s2s_pack_conv_weight_mode(w, Cout, Cin, taps, ci_begin, ci_count, dst, ld_k, k_off, transpose_flip, fmt, 0, stream);
+}
+
+int s2s_pack_conv_weight_mode(const float* w, int Cout, int Cin, int taps, int ci_begin, int ci_count, void* dst, int ld_k,
+                              int k_off, int transpose_flip, int fmt, int mode, void* stream) {
     if (!w || !dst || Cout <= 0 || ci_count <= 0 || ci_begin < 0 || ci_begin + ci_count > Cin || (taps != 1 && taps != 9))
         return fail(S2S_ERR_INVALID, "pack_conv_weight: bad arguments");
-    const long long total = (long long)Cout * ci_count * taps;
-    pack_conv_weight_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(
-        w, Cout, Cin, taps, ci_begin, ci_count, (uint16_t*)dst, ld_k, k_off, transpose_flip, fmt);
+    if (mode < 0 || mode > 4 || (mode != 0 && taps != 9))
+        return fail(S2S_ERR_INVALID, "pack_conv_weight: mode %d (phase-summed taps) needs a 3x3 weight", mode);
+    PackJob jb;
+    jb.w = w; jb.dst = (uint16_t*)dst; jb.Cout = Cout; jb.Cin = Cin; jb.taps = taps; jb.ci_begin = ci_begin;
+    jb.ci_count = ci_count; jb.ld_k = ld_k; jb.k_off = k_off; jb.transpose_flip = transpose_flip; jb.fmt = fmt; jb.mode = mode;
+    const long long total = (long long)Cout * ci_count * (mode == 0 ? taps : 4);
+    pack_conv_weight_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(jb);
     LAUNCH_CHECK("pack_conv_weight_kernel");
     return S2S_OK;
 }
@@ -288,6 +288,141 @@ int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wo
     return s2s_conv_stat_tiles(Hout, Wout, Cout);
 }
 
+
+// A 16-bit NHWC tensor seen through arbitrary pixel strides: [B][H][W][C] with strides (sb, sy, sx) in ELEMENTS.  The
+// phase views of an Upsample conv's output (pixels (2y+py, 2x+px)) are such views; so is any dense tensor.
+struct ActView {
+    const void* base;
+    int B, H, W, C;
+    long long sx, sy, sb;
+};
+static ActView dense_view(const void* x, int B, int H, int W, int C) {
+    ActView v;
+    v.base = x; v.B = B; v.H = H; v.W = W; v.C = C;
+    v.sx = C; v.sy = (long long)W * C; v.sb = (long long)H * W * C;
+    return v;
+}
+// pixels (2y + py, 2x + px) of a dense [B, 2H, 2W, C] tensor as a [B, H, W, C] view
+static ActView phase_view(const void* x, int B, int H, int W, int C, int py, int px) {
+    ActView v;
+    v.base = (const uint8_t*)x + ((size_t)py * 2 * W + px) * C * 2;
+    v.B = B; v.H = H; v.W = W; v.C = C;
+    v.sx = 2LL * C; v.sy = 4LL * W * C; v.sb = 4LL * H * W * C;
+    return v;
+}
+static int make_view_tmap(CUtensorMap* m, const ActView& v, int box_w, int box_h) {
+    if (v.C % 8) return fail(S2S_ERR_INVALID, "activation channels (%d) must be a multiple of 8", v.C);
+    cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)v.W, 1, (cuuint64_t)v.H, (cuuint64_t)v.B};
+    cuuint64_t str[4] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sb * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
+    return make_tmap(m, v.base, 5, dims, str, box);
+}
+
+struct HaloSeg {
+    ActView view;
+    int kind;                   // 9: 3x3 neighbourhood (halo box), 1: 1x1
+    int ntaps;                  // logical taps multiplied (kind 9: 1..9, kind 1: 1)
+    unsigned long long tapmap;  // 3x3 position of each logical tap
+};
+
+// One launch of the halo-tiled CTA-pair kernel over explicit views.  Output view dims = the GEMM's pixel space.
+static int halo_launch(const HaloSeg* segs, int nseg, const ActView& outv, const void* w_packed, int Ktot, int kb_first,
+                       int Cout, const float* bias, const void* residual, float* stats_out, int stat_tiles_total,
+                       int stat_off, int a_fmt, int w_fmt, int out_fmt, int res_fmt, void* stream,
+                       const s2s_conv_norm* norms, int act) {
+    const int B = outv.B, Hout = outv.H, Wout = outv.W;
+    Conv3Params q;
+    memset(&q, 0, sizeof(q));
+    const bool cols3 = conv_halo() == 3;
+    int BN3, mt3, tx3, ty3;
+    halo_geometry(Hout, Wout, Cout, &BN3, &mt3, &tx3, &ty3);
+    q.cols3 = cols3 ? 1 : 0;
+    q.nseg = nseg;
+    int kb3 = kb_first;
+    for (int s = 0; s < nseg; ++s) {
+        const HaloSeg& sc = segs[s];
+        if (sc.view.B != B || sc.view.H != Hout || sc.view.W != Wout)
+            return fail(S2S_ERR_INVALID, "conv(halo): segment %d view does not match the output pixel space", s);
+        int rc = sc.kind == 9 ? make_view_tmap(&q.tmA[s], sc.view, cols3 ? kHaloTW : kHaloPitch, kHaloTH * mt3 + 2)
+                              : make_view_tmap(&q.tmA[s], sc.view, kHaloTW, kHaloTH);
+        if (rc) return rc;
+        q.seg[s].taps = sc.kind;
+        q.seg[s].ntaps = sc.ntaps;
+        q.seg[s].tapmap = sc.tapmap;
+        q.seg[s].cblocks = (sc.view.C + kBlockK - 1) / kBlockK;
+        q.seg[s].stride = 1;
+        q.seg[s].C = sc.view.C;
+        q.seg_kb[s] = kb3;
+        kb3 += sc.ntaps * q.seg[s].cblocks;
+    }
+    if (kb3 * kBlockK > Ktot)
+        return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d is smaller than the segments need (%d)", Ktot, kb3 * kBlockK);
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+        cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
+        cuuint32_t box[2] = {kBlockK, (cuuint32_t)(BN3 / 2)};
+        int rc = make_tmap(&q.tmW, w_packed, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    int rc = make_view_tmap(&q.tmOut, outv, kHaloTW, kHaloTH);
+    if (rc) return rc;
+    q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
+    q.tiles_x = tx3;
+    q.tiles_y = ty3;
+    q.stats = (float2*)stats_out;
+    q.stat_tiles = stat_tiles_total > 0 ? stat_tiles_total : tx3 * ty3 * mt3;
+    q.stat_off = stat_off;
+    if (norms) {
+        q.prologue = 1;
+        q.act = act;
+        for (int s = 0; s < nseg; ++s) {
+            q.seg_coef[s] = (const float2*)norms[s].coef;
+            q.seg_x[s] = (const uint16_t*)segs[s].view.base;
+            q.seg_coef_ld[s] = norms[s].ld;
+            q.seg_coef_off[s] = norms[s].off;
+        }
+    }
+    q.m_tiles = B * q.tiles_x * q.tiles_y;
+    q.n_tiles_n = Cout / BN3;
+    q.total_pairs = ((q.m_tiles + 1) / 2) * q.n_tiles_n;
+    q.BN = BN3;
+    q.tmem_cols = pow2_cols(2 * mt3 * BN3);
+    q.base_off_mode = conv_halo() == 1 ? 1 : 0;
+    q.bias = bias;
+    q.residual = (const __nv_bfloat16*)residual;
+    q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
+    const size_t halo_bytes = cols3 ? (size_t)3 * (kHaloTH * mt3 + 2) * kHaloTW * 128
+                                    : (size_t)(kHaloTH * mt3 + 2) * kHaloPitch * 128;
+    size_t a_slot = halo_bytes > (size_t)mt3 * kABytes ? halo_bytes : (size_t)mt3 * kABytes;
+    a_slot = (a_slot + 1023) / 1024 * 1024;
+    q.a_slot = (uint32_t)a_slot;
+    const size_t b_bytes = (size_t)(BN3 / 2) * kBlockK * 2;
+    const size_t fixed = 2 * kOutStageBytes + 1024 + 3072;  // + alignment slack + barriers / statistics scratch
+    q.sa = cols3 ? 2 : 3;
+    int sb = (int)((kSmemBudget - fixed - (size_t)q.sa * a_slot) / b_bytes);
+    if (sb > 8) sb = 8;
+    if (sb < 2) return fail(S2S_ERR_INVALID, "conv_fwd(halo): tile does not fit in shared memory");
+    q.sb = sb;
+    const size_t smem = (size_t)q.sa * a_slot + (size_t)sb * b_bytes + fixed;
+    int clusters = num_sms() / 2;
+    if (clusters > q.total_pairs) clusters = q.total_pairs;
+    const dim3 grid3(2 * clusters);
+    cudaStream_t st3 = (cudaStream_t)stream;
+#define S2S_HALO_LAUNCH(MTV, PROV)                                                          \
+    do {                                                                                    \
+        rc = set_smem(conv_halo_pair_kernel<MTV, PROV>, smem);                              \
+        if (rc) return rc;                                                                  \
+        conv_halo_pair_kernel<MTV, PROV><<<grid3, kConvThreads, smem, st3>>>(q);            \
+    } while (0)
+    if (mt3 == 2 && q.prologue) S2S_HALO_LAUNCH(2, true);
+    else if (mt3 == 2) S2S_HALO_LAUNCH(2, false);
+    else if (q.prologue) S2S_HALO_LAUNCH(1, true);
+    else S2S_HALO_LAUNCH(1, false);
+#undef S2S_HALO_LAUNCH
+    LAUNCH_CHECK("conv_halo_pair_kernel");
+    return S2S_OK;
+}
+
 static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, int Wout, const void* w_packed, int Ktot,
                          int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                          const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt,
@@ -332,97 +467,20 @@ static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, in
     if ((out_bf16 != nullptr) == (out_f32 != nullptr))
         return fail(S2S_ERR_INVALID, "conv_fwd: exactly one of out_bf16 / out_f32 must be given");
     // halo-tiled CTA-pair kernel: stride-1 convs with at least one 3x3 segment
-    {
-        const bool ok = out_bf16 && !axpy_x && halo_eligible(srcs, nsrc, Cout);
-        const bool any3 = ok;
-        if (ok && any3) {
-            Conv3Params q;
-            memset(&q, 0, sizeof(q));
-            const bool cols3 = conv_halo() == 3;
-            int BN3, mt3, tx3, ty3;
-            halo_geometry(Hout, Wout, Cout, &BN3, &mt3, &tx3, &ty3);
-            q.cols3 = cols3 ? 1 : 0;
-            q.nseg = nsrc;
-            int kb3 = 0;
-            for (int s = 0; s < nsrc; ++s) {
-                const s2s_conv_src& sc = srcs[s];
-                int rc = sc.taps == 9 ? make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, cols3 ? kHaloTW : kHaloPitch,
-                                                          kHaloTH * mt3 + 2)
-                                      : make_act_tmap_box(&q.tmA[s], sc.x, B, Hout, Wout, sc.C, kHaloTW, kHaloTH);
-                if (rc) return rc;
-                q.seg[s].taps = sc.taps;
-                q.seg[s].cblocks = (sc.C + kBlockK - 1) / kBlockK;
-                q.seg[s].stride = 1;
-                q.seg[s].C = sc.C;
-                q.seg_kb[s] = kb3;
-                kb3 += sc.taps * q.seg[s].cblocks;
-            }
-            if (kb3 * kBlockK != Ktot)
-                return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kb3 * kBlockK);
-            {
-                cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-                cuuint64_t str[1] = {(cuuint64_t)Ktot * 2};
-                cuuint32_t box[2] = {kBlockK, (cuuint32_t)(BN3 / 2)};
-                int rc = make_tmap(&q.tmW, w_packed, 2, dims, str, box);
-                if (rc) return rc;
-            }
-            int rc = make_act_tmap_box(&q.tmOut, out_bf16, B, Hout, Wout, Cout, kHaloTW, kHaloTH);
-            if (rc) return rc;
-            q.B = B; q.Hout = Hout; q.Wout = Wout; q.Cout = Cout;
-            q.tiles_x = tx3;
-            q.tiles_y = ty3;
-            q.stats = (float2*)stats_out;
-            q.stat_tiles = tx3 * ty3 * mt3;
-            if (norms) {
-                q.prologue = 1;
-                q.act = act;
-                for (int s = 0; s < nsrc; ++s) {
-                    q.seg_coef[s] = (const float2*)norms[s].coef;
-                    q.seg_x[s] = (const uint16_t*)srcs[s].x;
-                    q.seg_coef_ld[s] = norms[s].ld;
-                    q.seg_coef_off[s] = norms[s].off;
-                }
-            }
-            q.m_tiles = B * q.tiles_x * q.tiles_y;
-            q.n_tiles_n = Cout / BN3;
-            q.total_pairs = ((q.m_tiles + 1) / 2) * q.n_tiles_n;
-            q.BN = BN3;
-            q.tmem_cols = pow2_cols(2 * mt3 * BN3);
-            q.base_off_mode = conv_halo() == 1 ? 1 : 0;
-            q.bias = bias;
-            q.residual = (const __nv_bfloat16*)residual;
-            q.a_fmt = a_fmt; q.w_fmt = w_fmt; q.out_fmt = out_fmt; q.res_fmt = res_fmt;
-            const size_t halo_bytes = cols3 ? (size_t)3 * (kHaloTH * mt3 + 2) * kHaloTW * 128
-                                            : (size_t)(kHaloTH * mt3 + 2) * kHaloPitch * 128;
-            size_t a_slot = halo_bytes > (size_t)mt3 * kABytes ? halo_bytes : (size_t)mt3 * kABytes;
-            a_slot = (a_slot + 1023) / 1024 * 1024;
-            q.a_slot = (uint32_t)a_slot;
-            const size_t b_bytes = (size_t)(BN3 / 2) * kBlockK * 2;
-            const size_t fixed = 2 * kOutStageBytes + 1024 + 3072;  // + alignment slack + barriers / statistics scratch
-            q.sa = cols3 ? 2 : 3;
-            int sb = (int)((kSmemBudget - fixed - (size_t)q.sa * a_slot) / b_bytes);
-            if (sb > 8) sb = 8;
-            if (sb < 2) return fail(S2S_ERR_INVALID, "conv_fwd(halo): tile does not fit in shared memory");
-            q.sb = sb;
-            const size_t smem = (size_t)q.sa * a_slot + (size_t)sb * b_bytes + fixed;
-            int clusters = num_sms() / 2;
-            if (clusters > q.total_pairs) clusters = q.total_pairs;
-            const dim3 grid3(2 * clusters);
-            cudaStream_t st3 = (cudaStream_t)stream;
-#define S2S_HALO_LAUNCH(MTV, PROV)                                                          \
-    do {                                                                                    \
-        rc = set_smem(conv_halo_pair_kernel<MTV, PROV>, smem);                              \
-        if (rc) return rc;                                                                  \
-        conv_halo_pair_kernel<MTV, PROV><<<grid3, kConvThreads, smem, st3>>>(q);            \
-    } while (0)
-            if (mt3 == 2 && q.prologue) S2S_HALO_LAUNCH(2, true);
-            else if (mt3 == 2) S2S_HALO_LAUNCH(2, false);
-            else if (q.prologue) S2S_HALO_LAUNCH(1, true);
-            else S2S_HALO_LAUNCH(1, false);
-#undef S2S_HALO_LAUNCH
-            LAUNCH_CHECK("conv_halo_pair_kernel");
-            return S2S_OK;
+    if (out_bf16 && !axpy_x && halo_eligible(srcs, nsrc, Cout)) {
+        HaloSeg hs[kMaxSeg];
+        int kb = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            hs[s].view = dense_view(srcs[s].x, B, Hout, Wout, srcs[s].C);
+            hs[s].kind = srcs[s].taps;
+            hs[s].ntaps = srcs[s].taps;
+            hs[s].tapmap = srcs[s].taps == 9 ? kTapIdentity : 0ull;
+            kb += srcs[s].taps * ((srcs[s].C + kBlockK - 1) / kBlockK);
         }
+        if (kb * kBlockK != Ktot)
+            return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d does not match the segments (%d)", Ktot, kb * kBlockK);
+        return halo_launch(hs, nsrc, dense_view(out_bf16, B, Hout, Wout, Cout), w_packed, Ktot, 0, Cout, bias, residual,
+                           stats_out, 0, 0, a_fmt, w_fmt, out_fmt, res_fmt, stream, norms, act);
     }
     // CTA-pair kernel (tcgen05 cta_group::2): 16-bit NHWC outputs with Cout a multiple of 128
     if (out_bf16 && !axpy_x && Cout % 128 == 0 && conv_pairs()) {
@@ -569,9 +627,21 @@ static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, in
     return S2S_OK;
 }
 
+static int wgrad_impl(const ActView& dyv, const void* x, int Cq, int taps, unsigned long long tapmap, int stride,
+                      float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream);
+
 int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int stride, int B, int Hout, int Wout,
                    float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream) {
     if (taps != 1 && taps != 9) return fail(S2S_ERR_INVALID, "conv_wgrad: taps = %d", taps);
+    return wgrad_impl(dense_view(dy, B, Hout, Wout, Cm), x, Cq, taps, taps == 9 ? kTapIdentity : 0ull, stride, dw, ldn, n_off,
+                      dy_fmt, x_fmt, stream);
+}
+
+// dyv: the output-side tensor as a (possibly strided) view; x: dense [B, H*stride, W*stride, Cq]; taps logical taps at the
+// 3x3 positions of `tapmap`
+static int wgrad_impl(const ActView& dyv, const void* x, int Cq, int taps, unsigned long long tapmap, int stride,
+                      float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream) {
+    const int B = dyv.B, Hout = dyv.H, Wout = dyv.W, Cm = dyv.C;
     if (dy_fmt != x_fmt)
         return fail(S2S_ERR_INVALID, "conv_wgrad: dy and x must share one 16-bit format (convert with s2s_convert16)");
     if (Cq % 64) return fail(S2S_ERR_INVALID, "conv_wgrad: input channels must be a multiple of 64 (got %d)", Cq);
@@ -579,11 +649,12 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     if (Cm % 256 == 0 && Cq % 128 == 0 && wgrad_pairs()) {  // CTA-pair kernel: M = 256 output channels per MMA
         Wgrad2Params q;
         memset(&q, 0, sizeof(q));
-        int rc = make_act_tmap(&q.tmP, dy, B, Hout, Wout, Cm, 1);
+        int rc = make_view_tmap(&q.tmP, dyv, kTileW, kTileH);
         if (rc) return rc;
         rc = make_act_tmap(&q.tmQ, x, B, Hout * stride, Wout * stride, Cq, stride);
         if (rc) return rc;
         q.taps = taps; q.stride = stride; q.Cq = Cq; q.Mtot = Cm; q.Ntot = Cq;
+        q.tapmap = tapmap;
         q.BN = (Cq % 256 == 0) ? 256 : 128;
         q.m_pairs = Cm / 256;
         q.n_tiles = Cq / q.BN;
@@ -612,11 +683,12 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
     }
     WgradParams p;
     memset(&p, 0, sizeof(p));
-    int rc = make_act_tmap(&p.tmP, dy, B, Hout, Wout, Cm, 1);
+    int rc = make_view_tmap(&p.tmP, dyv, kTileW, kTileH);
     if (rc) return rc;
     rc = make_act_tmap(&p.tmQ, x, B, Hout * stride, Wout * stride, Cq, stride);
     if (rc) return rc;
     p.taps = taps; p.stride = stride; p.Cq = Cq; p.Mtot = Cm; p.Ntot = Cq;
+    p.tapmap = tapmap;
     p.BN = (Cq % 256 == 0) ? 256 : (Cq % 128 == 0 ? 128 : 64);
     p.m_tiles = (Cm + 127) / 128;
     p.n_tiles = Cq / p.BN;
@@ -665,6 +737,95 @@ int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n
     unpack_wgrad_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(dw, taps, M, ldn, n_off, n_count, grad,
                                                                                   Cin_total, n_begin, beta);
     LAUNCH_CHECK("unpack_wgrad_kernel");
+    return S2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ phase-decomposed Upsample conv
+// torchcfm Upsample = F.interpolate(x, scale_factor=2, mode="nearest") -> conv3x3(pad 1).  For output pixels (2y+py, 2x+px)
+// that is a 2x2 conv over the LOW-resolution tensor with tap-summed weights (s2s_pack_conv_weight_mode, mode 1 + phase):
+// the 4x tensor is never materialised and 4/9 of the MACs remain -- in forward, dgrad and wgrad alike.
+// Logical tap ti = ai*2 + bi of phase (py, px) reads low-res pixel (y + ai - 1 + py, x + bi - 1 + px).
+static unsigned long long upconv_tapmap(int py, int px, bool mirrored) {
+    unsigned long long m = 0;
+    for (int ti = 0; ti < 4; ++ti) {
+        const int ai = ti >> 1, bi = ti & 1;
+        int ry = ai + py, rx = bi + px;  // 3x3 position (offset + 1) of the tap in the low-res neighbourhood
+        if (mirrored) { ry = 2 - ry; rx = 2 - rx; }
+        m |= (unsigned long long)(ry * 3 + rx) << (4 * ti);
+    }
+    return m;
+}
+
+int s2s_upconv_stat_tiles(int H, int W, int Cout) {
+    if (!conv_halo() || !conv_pairs() || Cout % 128 != 0) return 0;
+    int BN, mt, tx, ty;
+    halo_geometry(H, W, Cout, &BN, &mt, &tx, &ty);
+    return 4 * tx * ty * mt;
+}
+
+int s2s_upconv_supported(int C, int Cout) {
+    return (conv_halo() && conv_pairs() && Cout % 128 == 0 && C % 128 == 0 && C % 64 == 0) ? 1 : 0;
+}
+
+int s2s_upconv_fwd(const void* x, int B, int H, int W, int C, const void* w_packed, int Cout, const float* bias, void* out,
+                   float* stats_out, int a_fmt, int w_fmt, int out_fmt, void* stream) {
+    if (!x || !w_packed || !out) return fail(S2S_ERR_INVALID, "upconv_fwd: null argument");
+    if (!s2s_upconv_supported(C, Cout))
+        return fail(S2S_ERR_INVALID, "upconv_fwd: needs C and Cout multiples of 128 and the halo CTA-pair kernel (C=%d Cout=%d)", C, Cout);
+    if (a_fmt != w_fmt) return fail(S2S_ERR_INVALID, "upconv_fwd: activations and weights must share one 16-bit format");
+    const int cblocks = C / kBlockK;
+    const int Ktot = 16 * cblocks * kBlockK;
+    const int st_total = stats_out ? s2s_upconv_stat_tiles(H, W, Cout) : 0;
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        HaloSeg seg;
+        seg.view = dense_view(x, B, H, W, C);
+        seg.kind = 9;
+        seg.ntaps = 4;
+        seg.tapmap = upconv_tapmap(py, px, false);
+        int rc = halo_launch(&seg, 1, phase_view(out, B, H, W, Cout, py, px), w_packed, Ktot, ph * 4 * cblocks, Cout, bias,
+                             nullptr, stats_out, st_total, ph * (st_total / 4), a_fmt, w_fmt, out_fmt, out_fmt, stream,
+                             nullptr, 0);
+        if (rc) return rc;
+    }
+    return S2S_OK;
+}
+
+int s2s_upconv_dgrad(const void* dy, int B, int H, int W, int Cm, const void* w_packed, int Cin, void* dx, int a_fmt,
+                     int w_fmt, int out_fmt, void* stream) {
+    if (!dy || !w_packed || !dx) return fail(S2S_ERR_INVALID, "upconv_dgrad: null argument");
+    if (!s2s_upconv_supported(Cm, Cin))
+        return fail(S2S_ERR_INVALID, "upconv_dgrad: needs channel counts that are multiples of 128 (Cm=%d Cin=%d)", Cm, Cin);
+    if (a_fmt != w_fmt) return fail(S2S_ERR_INVALID, "upconv_dgrad: gradients and weights must share one 16-bit format");
+    const int cblocks = Cm / kBlockK;
+    HaloSeg segs[4];
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        segs[ph].view = phase_view(dy, B, H, W, Cm, py, px);
+        segs[ph].kind = 9;
+        segs[ph].ntaps = 4;
+        segs[ph].tapmap = upconv_tapmap(py, px, true);  // adjoint: the tap that read (y + a, x + b) scatters back from (y - a, x - b)
+    }
+    return halo_launch(segs, 4, dense_view(dx, B, H, W, Cin), w_packed, 16 * cblocks * kBlockK, 0, Cin, nullptr, nullptr,
+                       nullptr, 0, 0, a_fmt, w_fmt, out_fmt, out_fmt, stream, nullptr, 0);
+}
+
+int s2s_upconv_wgrad(const void* dy, int Cm, const void* x, int Cq, int B, int H, int W, float* dw16, int dy_fmt, int x_fmt,
+                     void* stream) {
+    if (!dy || !x || !dw16) return fail(S2S_ERR_INVALID, "upconv_wgrad: null argument");
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        int rc = wgrad_impl(phase_view(dy, B, H, W, Cm, py, px), x, Cq, 4, upconv_tapmap(py, px, false), 1,
+                            dw16 + (size_t)ph * 4 * Cm * Cq, Cq, 0, dy_fmt, x_fmt, stream);
+        if (rc) return rc;
+    }
+    return S2S_OK;
+}
+
+int s2s_upconv_unpack_wgrad(const float* dw16, int M, int N, float* grad_oihw, void* stream) {
+    if (!dw16 || !grad_oihw) return fail(S2S_ERR_INVALID, "upconv_unpack_wgrad: null argument");
+    upconv_unpack_wgrad_kernel<<<ew_grid((long long)M * N * 9), kEwThreads, 0, (cudaStream_t)stream>>>(dw16, M, N, grad_oihw);
+    LAUNCH_CHECK("upconv_unpack_wgrad_kernel");
     return S2S_OK;
 }
 

@@ -28,17 +28,23 @@ constexpr int kTileW = 16, kTileH = 8, kTileM = kTileW * kTileH;  // 128 output 
 constexpr int kBlockK = 64;                                      // bf16 channels per k-block = one 128 B swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;                    // 16 KB
 constexpr int kOutStageBytes = kTileM * 64 * 2;                  // 16 KB staging per 64-channel output chunk
-constexpr int kMaxSeg = 3;
+constexpr int kMaxSeg = 4;
 constexpr int kConvThreads = 256;
 
 enum ConvMode : int { kModeBf16Nhwc = 0, kModeF32Nchw = 1 };
 
 struct ConvSeg {
-    int taps;     // 9 (3x3, pad 1) or 1 (1x1)
+    int taps;     // 9 (3x3 neighbourhood, pad 1) or 1 (1x1): the KIND of the segment (which box is fetched)
     int cblocks;  // ceil(C / 64)
     int stride;   // 1 or 2
     int C;        // channels of this segment's tensor
+    // halo-tiled kernel only: the filter taps actually multiplied, in the order the packed weight stores them.  Entry i
+    // (4 bits of tapmap) is the 3x3 position dy*3 + dx of logical tap i.  A plain 3x3 conv has ntaps = 9 and the identity
+    // map; the phase-decomposed Upsample / transposed convs use 1-, 2- and 4-tap subsets (0 = plain).
+    int ntaps;
+    unsigned long long tapmap;
 };
+constexpr unsigned long long kTapIdentity = 0x876543210ull;
 
 struct ConvParams {
     CUtensorMap tmA[kMaxSeg];
@@ -711,7 +717,8 @@ struct Conv3Params {
     const float* bias;
     const __nv_bfloat16* residual;
     float2* stats;             // optional per-sub-tile (sum, sumsq) of the stored outputs, as in Conv2Params
-    int stat_tiles;
+    int stat_tiles, stat_off;  // sub-tiles per sample in the statistics buffer; first sub-tile this launch writes (the four
+                               // phase launches of an Upsample conv fill one buffer)
     int a_fmt, w_fmt, out_fmt, res_fmt;
     // Fused normalisation prologue (inference): a segment with seg_coef != nullptr is NOT the activated tensor but the
     // raw one; warps 2-3 rewrite each landed halo box in place as act(x * A + Bc) with the per-(sample, channel)
@@ -850,7 +857,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             ia = 0;
                             pha ^= 1;
                         }
-                        for (int tap = 0; tap < sg.taps; ++tap) {
+                        for (int tap = 0; tap < sg.ntaps; ++tap) {  // logical taps, in packed-weight order
                             mbar_wait(&emptyB[ib], phb ^ 1);
                             if (elect_one()) {
                                 if (leader) mbar_arrive_expect_tx(&fullB[ib], 2 * b_bytes);
@@ -889,7 +896,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                         else
                             mbar_wait(&fullA[ia], pha);
                         const uint32_t a_base = smem_u32(ringA + (size_t)ia * p.a_slot);
-                        for (int tap = 0; tap < sg.taps; ++tap) {
+                        for (int ti = 0; ti < sg.ntaps; ++ti) {
+                            const int tap = (int)((sg.tapmap >> (4 * ti)) & 15ull);  // 3x3 position of logical tap ti
                             mbar_wait(&fullB[ib], phb);
                             tc_fence_after();
                             const uint32_t b_addr = smem_u32(ringB + (size_t)ib * b_bytes);
@@ -1171,7 +1179,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                                 o.x += t2.x;
                                 o.y += t2.y;
                             }
-                            const int sub = (ty * MT + h) * p.tiles_x + tx;
+                            const int sub = p.stat_off + (ty * MT + h) * p.tiles_x + tx;
                             p.stats[((size_t)b * p.stat_tiles + sub) * p.Cout + nbase + et] = o;
                         }
                     }
@@ -1202,6 +1210,7 @@ struct WgradParams {
     CUtensorMap tmP;  // 5-D {Cm, W, 1, H, B}      (output-side tensor, never shifted)
     CUtensorMap tmQ;  // 5-D parity view of the input-side tensor
     int taps, stride, Cq;       // Cq = channels of Q (parity offset for stride 2)
+    unsigned long long tapmap;  // taps > 1: 3x3 position (dy*3 + dx) of logical tap i in bits [4i, 4i+4)
     int Mtot, Ntot;             // real extents (Cout, Cin of this segment)
     int BN;                     // 64, 128 or 256
     int m_tiles, n_tiles, splits;
@@ -1267,8 +1276,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     if (warp == 0) {
         {  // whole warp, convergent; one elected lane issues the TMA loads
             int sx = 0, sy = 0, cp = 0, coff = 0;
-            if (p.taps == 9) {
-                const int dx = tap % 3, dy = tap / 3;
+            if (p.taps > 1) {
+                const int pos = (int)((p.tapmap >> (4 * tap)) & 15ull);
+                const int dx = pos % 3, dy = pos / 3;
                 if (p.stride == 1) {
                     sx = dx - 1;
                     sy = dy - 1;
@@ -1389,6 +1399,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
 struct Wgrad2Params {
     CUtensorMap tmP, tmQ;
     int taps, stride, Cq;
+    unsigned long long tapmap;
     int Mtot, Ntot, BN;
     int m_pairs, n_tiles, splits;
     int tiles_x, tiles_y, pix_tiles;
@@ -1452,8 +1463,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     if (warp == 0) {
         {  // whole warp, convergent; one elected lane issues the TMA loads
             int sx = 0, sy = 0, cp = 0, coff = 0;
-            if (p.taps == 9) {
-                const int dx = tap % 3, dy = tap / 3;
+            if (p.taps > 1) {
+                const int pos = (int)((p.tapmap >> (4 * tap)) & 15ull);
+                const int dx = pos % 3, dy = pos / 3;
                 if (p.stride == 1) {
                     sx = dx - 1;
                     sy = dy - 1;

@@ -89,62 +89,95 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsig
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// OIHW fp32 -> bf16 [rows_pad][ld_k] K-major operand of the implicit GEMM.
+// OIHW fp32 -> 16-bit [rows_pad][ld_k] K-major operand of the implicit GEMM.
 //   forward : dst[co][k_off + tap*ci_count + (ci-ci_begin)]           = w[co][ci][tap]          rows = Cout
 //   dgrad   : dst[ci-ci_begin][k_off + tap*Cout + co]                 = w[co][ci][taps-1-tap]   rows = ci_count
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ci_begin,
-                                        int ci_count, uint16_t* __restrict__ dst, int ld_k, int k_off,
-                                        int transpose_flip, int fmt) {
-    const long long total = (long long)Cout * ci_count * taps;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        // iterate in destination order so that writes are coalesced
-        int row, tap, inner;
-        if (!transpose_flip) {
-            inner = (int)(i % ci_count);
-            tap = (int)((i / ci_count) % taps);
-            row = (int)(i / ((long long)ci_count * taps));
-            const float v = w[((size_t)row * Cin + ci_begin + inner) * taps + tap];
-            dst[(size_t)row * ld_k + k_off + (size_t)tap * ci_count + inner] = pack1(v, fmt);
-        } else {
-            inner = (int)(i % Cout);
-            tap = (int)((i / Cout) % taps);
-            row = (int)(i / ((long long)Cout * taps));
-            const float v = w[((size_t)inner * Cin + ci_begin + row) * taps + (taps - 1 - tap)];
-            dst[(size_t)row * ld_k + k_off + (size_t)tap * Cout + inner] = pack1(v, fmt);
-        }
+// mode = 1 + phase (phase = py*2 + px), 3x3 weights only -- the phase-decomposed Upsample conv: nearest x2 followed by a
+// 3x3/pad-1 conv is, for the output pixels (2y+py, 2x+px), a 2x2 conv over the LOW-resolution input whose taps are sums
+// of the 3x3 taps that land on the same low-resolution pixel.  Logical tap ti = ai*2 + bi covers the filter rows
+// R(py, ai) and columns R(px, bi) with R(0,0) = {0}, R(0,1) = {1,2}, R(1,0) = {0,1}, R(1,1) = {2} (summed in fp32
+// before rounding to 16 bit):
+//   forward : dst[co][k_off + ti*ci_count + (ci-ci_begin)]  = sum w[co][ci][R x R]
+//   dgrad   : dst[ci-ci_begin][k_off + ti*Cout + co]        = the same sum (tap positions are mirrored by the tap map
+//                                                              of the launch, not by the packing)
+struct PackJob {
+    const float* w;
+    uint16_t* dst;
+    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, mode;
+};
+__device__ __forceinline__ void phase_range(int parity, int idx, int& lo, int& hi) {  // R(parity, idx) = [lo, hi]
+    if (parity == 0) { lo = idx == 0 ? 0 : 1; hi = idx == 0 ? 0 : 2; }
+    else             { lo = idx == 0 ? 0 : 2; hi = idx == 0 ? 1 : 2; }
+}
+__device__ __forceinline__ void pack_conv_weight_elem(const PackJob& jb, long long i) {
+    const int ltaps = jb.mode == 0 ? jb.taps : 4;  // logical taps of the packed operand
+    int row, tap, inner;
+    // iterate in destination order so that writes are coalesced
+    if (!jb.transpose_flip) {
+        inner = (int)(i % jb.ci_count);
+        tap = (int)((i / jb.ci_count) % ltaps);
+        row = (int)(i / ((long long)jb.ci_count * ltaps));
+    } else {
+        inner = (int)(i % jb.Cout);
+        tap = (int)((i / jb.Cout) % ltaps);
+        row = (int)(i / ((long long)jb.Cout * ltaps));
     }
+    const int co = jb.transpose_flip ? inner : row;
+    const int ci = jb.ci_begin + (jb.transpose_flip ? row : inner);
+    const float* wp = jb.w + ((size_t)co * jb.Cin + ci) * jb.taps;
+    float v;
+    if (jb.mode == 0) {
+        v = wp[jb.transpose_flip ? (jb.taps - 1 - tap) : tap];
+    } else {
+        const int phase = jb.mode - 1;
+        int y0, y1, x0, x1;
+        phase_range(phase >> 1, tap >> 1, y0, y1);
+        phase_range(phase & 1, tap & 1, x0, x1);
+        v = 0.f;
+        for (int dy = y0; dy <= y1; ++dy)
+            for (int dx = x0; dx <= x1; ++dx) v += wp[dy * 3 + dx];
+    }
+    const size_t col = (size_t)jb.k_off + (size_t)tap * (jb.transpose_flip ? jb.Cout : jb.ci_count) + inner;
+    jb.dst[(size_t)row * jb.ld_k + col] = pack1(v, jb.fmt);
+}
+__global__ void pack_conv_weight_kernel(PackJob jb) {
+    const long long total = (long long)jb.Cout * jb.ci_count * (jb.mode == 0 ? jb.taps : 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        pack_conv_weight_elem(jb, i);
 }
 
 // The same packing for MANY weights in one launch (after an optimizer step every cached GEMM operand is stale: 158
 // tensors per training step).  Host uploads a job table + (job, chunk) work list, as for the multi-tensor Adam.
 constexpr int kPackChunk = 16384;
-struct PackJob {
-    const float* w;
-    uint16_t* dst;
-    int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, pad;
-};
 __global__ void __launch_bounds__(256) pack_conv_weight_multi_kernel(const PackJob* __restrict__ jobs,
                                                                      const int2* __restrict__ work) {
     const int2 wi = work[blockIdx.x];
     const PackJob jb = jobs[wi.x];
-    const long long total = (long long)jb.Cout * jb.ci_count * jb.taps;
+    const long long total = (long long)jb.Cout * jb.ci_count * (jb.mode == 0 ? jb.taps : 4);
     const long long beg = (long long)wi.y * kPackChunk;
     const long long end = min(total, beg + kPackChunk);
-    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
-        int row, tap, inner;
-        if (!jb.transpose_flip) {
-            inner = (int)(i % jb.ci_count);
-            tap = (int)((i / jb.ci_count) % jb.taps);
-            row = (int)(i / ((long long)jb.ci_count * jb.taps));
-            const float v = jb.w[((size_t)row * jb.Cin + jb.ci_begin + inner) * jb.taps + tap];
-            jb.dst[(size_t)row * jb.ld_k + jb.k_off + (size_t)tap * jb.ci_count + inner] = pack1(v, jb.fmt);
-        } else {
-            inner = (int)(i % jb.Cout);
-            tap = (int)((i / jb.Cout) % jb.taps);
-            row = (int)(i / ((long long)jb.Cout * jb.taps));
-            const float v = jb.w[((size_t)inner * jb.Cin + jb.ci_begin + row) * jb.taps + (jb.taps - 1 - tap)];
-            jb.dst[(size_t)row * jb.ld_k + jb.k_off + (size_t)tap * jb.Cout + inner] = pack1(v, jb.fmt);
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) pack_conv_weight_elem(jb, i);
+}
+
+// Weight gradient of the phase-decomposed Upsample conv: src = [16 = phase*4 + ti][M][N] fp32 (what the four phase wgrad
+// launches accumulated) -> OIHW [M][N][9]: each 3x3 tap belongs, in every phase, to exactly one logical tap, so
+// dW[m][n][dy][dx] = sum_phase src[phase][ti(phase, dy, dx)][m][n].
+__global__ void upconv_unpack_wgrad_kernel(const float* __restrict__ src, int M, int N, float* __restrict__ grad) {
+    const long long total = (long long)M * N * 9;
+    const size_t plane = (size_t)M * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 9);
+        const long long mn = i / 9;
+        const int dy = tap / 3, dx = tap % 3;
+        float v = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const int py = ph >> 1, px = ph & 1;
+            const int ai = py == 0 ? (dy == 0 ? 0 : 1) : (dy == 2 ? 1 : 0);
+            const int bi = px == 0 ? (dx == 0 ? 0 : 1) : (dx == 2 ? 1 : 0);
+            v += src[(size_t)(ph * 4 + ai * 2 + bi) * plane + mn];
         }
+        grad[i] = v;
     }
 }
 

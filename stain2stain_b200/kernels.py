@@ -97,37 +97,39 @@ def to_float(x: torch.Tensor, fmt: int) -> torch.Tensor:
 
 
 def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, k_off: int = 0, ci_begin: int = 0,
-                     ci_count: Optional[int] = None, transpose_flip: bool = False, fmt: int = ACT):
-    """w: fp32 [Cout, Cin, kh, kw] (or [Cout, Cin(,1)] for linear / Conv1d) -> rows of dst (16-bit [rows, ld_k])."""
+                     ci_count: Optional[int] = None, transpose_flip: bool = False, fmt: int = ACT, mode: int = 0):
+    """w: fp32 [Cout, Cin, kh, kw] (or [Cout, Cin(,1)] for linear / Conv1d) -> rows of dst (16-bit [rows, ld_k]).
+    mode = 1 + phase: tap-summed operand of the phase-decomposed Upsample conv (include/s2s_b200.h)."""
     cout, cin = w.shape[0], w.shape[1]
     taps = w[0, 0].numel() if w.dim() > 2 else 1
     ci_count = cin - ci_begin if ci_count is None else ci_count
     assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == T16 and dst.is_contiguous()
     with _Prof("pack_conv_weight", 0.0, 6.0 * cout * ci_count * taps):
-        check(_L().s2s_pack_conv_weight(ptr(w), cout, cin, taps, ci_begin, ci_count, ptr(dst), dst.shape[1], k_off,
-                                        int(transpose_flip), fmt, stream_ptr()), "pack_conv_weight")
+        check(_L().s2s_pack_conv_weight_mode(ptr(w), cout, cin, taps, ci_begin, ci_count, ptr(dst), dst.shape[1], k_off,
+                                             int(transpose_flip), fmt, int(mode), stream_ptr()), "pack_conv_weight")
 
 
 def pack_conv_weight_multi(jobs, table_cache: dict):
-    """jobs: [(w fp32, dst 16-bit, k_off, ci_begin, ci_count, transpose_flip, fmt)] on ONE device -> one launch.
+    """jobs: [(w fp32, dst 16-bit, k_off, ci_begin, ci_count, transpose_flip, fmt, mode)] on ONE device -> one launch.
     The device job table / work list are cached in `table_cache` by the job set (pointers are stable across steps)."""
     if not jobs:
         return
     dev = jobs[0][0].device
-    sig = tuple((w.data_ptr(), dst.data_ptr(), k_off, cb, cc, tf, fmt) for (w, dst, k_off, cb, cc, tf, fmt) in jobs)
+    sig = tuple((w.data_ptr(), dst.data_ptr(), k_off, cb, cc, tf, fmt, mode) for (w, dst, k_off, cb, cc, tf, fmt, mode) in jobs)
     hit = table_cache.get(sig)
     if hit is None:
         chunk = int(_L().s2s_pack_chunk())
         arr = (_lib.PackJob * len(jobs))()
         work = []
         total_bytes = 0.0
-        for i, (w, dst, k_off, cb, cc, tf, fmt) in enumerate(jobs):
+        for i, (w, dst, k_off, cb, cc, tf, fmt, mode) in enumerate(jobs):
             assert w.is_contiguous() and w.dtype == torch.float32 and dst.dtype == T16 and dst.is_contiguous()
             assert w.device == dev and dst.device == dev
             cout, cin = w.shape[0], w.shape[1]
             taps = w[0, 0].numel() if w.dim() > 2 else 1
-            arr[i] = _lib.PackJob(w.data_ptr(), dst.data_ptr(), cout, cin, taps, cb, cc, dst.shape[1], k_off, int(tf), fmt, 0)
-            n = cout * cc * taps
+            arr[i] = _lib.PackJob(w.data_ptr(), dst.data_ptr(), cout, cin, taps, cb, cc, dst.shape[1], k_off, int(tf), fmt,
+                                  int(mode))
+            n = cout * cc * (taps if mode == 0 else 4)
             total_bytes += 6.0 * n
             work.extend((i, c) for c in range((n + chunk - 1) // chunk))
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().pin_memory()
@@ -354,6 +356,59 @@ def gn_bwd_apply(x, g, coef, pqr, c_off: int, add, dx, silu: bool, drop_p: float
         check(_L().s2s_gn_bwd_apply(ptr(x), ptr(g), g.shape[3], B, H * W, Cc, ptr(coef), ptr(pqr), coef.shape[1],
                                     c_off, ptr(add), ptr(dx), int(silu), float(drop_p), int(seed), ptr(mask), x_fmt,
                                     g_fmt, stream_ptr()), "gn_bwd_apply")
+
+
+def upconv_supported(c: int, cout: int) -> bool:
+    return bool(_L().s2s_upconv_supported(int(c), int(cout)))
+
+
+def upconv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: Optional[torch.Tensor], want_stats: bool = False,
+               a_fmt: int = ACT, out_fmt: int = ACT):
+    """nearest-x2 upsample + 3x3 conv of x [B,H,W,C] -> [B,2H,2W,cout] as four phase launches over the low-res tensor.
+    w_packed: 16-bit [cout][16*C] (phase-summed taps).  Algorithmic work = the reference's 9 taps at full resolution."""
+    _nhwc_check(x)
+    B, H, W, Cc = x.shape
+    assert w_packed.dtype == T16 and w_packed.is_contiguous() and tuple(w_packed.shape) == (cout, 16 * Cc)
+    out = torch.empty((B, 2 * H, 2 * W, cout), dtype=T16, device=x.device)
+    stats = None
+    if want_stats and EPI_STATS:
+        nt = int(_L().s2s_upconv_stat_tiles(H, W, cout))
+        if nt > 0:
+            stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=x.device)
+    with _Prof("conv_igemm", 2.0 * B * 4 * H * W * cout * Cc * 9):
+        check(_L().s2s_upconv_fwd(ptr(x), B, H, W, Cc, ptr(w_packed), cout, ptr(bias), ptr(out), ptr(stats), a_fmt, a_fmt,
+                                  out_fmt, stream_ptr()), "upconv_fwd")
+        LAUNCHES[0] += 3
+    return out, stats
+
+
+def upconv_dgrad(dy: torch.Tensor, w_packed: torch.Tensor, cin: int, fmt: int = GRAD):
+    """dy [B,2H,2W,Cm] -> dx [B,H,W,cin]: ONE launch, four phase views of dy as GEMM segments (16 logical taps)."""
+    _nhwc_check(dy)
+    B, H2, W2, Cm = dy.shape
+    assert w_packed.dtype == T16 and w_packed.is_contiguous() and tuple(w_packed.shape) == (cin, 16 * Cm)
+    dx = torch.empty((B, H2 // 2, W2 // 2, cin), dtype=T16, device=dy.device)
+    with _Prof("conv_igemm", 2.0 * B * H2 * W2 * cin * Cm * 9):
+        check(_L().s2s_upconv_dgrad(ptr(dy), B, H2 // 2, W2 // 2, Cm, ptr(w_packed), cin, ptr(dx), fmt, fmt, fmt,
+                                    stream_ptr()), "upconv_dgrad")
+    return dx
+
+
+def upconv_wgrad(dy: torch.Tensor, x: torch.Tensor, fmt: int = GRAD) -> torch.Tensor:
+    """-> OIHW fp32 [Cm][Cq][3][3] weight gradient of the Upsample conv (dy [B,2H,2W,Cm], x [B,H,W,Cq] low-res)."""
+    _nhwc_check(dy)
+    _nhwc_check(x)
+    B, H, W, Cq = x.shape
+    Cm = dy.shape[3]
+    assert dy.shape[1] == 2 * H and dy.shape[2] == 2 * W
+    dw16 = torch.zeros((16, Cm, Cq), dtype=torch.float32, device=x.device)
+    with _Prof("conv_wgrad", 2.0 * B * 4 * H * W * Cm * Cq * 9):
+        check(_L().s2s_upconv_wgrad(ptr(dy), Cm, ptr(x), Cq, B, H, W, ptr(dw16), fmt, fmt, stream_ptr()), "upconv_wgrad")
+        LAUNCHES[0] += 3
+    grad = torch.empty((Cm, Cq, 3, 3), dtype=torch.float32, device=x.device)
+    with _Prof("unpack_wgrad", 0.0, 4.0 * (16 + 9) * Cm * Cq):
+        check(_L().s2s_upconv_unpack_wgrad(ptr(dw16), Cm, Cq, ptr(grad), stream_ptr()), "upconv_unpack_wgrad")
+    return grad
 
 
 def upsample2x(x):

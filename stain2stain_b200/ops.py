@@ -23,7 +23,8 @@ class _PackCache:
 
     `make(dst)` returns `(operand, jobs)`: the destination tensor (allocated zero-filled when `dst` is None, else the
     previous operand of the same parameters -- an optimizer step only changed the values, the zero padding is never
-    written) and the pack jobs `(index of the weight in ws, k_off, ci_begin, ci_count, transpose_flip, fmt)` that fill it.  When a stale
+    written) and the pack jobs `(index of the weight in ws, k_off, ci_begin, ci_count, transpose_flip, fmt[, mode])` that fill it
+    (mode: 0 plain, 1 + phase = tap-summed operand of the phase-decomposed Upsample conv).  When a stale
     operand is requested, EVERY stale operand of the cache is re-packed by one multi-tensor launch
     (`s2s_pack_conv_weight_multi`): after an optimizer step that is all 158 operands of the model at once."""
 
@@ -62,9 +63,9 @@ class _PackCache:
 
     @staticmethod
     def _run_jobs(dst, jobs, ws):
-        for (wi, k_off, ci_begin, ci_count, tf, fmt) in jobs:
+        for (wi, k_off, ci_begin, ci_count, tf, fmt, *mode) in jobs:
             K.pack_conv_weight(ws[wi].detach(), dst, k_off=k_off, ci_begin=ci_begin, ci_count=ci_count, transpose_flip=tf,
-                               fmt=fmt)
+                               fmt=fmt, mode=mode[0] if mode else 0)
 
     def _refresh_stale(self, device):
         """Re-pack, in one launch, every operand on `device` whose parameters changed in place (same storage, new version)."""
@@ -83,8 +84,8 @@ class _PackCache:
             return
         jobs = []
         for key, ent, ws, sig in stale:
-            for (wi, k_off, ci_begin, ci_count, tf, fmt) in ent[3]:
-                jobs.append((ws[wi].detach(), ent[1], k_off, ci_begin, ci_count, tf, fmt))
+            for (wi, k_off, ci_begin, ci_count, tf, fmt, *mode) in ent[3]:
+                jobs.append((ws[wi].detach(), ent[1], k_off, ci_begin, ci_count, tf, fmt, mode[0] if mode else 0))
         K.pack_conv_weight_multi(jobs, self._tables)
         for key, ent, ws, sig in stale:
             ent[0] = sig
@@ -310,6 +311,61 @@ class _Upsample2x(torch.autograd.Function):
 
 def upsample2x(x):
     return _Upsample2x.apply(x)
+
+
+class UpConvPlan:
+    """Packed operands of one Upsample conv (nearest x2 -> conv3x3) in its phase-decomposed form."""
+    _counter = [0]
+
+    def __init__(self, cin: int, cout: int):
+        UpConvPlan._counter[0] += 1
+        self.uid, self.cin, self.cout = UpConvPlan._counter[0], cin, cout
+
+    def packed_fwd(self, w):
+        def make(dst):
+            wp = dst if dst is not None else torch.zeros((self.cout, 16 * self.cin), dtype=T16, device=w.device)
+            return wp, [(0, ph * 4 * self.cin, 0, self.cin, False, K.ACT, 1 + ph) for ph in range(4)]
+        return PACK_CACHE.get(("upfwd", self.uid), [w], make)
+
+    def packed_dgrad(self, w):
+        def make(dst):
+            wd = dst if dst is not None else torch.zeros((self.cin, 16 * self.cout), dtype=T16, device=w.device)
+            return wd, [(0, ph * 4 * self.cout, 0, self.cin, True, K.GRAD, 1 + ph) for ph in range(4)]
+        return PACK_CACHE.get(("updgrad", self.uid), [w], make)
+
+
+class _UpConv(torch.autograd.Function):
+    """torchcfm `Upsample.forward` with use_conv: F.interpolate(x, 2, "nearest") -> conv3x3, without the 4x tensor and at
+    4/9 of its MACs (four 2x2 convs over the low-resolution input, one per output pixel phase)."""
+
+    @staticmethod
+    def forward(ctx, plan: UpConvPlan, stats_box, x, w, b):
+        out, st = K.upconv_fwd(x, plan.packed_fwd(w), plan.cout, b.detach(), want_stats=True)
+        stats_box.append(st)
+        ctx.plan = plan
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, w = ctx.saved_tensors
+        plan = ctx.plan
+        d_out = d_out.contiguous()
+        need = ctx.needs_input_grad
+        d_x = d_w = d_b = None
+        if need[4]:
+            d_b = torch.zeros(plan.cout, dtype=torch.float32, device=d_out.device)
+            K.channel_sum(d_out, d_b)
+        if need[3]:
+            d_w = K.upconv_wgrad(d_out, K.convert16(x, K.ACT, K.GRAD))
+        if need[2]:
+            d_x = K.upconv_dgrad(d_out, plan.packed_dgrad(w), plan.cin)
+        return None, None, d_x, d_w, d_b
+
+
+def upsample_conv(plan: UpConvPlan, x, w, b):
+    box = []
+    return _tag(_UpConv.apply(plan, box, x, w, b), box)
 
 
 # --------------------------------------------------------------------------------------------- stem / head (3-channel ends)

@@ -88,9 +88,14 @@ class Upsample(nn.Module):
         if use_conv:
             self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=1)
             self._plan = ConvPlan((Seg(0, 0, 0, channels, 9, 1),), self.out_channels)
+            self._up_plan = ops.UpConvPlan(channels, self.out_channels)
 
     def forward(self, srcs):
-        u = ops.upsample2x(_single(srcs))
+        x = _single(srcs)
+        if self.use_conv and ops.K.upconv_supported(self.channels, self.out_channels):
+            # phase-decomposed: four 2x2 convs over the low-resolution tensor, the 4x tensor is never written
+            return ops.upsample_conv(self._up_plan, x, self.conv.weight, self.conv.bias)
+        u = ops.upsample2x(x)
         if not self.use_conv:
             return u
         return ops.fused_conv(self._plan, [u], [self.conv.weight], [self.conv.bias])
