@@ -136,6 +136,13 @@ int s2s_upconv_wgrad(const void* dy, int Cm, const void* x, int Cq, int B, int H
                      void* stream);
 int s2s_upconv_unpack_wgrad(const float* dw16, int M, int N, float* grad_oihw, void* stream);
 
+/* Data gradient of Downsample = conv3x3(stride 2, pad 1) (torchcfm unet.py Downsample.op) without zero insertion: the four
+ * input-pixel phases (2y+py, 2x+px) are 1-, 2-, 2- and 4-tap convs over the low-resolution gradient dy [B,H,W,Cm], stored
+ * into dx [B,2H,2W,Cin] through strided TMA maps.  w_packed = the ordinary dgrad operand of s2s_pack_conv_weight
+ * (transpose_flip = 1): 16-bit [Cin][9*Cm].  Needs Cm % 128 == 0 and Cin % 128 == 0 (s2s_upconv_supported). */
+int s2s_downconv_dgrad(const void* dy, int B, int H, int W, int Cm, const void* w_packed, int Cin, void* dx, int a_fmt,
+                       int w_fmt, int out_fmt, void* stream);
+
 /* dw fp32 [taps][M][ldn] -> grad_oihw[m][n_begin + n][tap] = beta * grad + dw[tap][m][n_off + n] */
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad_oihw,
                      int Cin_total, int n_begin, float beta, void* stream);

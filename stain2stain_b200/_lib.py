@@ -48,6 +48,7 @@ SIGNATURES = {
     "s2s_upconv_dgrad": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp],
     "s2s_upconv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "s2s_upconv_unpack_wgrad": [_vp, _i, _i, _vp, _vp],
+    "s2s_downconv_dgrad": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp],
     "s2s_pack_chunk": [],
     "s2s_pack_conv_weight_multi": [_vp, _vp, _i, _vp],
     "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],

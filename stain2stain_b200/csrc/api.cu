@@ -323,6 +323,8 @@ struct HaloSeg {
     int kind;                   // 9: 3x3 neighbourhood (halo box), 1: 1x1
     int ntaps;                  // logical taps multiplied (kind 9: 1..9, kind 1: 1)
     unsigned long long tapmap;  // 3x3 position of each logical tap
+    unsigned long long wmap;    // weight tap slot of each logical tap (kTapIdentity: packed in logical order)
+    int wslots;                 // tap slots this segment occupies in the packed weight (0 = ntaps)
 };
 
 // One launch of the halo-tiled CTA-pair kernel over explicit views.  Output view dims = the GEMM's pixel space.
@@ -349,11 +351,12 @@ static int halo_launch(const HaloSeg* segs, int nseg, const ActView& outv, const
         q.seg[s].taps = sc.kind;
         q.seg[s].ntaps = sc.ntaps;
         q.seg[s].tapmap = sc.tapmap;
+        q.seg[s].wmap = sc.wmap;
         q.seg[s].cblocks = (sc.view.C + kBlockK - 1) / kBlockK;
         q.seg[s].stride = 1;
         q.seg[s].C = sc.view.C;
         q.seg_kb[s] = kb3;
-        kb3 += sc.ntaps * q.seg[s].cblocks;
+        kb3 += (sc.wslots > 0 ? sc.wslots : sc.ntaps) * q.seg[s].cblocks;
     }
     if (kb3 * kBlockK > Ktot)
         return fail(S2S_ERR_INVALID, "conv_fwd: Ktot = %d is smaller than the segments need (%d)", Ktot, kb3 * kBlockK);
@@ -475,6 +478,8 @@ static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, in
             hs[s].kind = srcs[s].taps;
             hs[s].ntaps = srcs[s].taps;
             hs[s].tapmap = srcs[s].taps == 9 ? kTapIdentity : 0ull;
+            hs[s].wmap = kTapIdentity;
+            hs[s].wslots = 0;
             kb += srcs[s].taps * ((srcs[s].C + kBlockK - 1) / kBlockK);
         }
         if (kb * kBlockK != Ktot)
@@ -783,6 +788,8 @@ int s2s_upconv_fwd(const void* x, int B, int H, int W, int C, const void* w_pack
         seg.kind = 9;
         seg.ntaps = 4;
         seg.tapmap = upconv_tapmap(py, px, false);
+        seg.wmap = kTapIdentity;
+        seg.wslots = 0;
         int rc = halo_launch(&seg, 1, phase_view(out, B, H, W, Cout, py, px), w_packed, Ktot, ph * 4 * cblocks, Cout, bias,
                              nullptr, stats_out, st_total, ph * (st_total / 4), a_fmt, w_fmt, out_fmt, out_fmt, stream,
                              nullptr, 0);
@@ -805,6 +812,8 @@ int s2s_upconv_dgrad(const void* dy, int B, int H, int W, int Cm, const void* w_
         segs[ph].kind = 9;
         segs[ph].ntaps = 4;
         segs[ph].tapmap = upconv_tapmap(py, px, true);  // adjoint: the tap that read (y + a, x + b) scatters back from (y - a, x - b)
+        segs[ph].wmap = kTapIdentity;
+        segs[ph].wslots = 0;
     }
     return halo_launch(segs, 4, dense_view(dx, B, H, W, Cin), w_packed, 16 * cblocks * kBlockK, 0, Cin, nullptr, nullptr,
                        nullptr, 0, 0, a_fmt, w_fmt, out_fmt, out_fmt, stream, nullptr, 0);
@@ -826,6 +835,46 @@ int s2s_upconv_unpack_wgrad(const float* dw16, int M, int N, float* grad_oihw, v
     if (!dw16 || !grad_oihw) return fail(S2S_ERR_INVALID, "upconv_unpack_wgrad: null argument");
     upconv_unpack_wgrad_kernel<<<ew_grid((long long)M * N * 9), kEwThreads, 0, (cudaStream_t)stream>>>(dw16, M, N, grad_oihw);
     LAUNCH_CHECK("upconv_unpack_wgrad_kernel");
+    return S2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dgrad of the stride-2 conv
+// Downsample = conv3x3(stride 2, pad 1): input pixel i = 2*o + d - 1.  The data gradient at input pixels (2y+py, 2x+px)
+// only receives the taps whose parity matches: py = 0 -> d = 1 (from output row y); py = 1 -> d = 0 (row y+1) and d = 2
+// (row y).  So the four input phases are 1-, 2-, 2- and 4-tap convs over the LOW-resolution gradient, written through
+// strided TMA store maps: the 9 algorithmic taps exactly, instead of 36 taps' worth over a zero-inserted 4x tensor.
+// w_packed is the ordinary dgrad operand ([Cin][9*Cm], slot t = filter tap 8 - t): the tap slots are permuted by `wmap`.
+int s2s_downconv_dgrad(const void* dy, int B, int H, int W, int Cm, const void* w_packed, int Cin, void* dx, int a_fmt,
+                       int w_fmt, int out_fmt, void* stream) {
+    if (!dy || !w_packed || !dx) return fail(S2S_ERR_INVALID, "downconv_dgrad: null argument");
+    if (!s2s_upconv_supported(Cm, Cin))
+        return fail(S2S_ERR_INVALID, "downconv_dgrad: needs channel counts that are multiples of 128 (Cm=%d Cin=%d)", Cm, Cin);
+    if (a_fmt != w_fmt) return fail(S2S_ERR_INVALID, "downconv_dgrad: gradients and weights must share one 16-bit format");
+    const int cblocks = Cm / kBlockK;
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        HaloSeg seg;
+        seg.view = dense_view(dy, B, H, W, Cm);
+        seg.kind = 9;
+        seg.ntaps = 0;
+        seg.tapmap = 0;
+        seg.wmap = 0;
+        seg.wslots = 9;
+        for (int d = 0; d < 3; ++d) {
+            if ((d & 1) == (py & 1)) continue;      // needs d == py + 1 (mod 2)
+            const int oy = (py == 1 && d == 0) ? 1 : 0;  // output row offset the tap reads: y + oy
+            for (int e = 0; e < 3; ++e) {
+                if ((e & 1) == (px & 1)) continue;
+                const int ox = (px == 1 && e == 0) ? 1 : 0;
+                seg.tapmap |= (unsigned long long)((oy + 1) * 3 + (ox + 1)) << (4 * seg.ntaps);
+                seg.wmap |= (unsigned long long)(8 - (d * 3 + e)) << (4 * seg.ntaps);
+                ++seg.ntaps;
+            }
+        }
+        int rc = halo_launch(&seg, 1, phase_view(dx, B, H, W, Cin, py, px), w_packed, 9 * cblocks * kBlockK, 0, Cin, nullptr,
+                             nullptr, nullptr, 0, 0, a_fmt, w_fmt, out_fmt, out_fmt, stream, nullptr, 0);
+        if (rc) return rc;
+    }
     return S2S_OK;
 }
 

@@ -43,6 +43,8 @@ struct ConvSeg {
     // map; the phase-decomposed Upsample / transposed convs use 1-, 2- and 4-tap subsets (0 = plain).
     int ntaps;
     unsigned long long tapmap;
+    unsigned long long wmap;  // tap slot of logical tap i inside the packed weight (bits [4i, 4i+4)); identity for a weight
+                              // packed in logical order, a permutation when a plain 9-tap operand is reused
 };
 constexpr unsigned long long kTapIdentity = 0x876543210ull;
 
@@ -862,7 +864,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             if (elect_one()) {
                                 if (leader) mbar_arrive_expect_tx(&fullB[ib], 2 * b_bytes);
                                 tma_load_2d_2cta(ringB + (size_t)ib * b_bytes, &p.tmW, &fullB[ib],
-                                                 (p.seg_kb[s] + tap * sg.cblocks + cb) * kBlockK, n0);
+                                                 (p.seg_kb[s] + (int)((sg.wmap >> (4 * tap)) & 15ull) * sg.cblocks + cb) * kBlockK,
+                                                 n0);
                             }
                             __syncwarp();
                             if (++ib == SB) {

@@ -411,6 +411,20 @@ def upconv_wgrad(dy: torch.Tensor, x: torch.Tensor, fmt: int = GRAD) -> torch.Te
     return grad
 
 
+def downconv_dgrad(dy: torch.Tensor, w_packed: torch.Tensor, cin: int, fmt: int = GRAD):
+    """Data gradient of a stride-2 3x3 conv: dy [B,H,W,Cm] -> dx [B,2H,2W,cin], four phase launches (1+2+2+4 = the 9
+    algorithmic taps) over the low-resolution gradient; w_packed = the ordinary dgrad operand [cin][9*Cm]."""
+    _nhwc_check(dy)
+    B, H, W, Cm = dy.shape
+    assert w_packed.dtype == T16 and w_packed.is_contiguous() and tuple(w_packed.shape) == (cin, 9 * Cm)
+    dx = torch.empty((B, 2 * H, 2 * W, cin), dtype=T16, device=dy.device)
+    with _Prof("conv_igemm", 2.0 * B * H * W * cin * Cm * 9):
+        check(_L().s2s_downconv_dgrad(ptr(dy), B, H, W, Cm, ptr(w_packed), cin, ptr(dx), fmt, fmt, fmt, stream_ptr()),
+              "downconv_dgrad")
+        LAUNCHES[0] += 3
+    return dx
+
+
 def upsample2x(x):
     _nhwc_check(x)
     B, H, W, Cc = x.shape

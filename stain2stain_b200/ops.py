@@ -208,6 +208,11 @@ class _FusedConv(torch.autograd.Function):
                 K.unpack_wgrad(dw, d_ws[s.weight].view(cout, w.shape[1], -1), 0, s.ci_count, s.ci_begin, 0.0)
             if need[4 + s.src]:
                 wd = plan.packed_dgrad(si, weights)
+                if s.stride == 2 and s.taps == 9 and K.upconv_supported(cout, s.ci_count):
+                    # phase-decomposed transposed conv: no zero-inserted tensor, the 9 algorithmic taps exactly
+                    dx = K.downconv_dgrad(d_out, wd, s.ci_count)
+                    d_srcs[s.src] = dx if d_srcs[s.src] is None else d_srcs[s.src] + dx
+                    continue
                 g = d_out if s.stride == 1 else K.zero_insert2x(d_out)
                 dx = K.conv_fwd([(g, s.taps, 1)], wd, s.ci_count, g.shape[1], g.shape[2], a_fmt=K.GRAD, w_fmt=K.GRAD,
                                 out_fmt=K.GRAD, alg_macs=float(B) * hout * wout * cout * s.ci_count * s.taps)

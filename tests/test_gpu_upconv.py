@@ -104,3 +104,33 @@ def test_upsample_module_uses_the_phase_path_and_matches_the_materialised_one():
     y2 = up([xh.detach()])
     ref2 = _ref(x, up.conv.weight, up.conv.bias)
     assert rel_l2(nchw(y2), ref2) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 128), (1, 32, 16, 256, 256), (2, 8, 24, 128, 256)])
+def test_downconv_dgrad_matches_autograd_of_the_stride2_conv(B, H, W, Cin, Cout):
+    """Phase-decomposed data gradient of Downsample (conv3x3, stride 2, pad 1): H, W are the OUTPUT dims."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(H * 13 + Cin)
+    x = torch.zeros(B, Cin, 2 * H, 2 * W, device=DEV, requires_grad=True)
+    w = rb(torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin), "grad")
+    dy = rb(torch.randn(B, Cout, H, W, device=DEV, generator=g), "grad")
+    F.conv2d(x, w, None, stride=2, padding=1).backward(dy)
+    wd = torch.zeros((Cin, 9 * Cout), dtype=k.T16, device=DEV)
+    k.pack_conv_weight(w, wd, ci_begin=0, ci_count=Cin, transpose_flip=True, fmt=k.GRAD)
+    dx = nchw(k.downconv_dgrad(nhwc(dy, "grad"), wd, Cin), "grad")
+    assert_close_bf16(dx, x.grad, "downconv dgrad")
+    # and through the autograd op the UNet's Downsample uses
+    from stain2stain_b200 import ops
+    from stain2stain_b200.ops import ConvPlan, Seg
+    plan = ConvPlan((Seg(0, 0, 0, Cin, 9, 2),), Cout)
+    xin = rb(torch.randn(B, Cin, 2 * H, 2 * W, device=DEV, generator=g))
+    xh = nhwc(xin).requires_grad_()
+    wp = w.clone().requires_grad_()
+    bias = torch.zeros(Cout, device=DEV, requires_grad=True)
+    n0 = k.LAUNCHES[0]
+    y = ops.fused_conv(plan, [xh], [wp], [bias])
+    y.backward(nhwc(dy, "grad"))
+    xr = xin.clone().requires_grad_()
+    ref = F.conv2d(xr, w, None, stride=2, padding=1)
+    gx, = torch.autograd.grad(ref, [xr], dy)
+    assert_close_bf16(nchw(xh.grad, "grad"), gx, "Downsample dgrad through fused_conv")
