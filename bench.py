@@ -167,13 +167,6 @@ def run_train(args, rank, world, local):
     B = args.batch
     lit = build_lit(dev)
     lit.train()
-    step_mod = _StepModule(lit)
-    if world > 1:
-        # ONE bucket: a single flat fp32 all-reduce (284 MB, < 1 ms over NVSwitch) right after backward.  The default
-        # 25 MB buckets put ~12 ncclAllReduce kernels next to persistent 148-CTA tcgen05 kernels whose static tile
-        # schedule turns every SM NCCL holds into a second wave (round 1: +9.4 ms per step at 8 GPUs).
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True,
-                                                             bucket_cap_mb=args.bucket_mb)
     opt = lit.configure_optimizers()["optimizer"]
     g = torch.Generator(device=dev).manual_seed(1984 + rank)
     # inputs larger than L2 (2 x 50 MB per step at B=64) and a fresh pair per step: no L2 reuse between steps
@@ -183,12 +176,57 @@ def run_train(args, rank, world, local):
     host0 = [x.cpu().pin_memory() for x in x0s[:2]]
     host1 = [x.cpu().pin_memory() for x in x1s[:2]]
 
-    def step(x0, x1):
+    def step_eager(x0, x1):  # the same step launched from Python (per-kernel CUDA events need eager launches)
         opt.zero_grad(set_to_none=True)
-        loss = step_mod(x0, x1)
+        loss = lit.training_step((x0, x1), 0)
         loss.backward()
         opt.step()
         return loss
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, one instrumented EAGER step
+    # (events cannot be placed inside a graph replay; same kernels, same shapes).  Taken before the graphs are captured so
+    # that the eager step's activations are freed again.  Every rank takes the steps, only rank 0 records events.
+    prof = {}
+    for _ in range(2):
+        step_eager(x0s[1], x1s[1])
+    torch.cuda.synchronize()
+    if rank == 0:
+        K.PROFILE = []
+    step_eager(x0s[0], x1s[0])
+    torch.cuda.synchronize()
+    if rank == 0:
+        prof = K.profile_summary(K.PROFILE)
+        K.PROFILE = None
+    opt.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    _barrier(world)
+
+    if args.no_graph:
+        step_mod = _StepModule(lit)
+        if world > 1:
+            # ONE bucket: a single flat fp32 all-reduce (284 MB, < 1 ms over NVSwitch) right after backward.  The default
+            # 25 MB buckets put ~12 ncclAllReduce kernels next to persistent 148-CTA tcgen05 kernels whose static tile
+            # schedule turns every SM NCCL holds into a second wave (round 1: +9.4 ms per step at 8 GPUs).
+            step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True,
+                                                                 bucket_cap_mb=args.bucket_mb)
+
+        def step(x0, x1):
+            opt.zero_grad(set_to_none=True)
+            loss = step_mod(x0, x1)
+            loss.backward()
+            opt.step()
+            return loss
+        how = "eager launches" + (f", torch DDP bucket_cap_mb={args.bucket_mb}" if world > 1 else "")
+    else:
+        # the step as CUDA graphs (stain2stain_b200/graphed.py): forward + backward + flat gradient gather [+ Adam] replayed;
+        # at N > 1 one eager all-reduce of the flat 284 MB gradient buffer sits between the two graphs
+        from stain2stain_b200.graphed import GraphedTrainStep
+        gs = GraphedTrainStep(lit, opt, (B, 3, 256, 256), dev, process_group=dist.group.WORLD if world > 1 else None)
+
+        def step(x0, x1):
+            return gs(x0, x1)
+        how = "CUDA-graph replay" + (", one flat fp32 gradient all-reduce (NCCL) between the backward and the Adam graph"
+                                     if world > 1 else "")
 
     for i in range(args.warmup):
         step(x0s[i % n_sets], x1s[i % n_sets])
@@ -212,26 +250,16 @@ def run_train(args, rank, world, local):
     _barrier(world)
     e0.record()
     for i in range(args.steps):
-        x0 = host0[i % 2].to(dev, non_blocking=True)
-        x1 = host1[i % 2].to(dev, non_blocking=True)
+        if args.no_graph:
+            x0 = host0[i % 2].to(dev, non_blocking=True)
+            x1 = host1[i % 2].to(dev, non_blocking=True)
+        else:  # the graphed step copies pinned host memory straight into its static input buffers
+            x0, x1 = host0[i % 2], host1[i % 2]
         loss_host = float(step(x0, x1).detach())  # device -> host read of the step's result
     e1.record()
     _barrier(world)
     ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, one instrumented step
-    roof = None
-    prof = {}
-    # (every rank takes the step -- it contains the gradient all-reduce -- but only rank 0 records events)
-    torch.cuda.synchronize()
-    if rank == 0:
-        K.PROFILE = []
-    step(x0s[0], x1s[0])
-    torch.cuda.synchronize()
-    if rank == 0:
-        prof = K.profile_summary(K.PROFILE)
-        K.PROFILE = None
-    _barrier(world)
     tiles = B * world * args.steps
     out = {
         "metric": "256x256 tiles/s, conditional flow-matching train step (FM sample + UNet fwd + MSE + bwd + allreduce + Adam)",
@@ -243,13 +271,14 @@ def run_train(args, rank, world, local):
         "config": {"workload": "configs[1]: simple flow-matching UNet training, 256x256 tiles, batch 64/GPU, DDP",
                    "per_gpu_batch": B, "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()),
                    "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "Adam lr 1e-4 (fused, own kernel)",
-                   "ddp_bucket_mb": args.bucket_mb if world > 1 else None,
+                   "step_launch": how,
                    "l2": "inputs larger than L2 (2 x %.0f MB per step, 4 rotating sets)" % (B * 3 * 256 * 256 * 4 / 1e6)},
         "loss": last_loss,
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": 2 * B * 3 * 256 * 256 * 4,
                 "d2h_bytes_per_step": 4, "loss": loss_host},
         "gpu_launches": launches,
     }
+    roof = None
     if rank == 0:
         pk = _peaks()
         step_ms = ms / args.steps
@@ -585,6 +614,8 @@ def main():
     ap.add_argument("--sample-tiles", type=int, default=0,
                     help="tiles of the sampling record over ALL ranks (default 512 per GPU: 4096 on 8 GPUs = configs[2])")
     ap.add_argument("--sample-batch", type=int, default=64, help="sampling micro-batch inside the train-mode run")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: launch the step from Python (torch DDP at N > 1) "
+                                                           "instead of replaying CUDA graphs")
     ap.add_argument("--bucket-mb", type=int, default=512,
                     help="DDP gradient bucket size; 512 = ONE flat all-reduce of the 284 MB of fp32 gradients")
     args = ap.parse_args()

@@ -183,6 +183,12 @@ int s2s_gn_coef_parts(const float* stats0, int C0, const float* stats1, int C1, 
  * reads 1 bit / element instead of re-evaluating the Philox hash (mask_in of the backward kernels; NULL = re-hash). */
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
                  int ld_out, int silu, float drop_p, uint64_t seed, void* mask_out, int x_fmt, int y_fmt, void* stream);
+/* s2s_gn_apply for launches replayed from a CUDA graph: seed_step_dev (may be NULL) points at a device-resident uint64 step
+ * counter that is mixed into `seed` (seed + counter * 0x9E3779B97F4A7C15), so every replay draws a fresh dropout mask
+ * although the host-side argument is frozen at capture. */
+int s2s_gn_apply_step(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
+                      int ld_out, int silu, float drop_p, uint64_t seed, const uint64_t* seed_step_dev, void* mask_out,
+                      int x_fmt, int y_fmt, void* stream);
 
 /* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g).
  *   reduce: red_part[b][chunk][c_off+c] = (sum dz, sum dz*xhat) over the chunk   (fp32 [B][s2s_gn_chunks][Ctot][2])
@@ -298,6 +304,34 @@ int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C,
                      const double* sums, float smooth, float w_dice, float w_ce, const float* gscale, float* dlogits,
                      void* stream);
 
+/* ---- embedding path (row a9): timestep embedding, time_embed MLP, label embedding, the 22 FiLM linears -------------- */
+
+/* One fp32 GEMM  C[m][n] = bias[n] + add[m][n] + sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]  (element strides; bias / add
+ * may be NULL), optionally with a second output C2 = silu(C).  Many of them run in ONE launch (s2s_linear_multi: the job
+ * table is a kernel parameter, so the launch is capturable in a CUDA graph; more than s2s_linear_max_jobs() jobs are
+ * split into several launches).  Plain fp32 FMA -- the reference's own arithmetic for these layers.
+ * Replaces: nn.Linear / nn.Embedding-add / nn.SiLU of torchcfm UNetModel.time_embed, label_emb and every
+ * ResBlock.emb_layers, forward and backward (dX = dY W, dW = dY^T X, db = 1^T dY are the same GEMM
+ * with other strides). */
+typedef struct {
+    const float* A;
+    const float* B;
+    float* C;
+    const float* bias;
+    const float* add;
+    float* C2;
+    int M, N, K;
+    int ldc, ld_add;
+    int sam, sak, sbk, sbn;
+} s2s_gemm_job;
+int s2s_linear_max_jobs(void);
+int s2s_linear_multi(const s2s_gemm_job* jobs_host, int njobs, void* stream);
+/* out[i] = (sum_j parts[j*n + i]) * silu'(z[i])  (z NULL: plain sum): folds the per-ResBlock partial gradients of the shared
+ * embedding and takes them through the SiLU in one pass. */
+int s2s_sum_parts_silu_bwd(const float* parts, int nparts, long long n, const float* z, float* out, void* stream);
+/* guided-diffusion timestep_embedding: emb[b] = [cos(t_b f_i) | sin(t_b f_i)], f_i = exp(-ln(max_period) i / (dim/2)). */
+int s2s_timestep_embedding(const float* t, int B, int dim, float max_period, float* emb, void* stream);
+
 /* One parameter tensor of the fused optimizer: fp32 param / grad / exp_avg / exp_avg_sq of n elements. */
 typedef struct {
     float* p;
@@ -317,6 +351,23 @@ int s2s_adam_chunk(void);
  * src/models/conditional_flow_matching.py:112-131). */
 int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1,
                    double beta2, double eps, double weight_decay, int step, double grad_scale, void* stream);
+
+/* s2s_adam_multi for launches replayed from a CUDA graph: step_dev (may be NULL -> `step` is used) points at the 1-based
+ * step count in device memory (int64); the bias corrections are evaluated on the device from the live counter. */
+int s2s_adam_multi_step(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, int step, const long long* step_dev,
+                        double grad_scale, void* stream);
+
+/* dst_i[0..n) = src_i[0..n) for many fp32 tensors in ONE launch (table / work list as s2s_adam_multi, chunks of
+ * s2s_adam_chunk() elements): gathers the per-parameter gradients into one flat buffer, so that the data-parallel training
+ * step (one gradient all-reduce per step) issues a single NCCL all-reduce.
+ * Replaces: DistributedDataParallel's bucket copies (configs/trainer/ddp.yaml strategy: ddp). */
+typedef struct {
+    const float* src;
+    float* dst;
+    long long n;
+} s2s_copy_tensor;
+int s2s_copy_multi(const s2s_copy_tensor* tensors_dev, const int* work_dev, int n_work, void* stream);
 
 #ifdef __cplusplus
 }

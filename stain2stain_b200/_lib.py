@@ -29,6 +29,12 @@ class PackJob(C.Structure):
                 ("transpose_flip", C.c_int), ("fmt", C.c_int), ("mode", C.c_int)]
 
 
+class GemmJob(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p), ("add", C.c_void_p),
+                ("C2", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("ldc", C.c_int), ("ld_add", C.c_int),
+                ("sam", C.c_int), ("sak", C.c_int), ("sbk", C.c_int), ("sbn", C.c_int)]
+
+
 class ConvNorm(C.Structure):
     _fields_ = [("coef", C.c_void_p), ("ld", C.c_int), ("off", C.c_int)]
 
@@ -92,6 +98,13 @@ SIGNATURES = {
     "s2s_nchw_f32_to_nhwc16_pad": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "s2s_seg_loss_sums": [_vp, _vp, _i, _i, _i, _ll, _vp, _vp],
     "s2s_seg_loss_bwd": [_vp, _vp, _i, _i, _i, _ll, _vp, _f, _f, _f, _vp, _vp, _vp],
+    "s2s_gn_apply_step": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _vp, _vp, _i, _i, _vp],
+    "s2s_adam_multi_step": [_vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _d, _vp],
+    "s2s_copy_multi": [_vp, _vp, _i, _vp],
+    "s2s_linear_max_jobs": [],
+    "s2s_linear_multi": [C.POINTER(GemmJob), _i, _vp],
+    "s2s_sum_parts_silu_bwd": [_vp, _i, _ll, _vp, _vp, _vp],
+    "s2s_timestep_embedding": [_vp, _i, _i, _f, _vp, _vp],
     "s2s_adam_chunk": [],
     "s2s_adam_multi": [_vp, _vp, _i, _d, _d, _d, _d, _d, _i, _d, _vp],
 }

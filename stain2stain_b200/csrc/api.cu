@@ -9,6 +9,7 @@
 
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
+#include "linear.cuh"
 #include "multitask.cuh"
 #include "optim.cuh"
 #include "tiles.cuh"
@@ -939,6 +940,13 @@ int s2s_gn_coef_parts(const float* stats0, int C0, const float* stats1, int C1, 
 
 int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
                  int ld_out, int silu, float drop_p, uint64_t seed, void* mask_out, int x_fmt, int y_fmt, void* stream) {
+    return s2s_gn_apply_step(x, B, HW, C, coef, Ctot, c_off, y, y2_bf16, ld_out, silu, drop_p, seed, nullptr, mask_out, x_fmt,
+                             y_fmt, stream);
+}
+
+int s2s_gn_apply_step(const void* x, int B, int HW, int C, const float* coef, int Ctot, int c_off, void* y, void* y2_bf16,
+                      int ld_out, int silu, float drop_p, uint64_t seed, const uint64_t* seed_step_dev, void* mask_out,
+                      int x_fmt, int y_fmt, void* stream) {
     int rc = check_vec_layout(C, "gn_apply");
     if (rc) return rc;
     if (ld_out % 8 || c_off % 8) return fail(S2S_ERR_INVALID, "gn_apply: ld_out / c_off must be multiples of 8");
@@ -947,7 +955,8 @@ int s2s_gn_apply(const void* x, int B, int HW, int C, const float* coef, int Cto
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(y2_bf16 != nullptr, DUAL, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
         (gn_apply_kernel<SILU, DROP, XF, YF, DUAL><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y,
-            (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed, (uint8_t*)mask_out)))))));
+            (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed, (uint8_t*)mask_out,
+            (const unsigned long long*)seed_step_dev)))))));
     LAUNCH_CHECK("gn_apply_kernel");
     return S2S_OK;
 }
@@ -1205,10 +1214,65 @@ int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C,
     return S2S_OK;
 }
 
+int s2s_linear_max_jobs(void) { return kLinMaxJobs; }
+
+int s2s_linear_multi(const s2s_gemm_job* jobs, int njobs, void* stream) {
+    static_assert(sizeof(s2s_gemm_job) == sizeof(GemmJob), "ABI struct drifted from the kernel's");
+    if (njobs <= 0) return S2S_OK;
+    if (!jobs) return fail(S2S_ERR_INVALID, "linear_multi: null job table");
+    for (int first = 0; first < njobs; first += kLinMaxJobs) {
+        GemmBatch b;
+        memset(&b, 0, sizeof(b));
+        b.njobs = njobs - first < kLinMaxJobs ? njobs - first : kLinMaxJobs;
+        int tiles = 0;
+        for (int j = 0; j < b.njobs; ++j) {
+            const s2s_gemm_job& jb = jobs[first + j];
+            if (!jb.A || !jb.B || !jb.C || jb.M <= 0 || jb.N <= 0 || jb.K <= 0)
+                return fail(S2S_ERR_INVALID, "linear_multi: job %d has bad arguments", first + j);
+            memcpy(&b.jobs[j], &jb, sizeof(GemmJob));
+            tiles += ((jb.M + kLinTile - 1) / kLinTile) * ((jb.N + kLinTile - 1) / kLinTile);
+            b.tile_end[j] = tiles;
+        }
+        linear_multi_kernel<<<tiles, kLinThreads, 0, (cudaStream_t)stream>>>(b);
+        LAUNCH_CHECK("linear_multi_kernel");
+    }
+    return S2S_OK;
+}
+
+int s2s_sum_parts_silu_bwd(const float* parts, int nparts, long long n, const float* z, float* out, void* stream) {
+    if (!parts || !out || nparts < 1 || n < 1) return fail(S2S_ERR_INVALID, "sum_parts_silu_bwd: bad arguments");
+    sum_parts_silu_bwd_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(parts, nparts, n, z, out);
+    LAUNCH_CHECK("sum_parts_silu_bwd_kernel");
+    return S2S_OK;
+}
+
+int s2s_timestep_embedding(const float* t, int B, int dim, float max_period, float* emb, void* stream) {
+    if (!t || !emb || B < 1 || dim < 2) return fail(S2S_ERR_INVALID, "timestep_embedding: bad arguments");
+    timestep_embedding_kernel<<<ew_grid((long long)B * dim), kEwThreads, 0, (cudaStream_t)stream>>>(t, B, dim, max_period, emb);
+    LAUNCH_CHECK("timestep_embedding_kernel");
+    return S2S_OK;
+}
+
 int s2s_adam_chunk(void) { return kAdamChunk; }
 
 int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1, double beta2,
                    double eps, double weight_decay, int step, double grad_scale, void* stream) {
+    return s2s_adam_multi_step(tensors_dev, work_dev, n_work, lr, beta1, beta2, eps, weight_decay, step, nullptr, grad_scale,
+                               stream);
+}
+
+int s2s_copy_multi(const s2s_copy_tensor* tensors_dev, const int* work_dev, int n_work, void* stream) {
+    static_assert(sizeof(s2s_copy_tensor) == sizeof(CopyTensor), "ABI struct drifted from the kernel's");
+    if (n_work <= 0) return S2S_OK;
+    if (!tensors_dev || !work_dev) return fail(S2S_ERR_INVALID, "copy_multi: bad arguments");
+    copy_multi_kernel<<<n_work, kAdamThreads, 0, (cudaStream_t)stream>>>((const CopyTensor*)tensors_dev, (const int2*)work_dev);
+    LAUNCH_CHECK("copy_multi_kernel");
+    return S2S_OK;
+}
+
+int s2s_adam_multi_step(const s2s_adam_tensor* tensors_dev, const int* work_dev, int n_work, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, int step, const long long* step_dev,
+                        double grad_scale, void* stream) {
     static_assert(sizeof(s2s_adam_tensor) == sizeof(AdamTensor), "ABI struct drifted from the kernel's");
     if (n_work <= 0) return S2S_OK;
     if (!tensors_dev || !work_dev || step < 1) return fail(S2S_ERR_INVALID, "adam_multi: bad arguments");
@@ -1221,7 +1285,7 @@ int s2s_adam_multi(const s2s_adam_tensor* tensors_dev, const int* work_dev, int 
     h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
     h.grad_scale = (float)grad_scale;
     adam_multi_kernel<<<n_work, kAdamThreads, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors_dev,
-                                                                          (const int2*)work_dev, h);
+                                                                          (const int2*)work_dev, h, step_dev);
     LAUNCH_CHECK("adam_multi_kernel");
     return S2S_OK;
 }

@@ -458,7 +458,11 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
                                                                  int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
                                                                  __nv_bfloat16* __restrict__ y2, int ld_out,
                                                                  float drop_p, unsigned long long seed,
-                                                                 uint8_t* __restrict__ mask_out) {
+                                                                 uint8_t* __restrict__ mask_out,
+                                                                 const unsigned long long* __restrict__ seed_step) {
+    // seed_step (optional): a device-resident step counter mixed into the seed, so that a launch replayed from a CUDA
+    // graph (whose host-side seed argument is frozen at capture) still draws a fresh mask every training step
+    if (kDrop && seed_step != nullptr) seed += __ldg(seed_step) * 0x9E3779B97F4A7C15ull;
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;

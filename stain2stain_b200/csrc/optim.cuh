@@ -36,8 +36,17 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
     p -= (h.lr / h.bias_corr1) * (m / denom);
 }
 
+// step_dev (optional): the 1-based step count in device memory.  A launch replayed from a CUDA graph has its host
+// arguments frozen at capture; the bias corrections are then evaluated here from the live counter (in double, as the
+// host path and torch do).
 __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const AdamTensor* __restrict__ tensors,
-                                                                  const int2* __restrict__ work, AdamHyper h) {
+                                                                  const int2* __restrict__ work, AdamHyper h,
+                                                                  const long long* __restrict__ step_dev) {
+    if (step_dev != nullptr) {
+        const double t = (double)__ldg(step_dev);
+        h.bias_corr1 = (float)(1.0 - pow((double)h.beta1, t));
+        h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)h.beta2, t)));
+    }
     const int2 wi = work[blockIdx.x];
     const AdamTensor t = tensors[wi.x];
     const long long beg = (long long)wi.y * kAdamChunk;
@@ -62,6 +71,30 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const AdamTens
         for (long long i = vend + threadIdx.x; i < end; i += kAdamThreads) adam_update(t.p[i], t.g[i], t.m[i], t.v[i], h);
     } else {
         for (long long i = beg + threadIdx.x; i < end; i += kAdamThreads) adam_update(t.p[i], t.g[i], t.m[i], t.v[i], h);
+    }
+}
+
+// dst_i[0..n) = src_i[0..n) for MANY fp32 tensors in one launch (same table / work-list scheme): gathers the per-parameter
+// gradients into ONE flat buffer so that the data-parallel step needs a single all-reduce.
+struct CopyTensor {
+    const float* src;
+    float* dst;
+    long long n;
+};
+__global__ void __launch_bounds__(kAdamThreads) copy_multi_kernel(const CopyTensor* __restrict__ tensors,
+                                                                  const int2* __restrict__ work) {
+    const int2 wi = work[blockIdx.x];
+    const CopyTensor t = tensors[wi.x];
+    const long long beg = (long long)wi.y * kAdamChunk;
+    const long long end = min(t.n, beg + kAdamChunk);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(t.src) | reinterpret_cast<uintptr_t>(t.dst)) & 15) == 0;
+    if (aligned) {
+        const long long vend = beg + ((end - beg) & ~3LL);
+        for (long long i = beg + 4LL * threadIdx.x; i < vend; i += 4LL * kAdamThreads)
+            *reinterpret_cast<float4*>(t.dst + i) = __ldg(reinterpret_cast<const float4*>(t.src + i));
+        for (long long i = vend + threadIdx.x; i < end; i += kAdamThreads) t.dst[i] = t.src[i];
+    } else {
+        for (long long i = beg + threadIdx.x; i < end; i += kAdamThreads) t.dst[i] = t.src[i];
     }
 }
 

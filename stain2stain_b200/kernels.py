@@ -143,6 +143,10 @@ def pack_conv_weight_multi(jobs, table_cache: dict):
               "pack_conv_weight_multi")
 
 
+# device-resident step counter (int64 scalar tensor) mixed into every dropout seed while set: the graphed training step
+# (graphed.py) sets it during capture so that replayed launches draw a fresh mask every step
+DROPOUT_STEP_DEV: Optional[torch.Tensor] = None
+
 EPI_STATS = os.environ.get("S2S_EPI_STATS", "1") != "0"  # GroupNorm statistics from the producing conv's epilogue
 # inference: GroupNorm(+FiLM)+SiLU applied inside the consuming conv (s2s_conv_fwd_norm).  OFF by default: with two helper
 # warps per CTA the prologue does not hide behind the MMAs (measured) -- the separate norm-apply pass is faster.
@@ -317,9 +321,11 @@ def gn_apply(x, coef, y, c_off: int, silu: bool, drop_p: float = 0.0, seed: int 
     if y2 is not None:
         assert y2.shape == y.shape and y2.dtype == T16 and y2.is_contiguous()
     nbytes = (4.0 + (2.0 if y2 is not None else 0.0)) * x.numel()  # 1 read + 1 (or 2) writes of 2-byte elements
+    step_dev = DROPOUT_STEP_DEV if drop_p > 0 else None
     with _Prof("gn_apply_dropout" if drop_p > 0 else "gn_apply", 0.0, nbytes):
-        check(_L().s2s_gn_apply(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), ptr(y2), y.shape[3],
-                                int(silu), float(drop_p), int(seed), ptr(mask), x_fmt, y_fmt, stream_ptr()), "gn_apply")
+        check(_L().s2s_gn_apply_step(ptr(x), B, H * W, Cc, ptr(coef), coef.shape[1], c_off, ptr(y), ptr(y2), y.shape[3],
+                                     int(silu), float(drop_p), int(seed), ptr(step_dev), ptr(mask), x_fmt, y_fmt,
+                                     stream_ptr()), "gn_apply")
 
 
 def gn_bwd_reduce(x, g, coef, mr, red, c_off: int, silu: bool, drop_p: float = 0.0, seed: int = 0, x_fmt: int = ACT,
@@ -493,6 +499,70 @@ def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
     with _Prof("convert16", 0.0, 4.0 * x.numel()):
         check(_L().s2s_convert16(ptr(x), ptr(out), x.numel(), in_fmt, out_fmt, stream_ptr()), "convert16")
     return out
+
+
+# ---- embedding path: fp32 multi-GEMM (csrc/linear.cuh) -----------------------------------------------------
+def gemm_job(A, B, C, M: int, N: int, Kd: int, sam: int, sak: int, sbk: int, sbn: int, bias=None, add=None, C2=None):
+    """One job of `linear_multi`: C[m][n] = bias[n] + add[m][n] + sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ C2 = silu(C)).
+    All tensors fp32 CUDA; C (and C2, add) row-major with row length = their last dimension."""
+    for tns in (A, B, C, bias, add, C2):
+        assert tns is None or (tns.is_cuda and tns.dtype == torch.float32), "linear_multi takes fp32 CUDA tensors"
+    assert C.is_contiguous() and (C2 is None or (C2.is_contiguous() and C2.shape == C.shape))
+    assert add is None or add.is_contiguous()
+    ldc = C.shape[-1] if C.dim() > 1 else N
+    return (_lib.GemmJob(ptr(A), ptr(B), ptr(C), ptr(bias), ptr(add), ptr(C2), M, N, Kd, ldc,
+                         (add.shape[-1] if add is not None else 0), sam, sak, sbk, sbn), (A, B, C, bias, add, C2), 2.0 * M * N * Kd)
+
+
+def linear_multi(jobs):
+    """Run a list of `gemm_job`s in as few launches as the kernel-parameter table allows (36 jobs each)."""
+    if not jobs:
+        return
+    arr = (_lib.GemmJob * len(jobs))(*[j[0] for j in jobs])
+    with _Prof("linear_multi", sum(j[2] for j in jobs)):
+        check(_L().s2s_linear_multi(arr, len(jobs), stream_ptr()), "linear_multi")
+    LAUNCHES[0] += (len(jobs) - 1) // int(_L().s2s_linear_max_jobs())
+
+
+def linear_fwd_job(x, w, b, out, act_out=None, add=None):
+    """out = x @ w.T + b (+ add); act_out = silu(out).  x [M,K], w [N,K] (nn.Linear layout)."""
+    M, Kd = x.shape
+    N = w.shape[0]
+    return gemm_job(x, w, out, M, N, Kd, Kd, 1, 1, Kd, bias=b, add=add, C2=act_out)
+
+
+def linear_dx_job(dy, w, dx):
+    """dx = dy @ w.  dy [M,N], w [N,K] -> dx [M,K]."""
+    M, N = dy.shape
+    Kd = w.shape[1]
+    return gemm_job(dy, w, dx, M, Kd, N, N, 1, Kd, 1)
+
+
+def linear_dw_job(dy, x, dw):
+    """dw = dy.T @ x.  dy [M,N], x [M,K] -> dw [N,K] (the nn.Linear weight layout)."""
+    M, N = dy.shape
+    Kd = x.shape[1]
+    return gemm_job(dy, x, dw, N, Kd, M, 1, N, Kd, 1)
+
+
+def linear_db_job(dy, ones, db):
+    """db = dy.sum(0) as a 1-row GEMM with a vector of ones (rides in the same launch)."""
+    M, N = dy.shape
+    return gemm_job(ones, dy, db, 1, N, M, 0, 1, N, 1)
+
+
+def sum_parts_silu_bwd(parts, nparts: int, z, out):
+    n = out.numel()
+    assert parts.is_contiguous() and parts.numel() >= nparts * n and out.is_contiguous() and (z is None or z.is_contiguous())
+    check(_L().s2s_sum_parts_silu_bwd(ptr(parts), nparts, n, ptr(z), ptr(out), stream_ptr()), "sum_parts_silu_bwd")
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 1 and t.is_contiguous()
+    emb = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(_L().s2s_timestep_embedding(ptr(t), t.shape[0], dim, float(max_period), ptr(emb), stream_ptr()),
+          "timestep_embedding")
+    return emb
 
 
 # ---- multitask model (config M) kernels ---------------------------------------------------------------------------

@@ -717,6 +717,104 @@ def seg_loss(logits, target, num_classes: int, ignore_index: int = -100, dice_we
     return _SegLoss.apply(logits, target, num_classes, ignore_index, dice_weight, smooth)
 
 
+# ============================================================================================= embedding path (row a9)
+class _EmbedFilms(torch.autograd.Function):
+    """timestep embedding -> time_embed MLP (+ label embedding) -> SiLU -> ALL FiLM projections of the UNet's ResBlocks.
+
+    torchcfm evaluates `emb_layers = SiLU -> Linear(512, 2*Cout)` inside each of the 22 ResBlocks: 24 small
+    GEMMs forward, 66 backward.  The SiLU'd embedding is the same for every block, so all projections run here as ONE
+    multi-GEMM launch (fp32 FMA: the reference's arithmetic), and the backward of all of them -- dX partials, dW, db -- is
+    one more.  Outputs: one contiguous fp32 [B, 2*Cout_i] tensor per block (`film` of the fused ResBlock node)."""
+
+    @staticmethod
+    def forward(ctx, t, model_channels: int, label_vec, w0, b0, w1, b1, *film_params):
+        B = t.shape[0]
+        dev = t.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        temb = K.timestep_embedding(t.detach().float().contiguous(), model_channels)
+        ted = w0.shape[0]
+        h0, a0 = torch.empty((B, ted), **f32), torch.empty((B, ted), **f32)
+        K.linear_multi([K.linear_fwd_job(temb, w0.detach(), b0.detach(), h0, act_out=a0)])
+        e, ea = torch.empty((B, w1.shape[0]), **f32), torch.empty((B, w1.shape[0]), **f32)
+        lab = None if label_vec is None else label_vec.detach().float().contiguous()
+        K.linear_multi([K.linear_fwd_job(a0, w1.detach(), b1.detach(), e, act_out=ea, add=lab)])
+        films, jobs = [], []
+        for i in range(0, len(film_params), 2):
+            w, b = film_params[i], film_params[i + 1]
+            f = torch.empty((B, w.shape[0]), **f32)
+            films.append(f)
+            jobs.append(K.linear_fwd_job(ea, w.detach(), b.detach(), f))
+        K.linear_multi(jobs)
+        ctx.has_label = label_vec is not None
+        ctx.save_for_backward(temb, h0, a0, e, ea, w0, w1, *film_params[0::2])
+        return tuple(films)
+
+    @staticmethod
+    def backward(ctx, *dfilms):
+        temb, h0, a0, e, ea, w0, w1, *fws = ctx.saved_tensors
+        B, ted = ea.shape
+        dev = ea.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        ones = torch.ones(B, **f32)
+        present = [i for i, d in enumerate(dfilms) if d is not None]
+        parts = torch.empty((max(1, len(present)), B, ted), **f32)
+        grads_f = [None] * (2 * len(fws))
+        jobs = []
+        for slot, i in enumerate(present):
+            d = dfilms[i].float().contiguous()
+            w = fws[i]
+            dw, db = torch.empty_like(w, dtype=torch.float32), torch.empty(w.shape[0], **f32)
+            grads_f[2 * i], grads_f[2 * i + 1] = dw, db
+            jobs += [K.linear_dx_job(d, w.detach(), parts[slot]), K.linear_dw_job(d, ea, dw), K.linear_db_job(d, ones, db)]
+        K.linear_multi(jobs)
+        d_e = torch.empty((B, ted), **f32)
+        if present:
+            K.sum_parts_silu_bwd(parts, len(present), e, d_e)
+        else:
+            d_e.zero_()
+        d_a0 = torch.empty((B, w1.shape[1]), **f32)
+        d_w1, d_b1 = torch.empty_like(w1, dtype=torch.float32), torch.empty(w1.shape[0], **f32)
+        K.linear_multi([K.linear_dx_job(d_e, w1.detach(), d_a0), K.linear_dw_job(d_e, a0, d_w1), K.linear_db_job(d_e, ones, d_b1)])
+        d_h0 = torch.empty_like(d_a0)
+        K.sum_parts_silu_bwd(d_a0, 1, h0, d_h0)
+        d_w0, d_b0 = torch.empty_like(w0, dtype=torch.float32), torch.empty(w0.shape[0], **f32)
+        K.linear_multi([K.linear_dw_job(d_h0, temb, d_w0), K.linear_db_job(d_h0, ones, d_b0)])
+        return (None, None, d_e if ctx.has_label else None, d_w0, d_b0, d_w1, d_b1, *grads_f)
+
+
+def embed_films(t, model_channels: int, label_vec, time_embed_params, film_params):
+    """-> list of FiLM tensors, one per (weight, bias) pair of `film_params` (ResBlock execution order)."""
+    flat = [p for wb in film_params for p in wb]
+    return list(_EmbedFilms.apply(t, int(model_channels), label_vec, *time_embed_params, *flat))
+
+
+class _FilmOne(torch.autograd.Function):
+    """FiLM projection of ONE block from an already SiLU'd embedding (blocks used outside a UNet: tests, custom nets)."""
+
+    @staticmethod
+    def forward(ctx, emb_act, w, b):
+        ea = emb_act.detach().float().contiguous()
+        f = torch.empty((ea.shape[0], w.shape[0]), dtype=torch.float32, device=ea.device)
+        K.linear_multi([K.linear_fwd_job(ea, w.detach(), b.detach(), f)])
+        ctx.save_for_backward(ea, w)
+        ctx.in_dtype = emb_act.dtype
+        return f
+
+    @staticmethod
+    def backward(ctx, d):
+        ea, w = ctx.saved_tensors
+        d = d.float().contiguous()
+        f32 = dict(dtype=torch.float32, device=d.device)
+        d_ea, d_w, d_b = torch.empty_like(ea), torch.empty_like(w, dtype=torch.float32), torch.empty(w.shape[0], **f32)
+        K.linear_multi([K.linear_dx_job(d, w.detach(), d_ea), K.linear_dw_job(d, ea, d_w),
+                        K.linear_db_job(d, torch.ones(d.shape[0], **f32), d_b)])
+        return d_ea.to(ctx.in_dtype), d_w, d_b
+
+
+def film_one(emb_act, w, b):
+    return _FilmOne.apply(emb_act, w, b)
+
+
 # ============================================================================================= fused ResBlock
 @dataclass
 class ResBlockCfg:
@@ -753,9 +851,9 @@ class _ResBlockFn(torch.autograd.Function):
     def forward(ctx, cfg: ResBlockCfg, n_src: int, drop_p: float, seed: int, src_stats, stats_box, grad_mode: bool,
                 *tensors):
         srcs = tensors[:n_src]
-        emb_act = tensors[n_src]
-        gn1w, gn1b, c1w, c1b, ew, eb, gn2w, gn2b, c2w, c2b = tensors[n_src + 1:n_src + 11]
-        skip = tensors[n_src + 11:]
+        film = tensors[n_src].detach()  # fp32 [B, 2*Cout] = Linear(SiLU(emb)) of this block (ops.embed_films)
+        gn1w, gn1b, c1w, c1b, gn2w, gn2b, c2w, c2b = tensors[n_src + 1:n_src + 9]
+        skip = tensors[n_src + 9:]
         B, H, W, _ = srcs[0].shape
         ctot = sum(s.shape[3] for s in srcs)
         cout = c1w.shape[0]
@@ -794,8 +892,8 @@ class _ResBlockFn(torch.autograd.Function):
                 off += s.shape[3]
             h, h_stats = K.conv_fwd([(a1, 9, 1)], cfg.plan1.packed_fwd([c1w]), cout, H, W, bias=c1b.detach(),
                                     want_stats=True)
-        # ---- FiLM from the (already SiLU'd) embedding, norm 2 (+SiLU, dropout)
-        film = torch.addmm(eb.detach(), emb_act.detach().float(), ew.detach().t()).contiguous()
+        # ---- norm 2 with FiLM (+SiLU, dropout)
+        assert film.dtype == torch.float32 and film.is_contiguous() and tuple(film.shape) == (B, 2 * cout)
         if h_stats is not None:
             coef2, mr2 = K.gn_coef_parts([h_stats], gn2w.detach(), gn2b.detach(), film, H * W, cfg.groups, cfg.eps)
             part2 = h_stats
@@ -833,8 +931,8 @@ class _ResBlockFn(torch.autograd.Function):
             ctx.cfg, ctx.n_src, ctx.drop = cfg, n_src, (drop_p, seed)
             ctx.dual = dual
             ctx.mask = mask  # uint8 keep bits of the dropout (1 bit / element), read by the two norm-backward passes
-            ctx.save_for_backward(*srcs, emb_act, h, a1g if dual else a1, a2g if dual else a2, coef1, mr1, coef2, mr2,
-                                  film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, sum_h, *skip[:1])
+            ctx.save_for_backward(*srcs, h, a1g if dual else a1, a2g if dual else a2, coef1, mr1, coef2, mr2,
+                                  film, gn1w, gn1b, c1w, gn2w, gn2b, c2w, sum_h, *skip[:1])
         return out
 
     @staticmethod
@@ -843,9 +941,8 @@ class _ResBlockFn(torch.autograd.Function):
         drop_p, seed = ctx.drop
         sv = ctx.saved_tensors
         srcs = sv[:n_src]
-        emb_act, h, a1s, a2s, coef1, mr1, coef2, mr2, film, gn1w, gn1b, c1w, ew, gn2w, gn2b, c2w, sum_h = \
-            sv[n_src:n_src + 17]
-        sw = sv[n_src + 17] if cfg.has_skip_conv else None
+        h, a1s, a2s, coef1, mr1, coef2, mr2, film, gn1w, gn1b, c1w, gn2w, gn2b, c2w, sum_h = sv[n_src:n_src + 15]
+        sw = sv[n_src + 15] if cfg.has_skip_conv else None
         a1g = a1s if ctx.dual else K.convert16(a1s, K.ACT, K.GRAD)
         a2g = a2s if ctx.dual else K.convert16(a2s, K.ACT, K.GRAD)
         d_out = d_out.contiguous()
@@ -877,12 +974,7 @@ class _ResBlockFn(torch.autograd.Function):
         pqr2, dfilm, red2f = K.gn_bwd_coef(red2, mr2, gn2w, gn2b, film, H * W, d_gn2w, d_gn2b, True, want_red=True)
         d_h = torch.empty_like(h)
         K.gn_bwd_apply(h, d_a2, coef2, pqr2, 0, None, d_h, True, drop_p, seed, mask=ctx.mask)
-        # ---- FiLM linear
-        emb32 = emb_act.float()
-        d_emb = dfilm @ ew.float()
-        d_ew = dfilm.t() @ emb32
-        d_eb = dfilm.sum(dim=0)
-        # ---- conv 1
+        # ---- conv 1  (dfilm goes back to ops.embed_films, which runs every block's FiLM backward as one multi-GEMM)
         d_c1w = torch.empty_like(c1w, dtype=torch.float32)
         _wgrad_to(d_h, a1g, 9, 1, d_c1w.view(cout, ctot, -1), 0)
         # bias gradient of conv 1 = sum over pixels of d_h = sum_b (P * sum dz + Q * sum h + HW * R): closed form from
@@ -911,15 +1003,16 @@ class _ResBlockFn(torch.autograd.Function):
             K.gn_bwd_apply(s, d_a1, coef1, pqr1, off, d_skip[i], dx, True)
             d_srcs.append(dx)
             off += s.shape[3]
-        grads = [None, None, None, None, None, None, None, *d_srcs, d_emb.to(emb_act.dtype), d_gn1w, d_gn1b, d_c1w, d_b1, d_ew, d_eb,
+        grads = [None, None, None, None, None, None, None, *d_srcs, dfilm, d_gn1w, d_gn1b, d_c1w, d_b1,
                  d_gn2w, d_gn2b, d_c2w, d_b2]
         if cfg.has_skip_conv:
             grads += [d_sw, d_b2]
         return tuple(grads)
 
 
-def res_block(cfg: ResBlockCfg, srcs, emb_act, params, drop_p: float, seed: int):
+def res_block(cfg: ResBlockCfg, srcs, film, params, drop_p: float, seed: int):
+    """film: fp32 [B, 2*Cout] FiLM tensor of this block; params: gn1 w/b, conv1 w/b, gn2 w/b, conv2 w/b (+ skip w/b)."""
     box = []
     src_stats = tuple(stats_of(t) for t in srcs)
     return _tag(_ResBlockFn.apply(cfg, len(srcs), float(drop_p), int(seed), src_stats, box, torch.is_grad_enabled(),
-                                  *srcs, emb_act, *params), box)
+                                  *srcs, film, *params), box)

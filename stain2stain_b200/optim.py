@@ -10,7 +10,7 @@ CUDA fp32 parameters only; anything else raises (no CPU fallback).
 from __future__ import annotations
 
 import ctypes as C
-from typing import List
+from typing import Dict, List, Optional
 
 import torch
 
@@ -33,11 +33,14 @@ class FusedAdam(torch.optim.Optimizer):
         self.grad_scale = float(grad_scale)
         self._tables = {}  # group index -> (signature, device tensor table, device work list, n_work, keep-alive)
 
-    def _table(self, gi: int, ps: List[torch.Tensor]):
+    def _table(self, gi, ps: List[torch.Tensor], gs: Optional[List[torch.Tensor]] = None):
+        """Device pointer table of one group; `gs` = the gradient tensors (default: each parameter's `.grad`)."""
+        if gs is None:
+            gs = [p.grad for p in ps]
         # every pointer the device table holds is part of the signature: `load_state_dict` / a state reset swaps the moment
         # tensors while parameters and gradients stay where they are
-        sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
-                     self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
+        sig = tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p, g in zip(ps, gs))
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == sig:
             return hit
@@ -45,9 +48,9 @@ class FusedAdam(torch.optim.Optimizer):
         chunk = _lib.load().s2s_adam_chunk()
         arr = (_AdamTensor * len(ps))()
         work = []
-        for i, p in enumerate(ps):
+        for i, (p, g) in enumerate(zip(ps, gs)):
             st = self.state[p]
-            arr[i] = _AdamTensor(p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+            arr[i] = _AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                  p.numel())
             work.extend((i, c) for c in range((p.numel() + chunk - 1) // chunk))
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().pin_memory()
@@ -70,6 +73,50 @@ class FusedAdam(torch.optim.Optimizer):
         if hasattr(self, "_tables"):
             self._tables.clear()
 
+    def _init_state(self, p):
+        st = self.state[p]
+        if not st:
+            st["step"] = torch.zeros((), dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    @torch.no_grad()
+    def step_on_device_counter(self, step_dev: torch.Tensor, grads: Optional[Dict[torch.Tensor, torch.Tensor]] = None,
+                               grad_scale: Optional[float] = None):
+        """The same update with the step count read from DEVICE memory (`step_dev`: int64 scalar, already incremented),
+        for launches captured in a CUDA graph (graphed.py): nothing host-side changes between replays, so the bias
+        corrections are evaluated on the device.  `grads`: parameter -> gradient tensor to read instead of `.grad` (views
+        of the flat all-reduced buffer).  The host-side `state[p]["step"]` is NOT advanced here; the caller accounts for it
+        (`advance_steps`)."""
+        assert step_dev.is_cuda and step_dev.dtype == torch.int64 and step_dev.numel() == 1
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if (p in grads if grads is not None else p.grad is not None)]
+            if not ps:
+                continue
+            gs = [grads[p] if grads is not None else p.grad for p in ps]
+            for p, g in zip(ps, gs):
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise _lib.S2SError("FusedAdam needs contiguous fp32 CUDA parameters (no CPU fallback)")
+                if g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != p.numel():
+                    raise _lib.S2SError("FusedAdam needs dense contiguous fp32 gradients")
+                self._init_state(p)
+            _, t_dev, w_dev, n_work, _ = self._table(("dev", gi, grads is not None), ps, gs)
+            b1, b2 = group["betas"]
+            with K._Prof("adam_multi", 0.0, 28.0 * sum(p.numel() for p in ps)):
+                K.check(_lib.load().s2s_adam_multi_step(t_dev.data_ptr(), w_dev.data_ptr(), n_work, float(group["lr"]),
+                                                        float(b1), float(b2), float(group["eps"]),
+                                                        float(group["weight_decay"]), 1, step_dev.data_ptr(),
+                                                        self.grad_scale if grad_scale is None else float(grad_scale),
+                                                        _lib.stream_ptr()), "adam_multi_step")
+            torch.autograd.graph.increment_version(ps)
+
+    def advance_steps(self, n: int):
+        """Account on the host for `n` updates that ran from a CUDA graph (keeps `state_dict()` = torch.optim.Adam's)."""
+        for st in self.state.values():
+            if "step" in st:
+                st["step"] += n
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -86,11 +133,7 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad
                 if g.is_sparse or g.dtype != torch.float32 or not g.is_contiguous():
                     raise _lib.S2SError("FusedAdam needs dense contiguous fp32 gradients")
-                st = self.state[p]
-                if not st:
-                    st["step"] = torch.zeros((), dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                self._init_state(p)
             steps = {int(self.state[p]["step"]) for p in ps}
             if len(steps) != 1:
                 raise _lib.S2SError("FusedAdam: parameters of one group must share a step count")

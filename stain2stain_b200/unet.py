@@ -156,7 +156,9 @@ class ResBlock(TimestepBlock):
             self._skip_plans[key] = ConvPlan(tuple(segs), self.out_channels)
         return self._skip_plans[key]
 
-    def forward(self, srcs, emb_act):
+    def forward(self, srcs, emb):
+        """emb: the UNet's FiLM table {ResBlock: fp32 [B, 2*Cout]} (all blocks' projections computed in one launch by
+        ops.embed_films), or -- for a block used on its own -- the SiLU'd embedding tensor [B, emb_channels]."""
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
         gn2, conv2 = self.out_layers[0], self.out_layers[3]
         lin = self.emb_layers[1]
@@ -171,11 +173,11 @@ class ResBlock(TimestepBlock):
                 off += w
             cfg = self._cfgs[widths] = ops.ResBlockCfg(self._plan1, self._plan2_skip(widths) if has_skip else self._plan2,
                                                        has_skip, plan1_multi=ConvPlan(tuple(segs), self.out_channels))
-        params = [gn1.weight, gn1.bias, conv1.weight, conv1.bias, lin.weight, lin.bias, gn2.weight, gn2.bias,
-                  conv2.weight, conv2.bias]
+        params = [gn1.weight, gn1.bias, conv1.weight, conv1.bias, gn2.weight, gn2.bias, conv2.weight, conv2.bias]
         if has_skip:
             params += [self.skip_connection.weight, self.skip_connection.bias]
-        return ops.res_block(cfg, list(srcs), emb_act, params, p, _next_dropout_seed() if p > 0 else 0)
+        film = emb[self] if isinstance(emb, dict) else ops.film_one(emb, lin.weight, lin.bias)
+        return ops.res_block(cfg, list(srcs), film, params, p, _next_dropout_seed() if p > 0 else 0)
 
 
 class AttentionBlock(nn.Module):
@@ -294,11 +296,23 @@ class RawUNetModel(nn.Module):
             t = t[:, 0]
         if t.dim() == 0:
             t = t.repeat(x.shape[0])
-        emb = self.time_embed(timestep_embedding(t.to(x.device), self.model_channels))
+        label_vec = None
         if self.num_classes is not None:
             assert y.shape == (x.shape[0],)
-            emb = emb + self.label_emb(y)
-        return F.silu(emb)  # every ResBlock's emb_layers starts with SiLU: apply it once
+            label_vec = self.label_emb(y)
+        # every ResBlock's emb_layers starts with SiLU: it is applied once, and all FiLM projections run in one launch
+        blocks = self._res_blocks()
+        te = self.time_embed
+        films = ops.embed_films(t.to(x.device).float().contiguous(), self.model_channels, label_vec,
+                                [te[0].weight, te[0].bias, te[2].weight, te[2].bias],
+                                [(b.emb_layers[1].weight, b.emb_layers[1].bias) for b in blocks])
+        return dict(zip(blocks, films))
+
+    def _res_blocks(self):
+        """The ResBlocks in execution order (input, middle, output blocks)."""
+        if getattr(self, "_res_block_list", None) is None:
+            object.__setattr__(self, "_res_block_list", [m for m in self.modules() if isinstance(m, ResBlock)])
+        return self._res_block_list
 
     def _trunk(self, h, emb_act):
         hs = [h]
