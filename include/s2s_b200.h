@@ -304,6 +304,24 @@ int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C,
                      const double* sums, float smooth, float w_dice, float w_ce, const float* gscale, float* dlogits,
                      void* stream);
 
+/* ---- attention core (rows a14, f3) ----------------------------------------------------------------------------------- */
+
+/* torchcfm AttentionBlock's QKVAttentionLegacy / QKVAttention: per (sample, head)
+ *   a = softmax_fp32(q k^T / sqrt(ch)) v        over T = H*W tokens
+ * reading q / k / v in place from the qkv 1x1 conv's NHWC output qkv [B][T][3*heads*ch] (new_order = 0: channel =
+ * head*3*ch + {q,k,v}*ch + c -- the legacy interleave every reference config uses; new_order = 1: {q,k,v}*C + head*ch + c)
+ * and writing out [B][T][heads*ch] (channel head*ch + c).  lse (may be NULL for inference): fp32 [B*heads][T] log2-domain
+ * logsumexp kept for the backward.  Flash-style: the T x T matrix never leaves registers; fp32 softmax statistics.
+ * Backward: d_qkv [B][T][3*heads*ch] (g_fmt) from d_out [B][T][heads*ch] (g_fmt), the saved qkv / out (a_fmt) and lse;
+ * dvec: fp32 [B*heads][T] scratch.  Three launches (row sums, dK/dV per key block, dQ per query block); no atomics.
+ * ch must be 32 or 64 (s2s_attn_supported).  Replaces: the reshape / split / einsum / softmax / einsum chain of
+ * QKVAttentionLegacy.forward and its autograd. */
+int s2s_attn_supported(int ch);
+int s2s_attn_fwd(const void* qkv, int B, int T, int heads, int ch, int new_order, void* out, float* lse, int a_fmt,
+                 void* stream);
+int s2s_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* dvec, void* d_qkv, int B, int T,
+                 int heads, int ch, int new_order, int a_fmt, int g_fmt, void* stream);
+
 /* ---- embedding path (row a9): timestep embedding, time_embed MLP, label embedding, the 22 FiLM linears -------------- */
 
 /* One fp32 GEMM  C[m][n] = bias[n] + add[m][n] + sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]  (element strides; bias / add

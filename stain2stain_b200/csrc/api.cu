@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "conv_igemm.cuh"
+#include "attention.cuh"
 #include "elementwise.cuh"
 #include "linear.cuh"
 #include "multitask.cuh"
@@ -1211,6 +1212,59 @@ int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C,
     seg_loss_bwd_kernel<<<ew_grid((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(
         logits, target, B, C, HW, ignore_index, sums, smooth, w_dice, w_ce, gscale, dlogits);
     LAUNCH_CHECK("seg_loss_bwd_kernel");
+    return S2S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ attention core
+static int attn_params(AttnParams* p, int B, int T, int heads, int ch, int new_order) {
+    if (B < 1 || T < 1 || heads < 1 || (ch != 32 && ch != 64))
+        return fail(S2S_ERR_INVALID, "attention: head channels = %d unsupported (32 or 64), B=%d T=%d heads=%d", ch, B, T, heads);
+    memset(p, 0, sizeof(*p));
+    p->B = B; p->T = T; p->heads = heads; p->C = heads * ch; p->ld = 3 * heads * ch;
+    p->head_stride = new_order ? ch : 3 * ch;
+    p->which_stride = new_order ? heads * ch : ch;
+    p->scale = 1.0f / sqrtf((float)ch);
+    p->scale_log2 = p->scale * 1.4426950408889634f;
+    return S2S_OK;
+}
+int s2s_attn_supported(int ch) { return (ch == 32 || ch == 64) ? 1 : 0; }
+
+int s2s_attn_fwd(const void* qkv, int B, int T, int heads, int ch, int new_order, void* out, float* lse, int a_fmt,
+                 void* stream) {
+    if (!qkv || !out) return fail(S2S_ERR_INVALID, "attn_fwd: null argument");
+    AttnParams p;
+    int rc = attn_params(&p, B, T, heads, ch, new_order);
+    if (rc) return rc;
+    p.qkv = (const uint16_t*)qkv; p.out = (uint16_t*)out; p.lse = lse;
+    const dim3 grid((T + kAttnBlock - 1) / kAttnBlock, B * heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ch == 32) S2S_FMT(a_fmt, AF, (attn_fwd_kernel<32, AF><<<grid, kAttnThreads, 0, st>>>(p)));
+    else S2S_FMT(a_fmt, AF, (attn_fwd_kernel<64, AF><<<grid, kAttnThreads, 0, st>>>(p)));
+    LAUNCH_CHECK("attn_fwd_kernel");
+    return S2S_OK;
+}
+
+int s2s_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, float* dvec, void* d_qkv, int B, int T,
+                 int heads, int ch, int new_order, int a_fmt, int g_fmt, void* stream) {
+    if (!qkv || !out || !d_out || !lse || !dvec || !d_qkv) return fail(S2S_ERR_INVALID, "attn_bwd: null argument");
+    AttnParams p;
+    int rc = attn_params(&p, B, T, heads, ch, new_order);
+    if (rc) return rc;
+    p.qkv = (const uint16_t*)qkv; p.o_fwd = (const uint16_t*)out; p.d_out = (const uint16_t*)d_out;
+    p.lse = const_cast<float*>(lse); p.dvec = dvec; p.d_qkv = (uint16_t*)d_qkv;
+    const dim3 grid((T + kAttnBlock - 1) / kAttnBlock, B * heads);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int prep_grid = ew_grid((long long)B * heads * T);
+#define S2S_ATTN_BWD(DV)                                                                                   \
+    S2S_FMT(a_fmt, AF, S2S_FMT(g_fmt, GF, {                                                                \
+        attn_bwd_prep_kernel<DV, AF, GF><<<prep_grid, kEwThreads, 0, st>>>(p);                             \
+        attn_bwd_kv_kernel<DV, AF, GF><<<grid, kAttnThreads, 0, st>>>(p);                                  \
+        attn_bwd_q_kernel<DV, AF, GF><<<grid, kAttnThreads, 0, st>>>(p);                                   \
+    }))
+    if (ch == 32) S2S_ATTN_BWD(32);
+    else S2S_ATTN_BWD(64);
+#undef S2S_ATTN_BWD
+    LAUNCH_CHECK("attn_bwd kernels");
     return S2S_OK;
 }
 

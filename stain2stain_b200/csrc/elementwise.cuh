@@ -567,7 +567,7 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
     cvt8_in_t<GF>(gu, dz);
     if (kDrop) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dz[e] = ((keep >> e) & 1u) ? dz[e] * keep_scale : 0.f;
+        for (int e = 0; e < 8; ++e) dz[e] *= (keep & (1u << e)) ? keep_scale : 0.f;  // ISETP + SEL + FMUL per element
     }
     if constexpr (kAct == kActSilu) {
         if constexpr (XF == kFmtF16) {
@@ -617,12 +617,15 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     float s1[8], s2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-    auto body = [&](const uint4& xu, const uint4& gu, int p) {
-        uint32_t m = 0xffu;
-        if (kDrop) {
-            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3);
-            m = mask_in != nullptr ? (uint32_t)__ldg(mask_in + e8) : dropout_keep8(seed, e8, thresh);
-        }
+    // stored keep bits: the byte is fetched TOGETHER with the x / g vectors of its pixel (a dependent 1-byte load inside
+    // the body exposed a full memory latency per pixel: the dropout variants ran at 0.53 of HBM peak, issue-stalled)
+    const bool stored = kDrop && mask_in != nullptr;
+    auto mask_at = [&](int p) -> uint32_t {
+        return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
+    };
+    auto body = [&](const uint4& xu, const uint4& gu, uint32_t m, int p) {
+        if (kDrop && !stored)
+            m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8];
         gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
         // optional side product: x in bf16 (the weight-gradient operand of a 1x1 skip conv over the raw block input) --
@@ -638,16 +641,19 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     int p = p0 + prow;
     for (; p + (U - 1) * pstep < p1; p += U * pstep) {
         uint4 xu[U], gu[U];
+        uint32_t mk[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
             xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
             gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
+            mk[i] = mask_at(p + i * pstep);
         }
 #pragma unroll
-        for (int i = 0; i < U; ++i) body(xu[i], gu[i], p + i * pstep);
+        for (int i = 0; i < U; ++i) body(xu[i], gu[i], mk[i], p + i * pstep);
     }
     for (; p < p1; p += pstep)
-        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)), p);
+        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)),
+             mask_at(p), p);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         red[threadIdx.x][e] = s1[e];
@@ -764,12 +770,13 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
     const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
                                        (unsigned long long)((c_off >> 3) + slot);
-    auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, int p) {
-        uint32_t m = 0xffu;
-        if (kDrop) {
-            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3);
-            m = mask_in != nullptr ? (uint32_t)__ldg(mask_in + e8) : dropout_keep8(seed, e8, thresh);
-        }
+    const bool stored = kDrop && mask_in != nullptr;  // keep bits fetched together with the pixel's vectors (see gn_bwd_reduce)
+    auto mask_at = [&](int p) -> uint32_t {
+        return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
+    };
+    auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, uint32_t m, int p) {
+        if (kDrop && !stored)
+            m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8], o[8];
         gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
 #pragma unroll
@@ -785,18 +792,20 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
     int p = p0 + prow;
     for (; p + (U - 1) * pstep < p1; p += U * pstep) {
         uint4 xu[U], gu[U], au[U];
+        uint32_t mk[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
             xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
             gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
             au[i] = kAdd ? ldg_stream(as + (size_t)(p + i * pstep) * vpp + slot) : make_uint4(0, 0, 0, 0);
+            mk[i] = mask_at(p + i * pstep);
         }
 #pragma unroll
-        for (int i = 0; i < U; ++i) body(xu[i], gu[i], au[i], p + i * pstep);
+        for (int i = 0; i < U; ++i) body(xu[i], gu[i], au[i], mk[i], p + i * pstep);
     }
     for (; p < p1; p += pstep)
         body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)),
-             kAdd ? ldg_stream(as + (size_t)p * vpp + slot) : make_uint4(0, 0, 0, 0), p);
+             kAdd ? ldg_stream(as + (size_t)p * vpp + slot) : make_uint4(0, 0, 0, 0), mask_at(p), p);
 }
 
 // ------------------------------------------------------------------------------------------------ resampling

@@ -501,6 +501,44 @@ def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
     return out
 
 
+# ---- attention core (csrc/attention.cuh) ---------------------------------------------------------------
+def attn_supported(ch: int) -> bool:
+    return bool(_L().s2s_attn_supported(int(ch)))
+
+
+def attn_fwd(qkv: torch.Tensor, heads: int, new_order: bool, want_lse: bool, fmt: int = ACT):
+    """qkv: 16-bit NHWC [B,H,W,3C] (the qkv conv's output) -> (a [B,H,W,C], lse fp32 [B*heads, T] or None)."""
+    _nhwc_check(qkv)
+    B, H, W, C3 = qkv.shape
+    Cc, T = C3 // 3, H * W
+    ch = Cc // heads
+    out = torch.empty((B, H, W, Cc), dtype=T16, device=qkv.device)
+    lse = torch.empty((B * heads, T), dtype=torch.float32, device=qkv.device) if want_lse else None
+    with _Prof("attention", 4.0 * B * heads * T * T * ch):
+        check(_L().s2s_attn_fwd(ptr(qkv), B, T, heads, ch, int(bool(new_order)), ptr(out), ptr(lse), fmt, stream_ptr()),
+              "attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, d_out, lse, heads: int, new_order: bool, a_fmt: int = ACT, g_fmt: int = GRAD):
+    """-> d_qkv 16-bit NHWC [B,H,W,3C] (gradient format)."""
+    _nhwc_check(qkv)
+    _nhwc_check(out)
+    _nhwc_check(d_out)
+    B, H, W, C3 = qkv.shape
+    Cc, T = C3 // 3, H * W
+    ch = Cc // heads
+    assert tuple(out.shape) == (B, H, W, Cc) and tuple(d_out.shape) == (B, H, W, Cc)
+    assert lse.dtype == torch.float32 and lse.numel() == B * heads * T and lse.is_contiguous()
+    d_qkv = torch.empty_like(qkv)
+    dvec = torch.empty_like(lse)
+    with _Prof("attention_bwd", 14.0 * B * heads * T * T * ch):  # 7 GEMMs of 2*T*T*ch (S and dP are recomputed per kernel)
+        check(_L().s2s_attn_bwd(ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(dvec), ptr(d_qkv), B, T, heads, ch,
+                                int(bool(new_order)), a_fmt, g_fmt, stream_ptr()), "attn_bwd")
+        LAUNCHES[0] += 2
+    return d_qkv
+
+
 # ---- embedding path: fp32 multi-GEMM (csrc/linear.cuh; SURVEY row a9) -----------------------------------------------------
 def gemm_job(A, B, C, M: int, N: int, Kd: int, sam: int, sak: int, sbk: int, sbn: int, bias=None, add=None, C2=None):
     """One job of `linear_multi`: C[m][n] = bias[n] + add[m][n] + sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ C2 = silu(C)).

@@ -717,6 +717,30 @@ def seg_loss(logits, target, num_classes: int, ignore_index: int = -100, dice_we
     return _SegLoss.apply(logits, target, num_classes, ignore_index, dice_weight, smooth)
 
 
+# ============================================================================================= attention core (rows a14, f3)
+class _Attention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(ch)) v per (sample, head) on the qkv conv's NHWC output (csrc/attention.cuh)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads: int, new_order: bool, grad_mode: bool):
+        train = grad_mode and ctx.needs_input_grad[0]  # (inside forward() grad mode is always off: the caller passes it)
+        out, lse = K.attn_fwd(qkv, heads, new_order, want_lse=train)
+        ctx.cfg = (heads, new_order)
+        if train:
+            ctx.save_for_backward(qkv, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, lse = ctx.saved_tensors
+        heads, new_order = ctx.cfg
+        return K.attn_bwd(qkv, out, d_out.contiguous(), lse, heads, new_order), None, None, None
+
+
+def attention(qkv, heads: int, new_order: bool = False):
+    return _Attention.apply(qkv, int(heads), bool(new_order), torch.is_grad_enabled())
+
+
 # ============================================================================================= embedding path (row a9)
 class _EmbedFilms(torch.autograd.Function):
     """timestep embedding -> time_embed MLP (+ label embedding) -> SiLU -> ALL FiLM projections of the UNet's ResBlocks.

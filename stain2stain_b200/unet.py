@@ -182,7 +182,9 @@ class ResBlock(TimestepBlock):
 
 class AttentionBlock(nn.Module):
     """GN -> qkv 1x1 -> multi-head softmax attention over H*W tokens -> proj 1x1 (+x).  qkv/proj are tcgen05 GEMMs; the
-    (T x T) softmax core is 0.5 % of the model's FLOPs and goes through torch SDPA (library flash kernel)."""
+    (T x T) softmax core is this package's flash-style kernel (csrc/attention.cuh) reading q/k/v in place from the qkv conv's
+    output, for 32 or 64 channels per head (every reference config: 32).  Other head sizes -- only reachable with
+    constructor arguments no reference config uses -- go through torch SDPA."""
 
     def __init__(self, channels, num_heads=1, num_head_channels=-1, use_new_attention_order=False):
         super().__init__()
@@ -206,6 +208,9 @@ class AttentionBlock(nn.Module):
         ch = Cc // nh
         a = ops.group_norm_act([x], self.norm.weight, self.norm.bias, None, silu=False)
         qkv = ops.fused_conv(self._plan_qkv, [a], [self.qkv.weight], [self.qkv.bias])
+        if ops.K.attn_supported(ch):
+            o = ops.attention(qkv, nh, self.new_order)
+            return ops.fused_conv(self._plan_proj, [o], [self.proj_out.weight], [self.proj_out.bias], residual=x)
         qkv = ops.act_to_bf16(qkv)
         if self.new_order:
             q, k, v = qkv.view(B, T, 3, nh, ch).unbind(2)
