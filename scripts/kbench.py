@@ -119,6 +119,21 @@ def bench_gn(B, iters, out):
         del x, g, y, dx, xb
 
 
+def bench_attn(B, iters, out):
+    for heads, ch, H in [(16, 32, 32), (4, 32, 16)]:
+        C = heads * ch
+        qkv = rnd16((B, H, H, 3 * C), K.ACT)
+        d_out = rnd16((B, H, H, C), K.GRAD)
+        o, lse = K.attn_fwd(qkv, heads, False, True)
+        T = H * H
+        ms = timeit(lambda: K.attn_fwd(qkv, heads, False, True), iters)
+        out.append(dict(kernel="attn_fwd", shape=f"h{heads}x{ch} T{T} B{B}", ms=ms, tflops=4.0 * B * heads * T * T * ch / ms / 1e9))
+        print(out[-1], flush=True)
+        ms = timeit(lambda: K.attn_bwd(qkv, o, d_out, lse, heads, False), iters)
+        out.append(dict(kernel="attn_bwd", shape=f"h{heads}x{ch} T{T} B{B}", ms=ms, tflops=14.0 * B * heads * T * T * ch / ms / 1e9))
+        print(out[-1], flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="*", default=["conv", "wgrad", "gn"])
@@ -136,6 +151,8 @@ def main():
         bench_wgrad(a.batch, a.iters, out)
     if "gn" in a.what:
         bench_gn(a.batch, a.iters, out)
+    if "attn" in a.what:
+        bench_attn(a.batch, a.iters, out)
     if a.json:
         with open(a.json, "w") as f:
             json.dump(out, f, indent=1)

@@ -160,6 +160,19 @@ constexpr size_t kSmemBudget = 227 * 1024;
             __VA_ARGS__;                          \
         }                                         \
     } while (0)
+#define S2S_DROP(drop_p, mask, NAME, ...)         \
+    do {                                          \
+        if (!((drop_p) > 0.f)) {                  \
+            constexpr int NAME = 0;               \
+            __VA_ARGS__;                          \
+        } else if ((mask) == nullptr) {           \
+            constexpr int NAME = 1;               \
+            __VA_ARGS__;                          \
+        } else {                                  \
+            constexpr int NAME = 2;               \
+            __VA_ARGS__;                          \
+        }                                         \
+    } while (0)
 #define S2S_ACT(act, NAME, ...)                   \
     do {                                          \
         if ((act) == 1) {                         \
@@ -969,7 +982,7 @@ int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
             (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in,
@@ -1003,7 +1016,7 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
         (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
             Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in)))))));

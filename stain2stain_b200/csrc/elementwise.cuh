@@ -560,14 +560,16 @@ __device__ __forceinline__ __half2 silu_grad_h2(__half2 z) {
 }
 
 // xf = x as fp32, dz = g * keep/(1-p) * act'(x*A + Bc) for 8 consecutive channels of one pixel
+// (the 1/(1-p) factor of the kept elements is NOT applied here: it is linear, the callers fold it into their per-channel
+// sums / coefficients -- one multiply per channel instead of one per element)
 template <int kAct, bool kDrop, int XF, int GF>
 __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const GnZCoef<gn_half_path<kAct, XF>()>& cf,
-                                       uint32_t keep, float keep_scale, float (&xf)[8], float (&dz)[8]) {
+                                       uint32_t keep, float (&xf)[8], float (&dz)[8]) {
     cvt8_in_t<XF>(xu, xf);
     cvt8_in_t<GF>(gu, dz);
     if (kDrop) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dz[e] *= (keep & (1u << e)) ? keep_scale : 0.f;  // ISETP + SEL + FMUL per element
+        for (int e = 0; e < 8; ++e) dz[e] = (keep & (1u << e)) ? dz[e] : 0.f;  // R2P + one FSEL per element
     }
     if constexpr (kAct == kActSilu) {
         if constexpr (XF == kFmtF16) {
@@ -589,7 +591,10 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
     }
 }
 
-template <int kAct, bool kDrop, int XF, int GF>
+// kDrop: 0 = no dropout, 1 = keep bits re-generated from the Philox counter, 2 = keep bits read from the stored mask (what the
+// ResBlock node uses).  A compile-time choice: with both paths in one kernel the Philox code's registers made the 64-register
+// variant spill in its main loop (profiles/r02_ncu_norm_attention_summary.txt).
+template <int kAct, int kDrop, int XF, int GF>
 __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                       int C, int HW, int pix_per_cta,
@@ -619,15 +624,15 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
     // stored keep bits: the byte is fetched TOGETHER with the x / g vectors of its pixel (a dependent 1-byte load inside
     // the body exposed a full memory latency per pixel: the dropout variants ran at 0.53 of HBM peak, issue-stalled)
-    const bool stored = kDrop && mask_in != nullptr;
+    constexpr bool stored = kDrop == 2;
     auto mask_at = [&](int p) -> uint32_t {
         return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
     };
     auto body = [&](const uint4& xu, const uint4& gu, uint32_t m, int p) {
-        if (kDrop && !stored)
+        if (kDrop == 1)
             m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8];
-        gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
+        gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
         // optional side product: x in bf16 (the weight-gradient operand of a 1x1 skip conv over the raw block input) --
         // +2 B/element here instead of a 4 B/element conversion pass
         if (x_bf16_out != nullptr)
@@ -656,8 +661,8 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
              mask_at(p), p);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        red[threadIdx.x][e] = s1[e];
-        red[threadIdx.x][8 + e] = s2[e];
+        red[threadIdx.x][e] = s1[e] * keep_scale;  // dz of the kept elements carries 1/(1-p): applied once per channel here
+        red[threadIdx.x][8 + e] = s2[e] * keep_scale;
     }
     __syncthreads();
     const int cpg = Ctot / G;
@@ -736,7 +741,7 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restri
 }
 
 // Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; 16-bit NHWC.
-template <int kAct, bool kDrop, bool kAdd, int XF, int GF>
+template <int kAct, int kDrop, bool kAdd, int XF, int GF>
 __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                      int C, int HW, int pix_per_cta,
@@ -770,15 +775,19 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
     const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
                                        (unsigned long long)((c_off >> 3) + slot);
-    const bool stored = kDrop && mask_in != nullptr;  // keep bits fetched together with the pixel's vectors (see gn_bwd_reduce)
+    constexpr bool stored = kDrop == 2;  // keep bits fetched together with the pixel's vectors (see gn_bwd_reduce)
+    if (kDrop != 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) P[e] *= keep_scale;  // dz only enters through dz * P: 1/(1-p) folded into P
+    }
     auto mask_at = [&](int p) -> uint32_t {
         return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
     };
     auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, uint32_t m, int p) {
-        if (kDrop && !stored)
+        if (kDrop == 1)
             m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
         float xf[8], dz[8], o[8];
-        gn_dz8<kAct, kDrop, XF, GF>(xu, gu, cf, m, keep_scale, xf, dz);
+        gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
         if (kAdd) {
