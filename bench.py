@@ -120,22 +120,25 @@ def _barrier(world):
     torch.cuda.synchronize()
 
 
-def build_lit(device, dropout=0.1):
+def build_lit(device, dropout=0.1, class_cond=False):
+    """config A (configs/model/conditional_flow_matching.yaml) or, class_cond, config B = the any2any model with a stain-class
+    embedding in every block (configs/model/class_conditional_flow_matching.yaml: class_cond true, num_classes 3)."""
     import functools
     from stain2stain_b200.flow_matching import ConditionalFlowMatcher
-    from stain2stain_b200.lit import ConditionalFlowMatchingLitModule
+    from stain2stain_b200.lit import ClassConditionalFlowMatchingLitModule, ConditionalFlowMatchingLitModule
     from stain2stain_b200.neural_ode import NeuralODE
     from stain2stain_b200.optim import FusedAdam
     from stain2stain_b200.unet import UNetModel
     torch.manual_seed(1984)
+    kw = dict(class_cond=True, num_classes=3) if class_cond else {}
     net = UNetModel(dim=[3, 256, 256], num_channels=128, num_res_blocks=2, attention_resolutions="16,8",
                     dropout=dropout, use_scale_shift_norm=True, num_heads=4, num_head_channels=32,
-                    channel_mult=[1, 2, 2, 4])
+                    channel_mult=[1, 2, 2, 4], **kw)
     _dezero(net)
-    lit = ConditionalFlowMatchingLitModule(
-        net=net, flow_matcher=ConditionalFlowMatcher(sigma=0.0),
-        solver=functools.partial(NeuralODE, solver="euler", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
-        optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=0.0), scheduler=None)
+    cls = ClassConditionalFlowMatchingLitModule if class_cond else ConditionalFlowMatchingLitModule
+    lit = cls(net=net, flow_matcher=ConditionalFlowMatcher(sigma=0.0),
+              solver=functools.partial(NeuralODE, solver="euler", sensitivity="adjoint", atol=1e-4, rtol=1e-4),
+              optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=0.0), scheduler=None)
     return lit.to(device)
 
 
@@ -152,12 +155,12 @@ def _dezero(net, seed=1984):
 class _StepModule(torch.nn.Module):
     """What Lightning's DDP strategy does: DDP wraps a module whose forward is the LightningModule's training_step."""
 
-    def __init__(self, lit):
+    def __init__(self, lit, y=None):
         super().__init__()
-        self.lit = lit
+        self.lit, self.y = lit, y
 
     def forward(self, x0, x1):
-        return self.lit.training_step((x0, x1), 0)
+        return self.lit.training_step((x0, x1) if self.y is None else (x0, x1, self.y), 0)
 
 
 def run_train(args, rank, world, local):
@@ -165,7 +168,8 @@ def run_train(args, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     B = args.batch
-    lit = build_lit(dev)
+    cc = args.mode == "classcond"
+    lit = build_lit(dev, class_cond=cc)
     lit.train()
     opt = lit.configure_optimizers()["optimizer"]
     g = torch.Generator(device=dev).manual_seed(1984 + rank)
@@ -175,10 +179,16 @@ def run_train(args, rank, world, local):
     x1s = [torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1 for _ in range(n_sets)]
     host0 = [x.cpu().pin_memory() for x in x0s[:2]]
     host1 = [x.cpu().pin_memory() for x in x1s[:2]]
+    # class-conditional (configs[3]): target stain label per tile, y ~ randint(0, 3)
+    ylab = torch.randint(0, 3, (B,), device=dev, generator=g) if cc else None
+    yhost = ylab.cpu().pin_memory() if cc else None
+
+    def batch_of(x0, x1):
+        return (x0, x1, ylab) if cc else (x0, x1)
 
     def step_eager(x0, x1):  # the same step launched from Python (per-kernel CUDA events need eager launches)
         opt.zero_grad(set_to_none=True)
-        loss = lit.training_step((x0, x1), 0)
+        loss = lit.training_step(batch_of(x0, x1), 0)
         loss.backward()
         opt.step()
         return loss
@@ -202,7 +212,7 @@ def run_train(args, rank, world, local):
     _barrier(world)
 
     if args.no_graph:
-        step_mod = _StepModule(lit)
+        step_mod = _StepModule(lit, ylab)
         if world > 1:
             # ONE bucket: a single flat fp32 all-reduce (284 MB, < 1 ms over NVSwitch) right after backward.  The default
             # 25 MB buckets put ~12 ncclAllReduce kernels next to persistent 148-CTA tcgen05 kernels whose static tile
@@ -221,10 +231,11 @@ def run_train(args, rank, world, local):
         # the step as CUDA graphs (stain2stain_b200/graphed.py): forward + backward + flat gradient gather [+ Adam] replayed;
         # at N > 1 one eager all-reduce of the flat 284 MB gradient buffer sits between the two graphs
         from stain2stain_b200.graphed import GraphedTrainStep
-        gs = GraphedTrainStep(lit, opt, (B, 3, 256, 256), dev, process_group=dist.group.WORLD if world > 1 else None)
+        gs = GraphedTrainStep(lit, opt, (B, 3, 256, 256), dev, process_group=dist.group.WORLD if world > 1 else None,
+                              label_shape=(B,) if cc else None)
 
         def step(x0, x1):
-            return gs(x0, x1)
+            return gs(x0, x1, y=(yhost if not x0.is_cuda else ylab) if cc else None)
         how = "CUDA-graph replay" + (", one flat fp32 gradient all-reduce (NCCL) between the backward and the Adam graph"
                                      if world > 1 else "")
 
@@ -268,14 +279,16 @@ def run_train(args, rank, world, local):
         "dtype": "f16 forward / bf16 backward operands, fp32 accumulate (tcgen05 kind::f16)" if K.ACT == K.FMT_F16
                  else "bf16 operands, fp32 accumulate",
         "data": "synthetic U(-1,1) 3x256x256 tile pairs, random-init (de-zeroed) config-A UNet, seed 1984",
-        "config": {"workload": "configs[1]: simple flow-matching UNet training, 256x256 tiles, batch 64/GPU, DDP",
+        "config": {"workload": ("configs[3]: stain-class-conditioned any2any flow matching (label embedding in every UNet block), "
+                                "256x256 tiles, batch 64/GPU, DDP" if cc else
+                                "configs[1]: simple flow-matching UNet training, 256x256 tiles, batch 64/GPU, DDP"),
                    "per_gpu_batch": B, "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()),
                    "parallelism": f"dp{world}", "dropout": 0.1, "optimizer": "Adam lr 1e-4 (fused, own kernel)",
                    "step_launch": how,
                    "l2": "inputs larger than L2 (2 x %.0f MB per step, 4 rotating sets)" % (B * 3 * 256 * 256 * 4 / 1e6)},
         "loss": last_loss,
-        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": 2 * B * 3 * 256 * 256 * 4,
-                "d2h_bytes_per_step": 4, "loss": loss_host},
+        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
+                "h2d_bytes_per_step": 2 * B * 3 * 256 * 256 * 4 + (8 * B if cc else 0), "d2h_bytes_per_step": 4, "loss": loss_host},
         "gpu_launches": launches,
     }
     roof = None
@@ -310,7 +323,7 @@ def run_train(args, rank, world, local):
         out["clocks"] = clocks
         out["cpu_baseline"] = cpu_baseline(sample_steps=1) if (world == 1 and not args.no_cpu) else None
     # ---- the metric's second half in the same line: 50-evaluation Euler sampling (configs[2]), tiles sharded by rank
-    if not args.no_sample:
+    if not args.no_sample and not cc:
         del x0s, x1s, host0, host1
         opt.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
@@ -607,7 +620,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "sample", "multitask"])
+    ap.add_argument("--mode", default="train", choices=["train", "sample", "multitask", "classcond"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (train: 64) / micro-batch (sample: 64; 4096 tiles on 8 GPUs = 8 micro-batches per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sample", action="store_true", help="train mode: skip the 50-step sampling record")
@@ -620,7 +633,7 @@ def main():
                     help="DDP gradient bucket size; 512 = ONE flat all-reduce of the 284 MB of fp32 gradients")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = {"train": 64, "sample": 64, "multitask": 16}[args.mode]
+        args.batch = {"train": 64, "sample": 64, "multitask": 16, "classcond": 64}[args.mode]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -631,7 +644,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
     rank, world, local = _dist_setup(args.gpus)
-    out = {"train": run_train, "sample": run_sample, "multitask": run_multitask}[args.mode](args, rank, world, local)
+    out = {"train": run_train, "sample": run_sample, "multitask": run_multitask, "classcond": run_train}[args.mode](
+        args, rank, world, local)
     if rank == 0:
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
