@@ -110,42 +110,47 @@ def odeint(f, x, t_span, solver="dopri5", atol=1e-4, rtol=1e-4):
         return t_span, torch.stack(sol)
     if solver != "dopri5":
         raise NotImplementedError(solver)
-    # adaptive dopri5, steps truncated to land on every t_span checkpoint (no dense output)
+    # adaptive dopri5 as torchdyn 1.0.6 runs it (`_adaptive_odeint`, `init_step`, `adapt_step`; restated from the published
+    # source, B.2): initial step from Hairer's heuristic with exponent 1/(order+1), order = 5; a step that would pass the
+    # next t_span point is cut to land on it (no dense output) and afterwards the controller continues from the REMAINDER
+    # of the un-cut proposal, (dt_old - dt) * factor; factor = clamp(safety * ratio^(-1/order), min_factor, max_factor) with
+    # min_factor raised to 1 for accepted steps (ratio < 1) and the plain max_factor for ratio == 0.
     t = t_span[0]
     k1 = f(t, x)
-    dt = _init_step(f, k1, x, t, 4, atol, rtol)
+    order, safety, min_f, max_f = 5, 0.9, 0.2, 10.0
+    dt = _init_step(f, k1, x, t, order, atol, rtol)
     ckpt = 1
-    safety, min_f, max_f, order = 0.9, 0.2, 10.0, 5
     n_fe = 2
     while ckpt < len(t_span):
         t_target = t_span[ckpt]
-        trunc = bool(t + dt > t_target)
-        h = (t_target - t) if trunc else dt
+        cut = bool(t + dt > t_target)
+        dt_old = dt
+        if cut:
+            dt = t_target - t
         ks = [k1]
         for s in range(1, 7):
-            xs = x + h * sum(a * k for a, k in zip(_DOPRI_A[s], ks))
-            ks.append(f(t + _DOPRI_C[s] * h, xs))
+            xs = x + dt * sum(a * k for a, k in zip(_DOPRI_A[s], ks))
+            ks.append(f(t + _DOPRI_C[s] * dt, xs))
         n_fe += 6
-        x_new = x + h * sum(b * k for b, k in zip(_DOPRI_B5, ks))
-        x_err = h * sum((b5 - b4) * k for b5, b4, k in zip(_DOPRI_B5, _DOPRI_B4, ks))
-        scale = atol + rtol * torch.max(x.abs(), x_new.abs())
-        err_ratio = _hairer_norm(x_err / scale)
-        accept = bool(err_ratio <= 1)
-        if accept:
-            t = t + h
+        x_new = x + dt * sum(b * k for b, k in zip(_DOPRI_B5, ks))
+        x_err = dt * sum((b5 - b4) * k for b5, b4, k in zip(_DOPRI_B5, _DOPRI_B4, ks))
+        err_ratio = float(_hairer_norm(x_err / (atol + rtol * torch.max(x.abs(), x_new.abs()))))
+        if err_ratio <= 1.0:
+            t = t_target if cut else t + dt
             x = x_new
             k1 = ks[-1]  # FSAL
-            if trunc:
+            if cut:
                 sol.append(x)
                 ckpt += 1
-        # step-size controller
-        if float(err_ratio) == 0.0:
+        if cut:
+            rest = dt_old - dt
+            dt = rest if float(rest) > 0.0 else dt  # (guard: a remainder rounded to 0 would stall the loop)
+        if err_ratio == 0.0:
             factor = max_f
         else:
-            factor = min(max_f, max(min_f, safety * float(err_ratio) ** (-1.0 / order)))
-        if not (accept and trunc):
-            dt = h * factor
-        # after an accepted truncated step the controller keeps the un-truncated proposal `dt`
+            lo = 1.0 if err_ratio < 1.0 else min_f
+            factor = min(max_f, max(lo, safety * err_ratio ** (-1.0 / order)))
+        dt = dt * factor
     odeint.last_nfe = n_fe
     return t_span, torch.stack(sol)
 

@@ -27,7 +27,7 @@ GRAD = FMT_BF16
 
 # ---- instrumentation: launch counter + optional per-launch CUDA-event profile (bench.py roofline) ----------------
 LAUNCHES = [0]
-PROFILE = None  # when a list: (kernel name, start event, end event, algorithmic flops, algorithmic bytes) per launch
+PROFILE = None  # when a list: (kernel name, start event, end event, algorithmic flops, algorithmic bytes, executed flops) per launch
 
 
 def check(rc: int, what: str = ""):
@@ -36,10 +36,14 @@ def check(rc: int, what: str = ""):
 
 
 class _Prof:
-    __slots__ = ("name", "flops", "bytes", "e0")
+    """flops / nbytes: ALGORITHMIC work of the launch (what the reference's formulation needs: rooflines are reported against
+    it); exec_flops: what the launch really multiplies when that differs (the phase-decomposed Upsample conv executes 4/9 of
+    its algorithmic MACs, a zero-inserted dgrad 4x) -- reported beside it, never used as the numerator."""
+    __slots__ = ("name", "flops", "bytes", "e0", "exec_flops")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0):
+    def __init__(self, name, flops=0.0, nbytes=0.0, exec_flops=None):
         self.name, self.flops, self.bytes, self.e0 = name, flops, nbytes, None
+        self.exec_flops = flops if exec_flops is None else exec_flops
 
     def __enter__(self):
         if PROFILE is not None:
@@ -51,19 +55,20 @@ class _Prof:
         if PROFILE is not None and self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.e0, e1, self.flops, self.bytes))
+            PROFILE.append((self.name, self.e0, e1, self.flops, self.bytes, self.exec_flops))
         return False
 
 
 def profile_summary(records):
     """-> {kernel: dict(launches, ms, flops, bytes)} (call after torch.cuda.synchronize())."""
     out = {}
-    for name, e0, e1, fl, by in records:
-        d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+    for name, e0, e1, fl, by, xfl in records:
+        d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, exec_flops=0.0))
         d["launches"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += fl
         d["bytes"] += by
+        d["exec_flops"] += xfl
     return out
 
 
@@ -204,8 +209,8 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     # algorithmic work: MACs over the REAL channels (padding of the K / N tiles is not counted).  `alg_macs`: the caller's
     # figure when the launch executes more than the algorithm needs (dgrad of a stride-2 conv through zero insertion
     # runs at 4x its algorithmic MACs) -- rooflines are reported against the algorithm, never against executed work
-    macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs) if alg_macs is None \
-        else float(alg_macs)
+    exec_macs = float(B) * hout * wout * cout * sum(x.shape[3] * taps for (x, taps, _) in srcs)
+    macs = exec_macs if alg_macs is None else float(alg_macs)
     stats = None
     if want_stats and not out_f32 and axpy_x is None and EPI_STATS:
         nt = int(_L().s2s_conv_stat_tiles_for(arr, len(srcs), hout, wout, cout))
@@ -219,12 +224,12 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
                 cf, off = nm
                 assert cf.dtype == torch.float32 and cf.is_contiguous() and cf.shape[0] == B and cf.shape[2] == 2
                 narr[i].coef, narr[i].ld, narr[i].off = cf.data_ptr(), cf.shape[1], off
-        with _Prof("conv_igemm", 2.0 * macs):
+        with _Prof("conv_igemm", 2.0 * macs, exec_flops=2.0 * exec_macs):
             check(_L().s2s_conv_fwd_norm(arr, narr, int(norm_act), len(srcs), B, hout, wout, ptr(w_packed),
                                          w_packed.shape[1], cout, ptr(bias), ptr(residual), o16, ptr(stats), a_fmt, w_fmt,
                                          out_fmt, res_fmt, stream_ptr()), "conv_fwd_norm")
         return (out, stats) if want_stats else out
-    with _Prof("conv_igemm", 2.0 * macs):
+    with _Prof("conv_igemm", 2.0 * macs, exec_flops=2.0 * exec_macs):
         check(_L().s2s_conv_fwd(arr, len(srcs), B, hout, wout, ptr(w_packed), w_packed.shape[1], cout, ptr(bias),
                                 ptr(residual), o16, o32, ptr(axpy_x), float(axpy_a), ptr(stats), a_fmt, w_fmt, out_fmt,
                                 res_fmt, stream_ptr()), "conv_fwd")
@@ -381,7 +386,7 @@ def upconv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, bias: Optiona
         nt = int(_L().s2s_upconv_stat_tiles(H, W, cout))
         if nt > 0:
             stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=x.device)
-    with _Prof("conv_igemm", 2.0 * B * 4 * H * W * cout * Cc * 9):
+    with _Prof("conv_igemm", 2.0 * B * 4 * H * W * cout * Cc * 9, exec_flops=2.0 * B * 4 * H * W * cout * Cc * 4):
         check(_L().s2s_upconv_fwd(ptr(x), B, H, W, Cc, ptr(w_packed), cout, ptr(bias), ptr(out), ptr(stats), a_fmt, a_fmt,
                                   out_fmt, stream_ptr()), "upconv_fwd")
         LAUNCHES[0] += 3
@@ -394,7 +399,7 @@ def upconv_dgrad(dy: torch.Tensor, w_packed: torch.Tensor, cin: int, fmt: int = 
     B, H2, W2, Cm = dy.shape
     assert w_packed.dtype == T16 and w_packed.is_contiguous() and tuple(w_packed.shape) == (cin, 16 * Cm)
     dx = torch.empty((B, H2 // 2, W2 // 2, cin), dtype=T16, device=dy.device)
-    with _Prof("conv_igemm", 2.0 * B * H2 * W2 * cin * Cm * 9):
+    with _Prof("conv_igemm", 2.0 * B * H2 * W2 * cin * Cm * 9, exec_flops=2.0 * B * H2 * W2 * cin * Cm * 4):
         check(_L().s2s_upconv_dgrad(ptr(dy), B, H2 // 2, W2 // 2, Cm, ptr(w_packed), cin, ptr(dx), fmt, fmt, fmt,
                                     stream_ptr()), "upconv_dgrad")
     return dx
@@ -408,7 +413,7 @@ def upconv_wgrad(dy: torch.Tensor, x: torch.Tensor, fmt: int = GRAD) -> torch.Te
     Cm = dy.shape[3]
     assert dy.shape[1] == 2 * H and dy.shape[2] == 2 * W
     dw16 = torch.zeros((16, Cm, Cq), dtype=torch.float32, device=x.device)
-    with _Prof("conv_wgrad", 2.0 * B * 4 * H * W * Cm * Cq * 9):
+    with _Prof("conv_wgrad", 2.0 * B * 4 * H * W * Cm * Cq * 9, exec_flops=2.0 * B * 4 * H * W * Cm * Cq * 4):
         check(_L().s2s_upconv_wgrad(ptr(dy), Cm, ptr(x), Cq, B, H, W, ptr(dw16), fmt, fmt, stream_ptr()), "upconv_wgrad")
         LAUNCHES[0] += 3
     grad = torch.empty((Cm, Cq, 3, 3), dtype=torch.float32, device=x.device)

@@ -165,9 +165,11 @@ def odeint(f: Callable, x: torch.Tensor, t_span: torch.Tensor, solver: str = "do
         return t_span, torch.stack(sol)
     if solver not in ("dopri5",):
         raise NotImplementedError(f"solver {solver!r}: available euler, midpoint, rk4, dopri5")
+    # torchdyn's adaptive stepping (B.2): init_step with exponent 1/(order+1), order 5; steps cut at every t_span point;
+    # after a cut the controller resumes from what was left of the un-cut proposal; accepted steps never shrink.
+    order, safety, fmin, fmax = 5, 0.9, 0.2, 10.0
     t = t_span[0]
     k1 = f(t, x)
-    # Hairer's initial step heuristic
     scale = atol + x.abs() * rtol
     d0, d1 = _rms(x / scale), _rms(k1 / scale)
     h0 = x.new_tensor(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
@@ -175,28 +177,32 @@ def odeint(f: Callable, x: torch.Tensor, t_span: torch.Tensor, solver: str = "do
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = torch.max(x.new_tensor(1e-6), h0 * 1e-3)
     else:
-        h1 = x.new_tensor((0.01 / max(float(d1), float(d2))) ** 0.2)
+        h1 = x.new_tensor((0.01 / max(float(d1), float(d2))) ** (1.0 / (order + 1)))
     dt = torch.min(100 * h0, h1)
-    ckpt = 1
-    while ckpt < len(t_span):
-        target = t_span[ckpt]
-        trunc = bool(t + dt > target)
-        h = (target - t) if trunc else dt
+    nxt = 1
+    while nxt < len(t_span):
+        stop = t_span[nxt]
+        lands = bool(t + dt > stop)
+        h = (stop - t) if lands else dt
         ks = [k1]
         for s in range(1, 7):
             ks.append(f(t + _DOPRI_C[s] * h, x + h * sum(a * k for a, k in zip(_DOPRI_A[s], ks))))
         x_new = x + h * sum(b * k for b, k in zip(_DOPRI_B5, ks))
         err = h * sum((b5 - b4) * k for b5, b4, k in zip(_DOPRI_B5, _DOPRI_B4, ks))
         ratio = float(_rms(err / (atol + rtol * torch.max(x.abs(), x_new.abs()))))
-        accept = ratio <= 1.0
-        if accept:
-            t, x, k1 = t + h, x_new, ks[-1]
-            if trunc:
+        if ratio <= 1.0:
+            t, x, k1 = (stop if lands else t + h), x_new, ks[-1]
+            if lands:
                 sol.append(x)
-                ckpt += 1
-        factor = 10.0 if ratio == 0.0 else min(10.0, max(0.2, 0.9 * ratio ** -0.2))
-        if not (accept and trunc):
-            dt = h * factor
+                nxt += 1
+        rest = (dt - h) if lands else h  # a cut step continues from the remainder of its proposal
+        if float(rest) <= 0.0:  # (guard: a remainder rounded to 0 would stall the loop)
+            rest = h
+        if ratio == 0.0:
+            grow = fmax
+        else:
+            grow = min(fmax, max(1.0 if ratio < 1.0 else fmin, safety * ratio ** (-1.0 / order)))
+        dt = rest * grow
     return t_span, torch.stack(sol)
 
 
