@@ -458,21 +458,52 @@ def run_multitask(args, rank, world, local):
 
         def forward(self, x0, x1, m):
             return self.lit.training_step((x0, x1, m), 0)
-    step_mod = Step(lit)
-    if world > 1:
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True)
     opt = lit.configure_optimizers()["optimizer"]
     g = torch.Generator(device=dev).manual_seed(1984 + rank)
     sets = [(torch.rand(B, 3, S, S, device=dev, generator=g) * 2 - 1, torch.rand(B, 3, S, S, device=dev, generator=g) * 2 - 1,
              torch.randint(0, 5, (B, 1, S, S), device=dev, generator=g).float()) for _ in range(2)]
     hosts = [tuple(t.cpu().pin_memory() for t in s) for s in sets]
 
-    def step(x0, x1, m):
+    def step_eager(x0, x1, m):
         opt.zero_grad(set_to_none=True)
-        loss = step_mod(x0, x1, m)
+        loss = lit.training_step((x0, x1, m), 0)
         loss.backward()
         opt.step()
         return loss
+    # instrumented eager step first (per-kernel CUDA events), then the graphs are captured
+    prof = {}
+    for _ in range(2):
+        step_eager(*sets[1])
+    torch.cuda.synchronize()
+    if rank == 0:
+        K.PROFILE = []
+    step_eager(*sets[0])
+    torch.cuda.synchronize()
+    if rank == 0:
+        prof = K.profile_summary(K.PROFILE)
+        K.PROFILE = None
+    opt.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    _barrier(world)
+    if args.no_graph:
+        step_mod = Step(lit)
+        if world > 1:
+            step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], gradient_as_bucket_view=True,
+                                                                 bucket_cap_mb=args.bucket_mb)
+
+        def step(x0, x1, m):
+            opt.zero_grad(set_to_none=True)
+            loss = step_mod(x0, x1, m)
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        from stain2stain_b200.graphed import GraphedTrainStep
+        gs = GraphedTrainStep(lit, opt, (B, 3, S, S), dev, process_group=dist.group.WORLD if world > 1 else None,
+                              extra=[((B, 1, S, S), torch.float32)])
+
+        def step(x0, x1, m):
+            return gs(x0, x1, extra=[m])
     for i in range(args.warmup):
         step(*sets[i % 2])
     _barrier(world)
@@ -492,20 +523,13 @@ def run_multitask(args, rank, world, local):
     _barrier(world)
     e0.record()
     for i in range(args.steps):
-        loss_host = float(step(*(t.to(dev, non_blocking=True) for t in hosts[i % 2])).detach())
+        if args.no_graph:
+            loss_host = float(step(*(t.to(dev, non_blocking=True) for t in hosts[i % 2])).detach())
+        else:  # the graphed step copies pinned host memory straight into its static buffers
+            loss_host = float(step(*hosts[i % 2]).detach())
     e1.record()
     _barrier(world)
     ms_e2e = _max_over_ranks(e0.elapsed_time(e1), world, dev)
-    torch.cuda.synchronize()
-    if rank == 0:
-        K.PROFILE = []
-    step(*sets[0])
-    torch.cuda.synchronize()
-    prof = {}
-    if rank == 0:
-        prof = K.profile_summary(K.PROFILE)
-        K.PROFILE = None
-    _barrier(world)
     tiles = B * world * args.steps
     pk = _peaks()
     step_ms = ms / args.steps
@@ -516,7 +540,9 @@ def run_multitask(args, rank, world, local):
            "dtype": "f16 forward / bf16 backward operands, fp32 accumulate",
            "data": "synthetic U(-1,1) 3x512x512 tile pairs + 5-class masks, default-init config-M model, seed 1984",
            "config": {"workload": "configs[4]: multi-task multi-class-loss model at 512x512 tiles", "per_gpu_batch": B,
-                      "params": sum(p.numel() for p in lit.parameters()), "parallelism": f"dp{world}"},
+                      "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()), "parallelism": f"dp{world}",
+                      "step_launch": "eager launches, torch DDP" if args.no_graph else
+                                     "CUDA-graph replay (+ one flat gradient all-reduce between two graphs at N > 1)"},
            "loss": float(loss.detach()), "gpu_launches": launches,
            "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s", "loss": loss_host,
                    "h2d_bytes_per_step": B * S * S * 4 * 7, "d2h_bytes_per_step": 4},

@@ -33,6 +33,7 @@ import torch.distributed as dist
 from . import _lib
 from . import kernels as K
 from .optim import FusedAdam
+from .parallel import FlatGradients
 
 
 class _CopyTensor(C.Structure):
@@ -41,10 +42,11 @@ class _CopyTensor(C.Structure):
 
 class GraphedTrainStep:
     def __init__(self, lit, optimizer: FusedAdam, batch_shape, device, process_group=None, warmup: int = 3,
-                 label_shape=None):
-        """lit: one of this package's flow-matching LitModules (model_step(batch, t=...) -> loss); optimizer: its FusedAdam;
-        batch_shape: [B, C, H, W] of x0 / x1 per rank; process_group: None = single GPU, else the NCCL group to average
-        gradients over (`dist.group.WORLD` for plain data parallel)."""
+                 label_shape=None, extra=None):
+        """lit: one of this package's flow-matching LitModules (model_step(batch, t=...) -> loss or (loss, dict)); optimizer:
+        its FusedAdam; batch_shape: [B, C, H, W] of x0 / x1 per rank; process_group: None = single GPU, else the NCCL group to
+        average gradients over (`dist.group.WORLD` for plain data parallel).  Further batch members: `label_shape` (int64
+        class labels of the class-conditional module) or `extra` = [(shape, dtype), ...] (e.g. the multitask module's mask)."""
         if not isinstance(optimizer, FusedAdam):
             raise TypeError("GraphedTrainStep needs the FusedAdam of this package (device-side step count)")
         self.lit, self.opt, self.pg = lit, optimizer, process_group
@@ -54,7 +56,9 @@ class GraphedTrainStep:
         self.x0 = torch.zeros(batch_shape, dtype=torch.float32, device=self.device)
         self.x1 = torch.zeros_like(self.x0)
         self.t = torch.zeros(B, dtype=torch.float32, device=self.device)
-        self.y = None if label_shape is None else torch.zeros(label_shape, dtype=torch.int64, device=self.device)
+        specs = list(extra or []) + ([(tuple(label_shape), torch.int64)] if label_shape is not None else [])
+        self.extras = [torch.zeros(tuple(sh), dtype=dt, device=self.device) for sh, dt in specs]
+        self.y = self.extras[-1] if label_shape is not None else None
         self._t_host = torch.zeros(B, dtype=torch.float32).pin_memory()
         self.params = [p for p in lit.parameters() if p.requires_grad]
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.device)
@@ -67,13 +71,15 @@ class GraphedTrainStep:
 
     # ------------------------------------------------------------------------------------------------ capture
     def _batch(self):
-        return (self.x0, self.x1) if self.y is None else (self.x0, self.x1, self.y)
+        return (self.x0, self.x1, *self.extras)
 
     def _fwd_bwd(self):
         self.step_dev.add_(1)
         for p in self.params:
             p.grad = None
         loss = self.lit.model_step(self._batch(), t=self.t)
+        if isinstance(loss, tuple):  # the multitask module returns (total, parts)
+            loss = loss[0]
         loss.backward()
         return loss.detach()
 
@@ -144,12 +150,8 @@ class GraphedTrainStep:
     def _ensure_flat(self):
         if self.flat_grad is not None:
             return
-        n = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self._flat_views, off = {}, 0
-        for p in self.params:
-            self._flat_views[p] = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self._flat = FlatGradients(self.params)  # layout shared with the CPU-testable host logic (parallel.py)
+        self.flat_grad, self._flat_views = self._flat.flat, self._flat.views
         # copy table: the work list never changes; the pointer table is rewritten whenever the gradients move (eager
         # warm-up vs. the graph's private pool).  Its host staging buffers are pinned and allocated HERE, outside any
         # capture; inside a capture only CPU writes into them and one captured H2D copy happen.
@@ -185,7 +187,7 @@ class GraphedTrainStep:
                                                _lib.stream_ptr()), "copy_multi")
 
     # ------------------------------------------------------------------------------------------------ replay
-    def load_inputs(self, x0, x1, t: Optional[torch.Tensor] = None, y=None):
+    def load_inputs(self, x0, x1, t: Optional[torch.Tensor] = None, y=None, extra=None):
         """Copy one batch into the static buffers (host or device sources; pinned host memory copies asynchronously).
         t: explicit times, else `torch.rand(B)` from the CPU default generator as torchcfm draws them."""
         self.x0.copy_(x0, non_blocking=True)
@@ -195,8 +197,10 @@ class GraphedTrainStep:
             self.t.copy_(self._t_host, non_blocking=True)
         else:
             self.t.copy_(t, non_blocking=True)
-        if self.y is not None:
+        if self.y is not None and y is not None:
             self.y.copy_(y, non_blocking=True)
+        for dst, src in zip(self.extras, extra or []):
+            dst.copy_(src, non_blocking=True)
 
     def replay(self) -> torch.Tensor:
         """One training step on whatever the static buffers hold.  Returns the (static) loss tensor."""
@@ -211,6 +215,6 @@ class GraphedTrainStep:
         torch.autograd.graph.increment_version(self.params)
         return self.loss
 
-    def __call__(self, x0, x1, t: Optional[torch.Tensor] = None, y=None) -> torch.Tensor:
-        self.load_inputs(x0, x1, t, y)
+    def __call__(self, x0, x1, t: Optional[torch.Tensor] = None, y=None, extra=None) -> torch.Tensor:
+        self.load_inputs(x0, x1, t, y, extra)
         return self.replay()

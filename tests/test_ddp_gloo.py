@@ -72,6 +72,16 @@ def _worker(rank, world, port, q):
         ref = _make_lit()
         ref.model_step((x0, x1), t=t).backward()
         ok = all(torch.allclose(a, p.grad, atol=1e-6) for a, p in zip(grads, ref.parameters()))
+        # the graphed step's collective (graphed.py): every gradient gathered into ONE flat buffer, one all-reduce(SUM), the
+        # optimizer reads it scaled by 1 / world -- must equal the DDP mean, i.e. the global-batch gradient
+        from stain2stain_b200.parallel import FlatGradients
+        lit2 = _make_lit()
+        lit2.model_step((x0[lo:hi], x1[lo:hi]), t=t[lo:hi]).backward()
+        fg = FlatGradients(list(lit2.parameters()))
+        fg.gather()
+        fg.all_reduce_sum()
+        ok = ok and all(torch.allclose(fg.views[p] / world, q.grad, atol=1e-6) for p, q in zip(lit2.parameters(), ref.parameters()))
+        ok = ok and fg.flat.numel() == sum(p.numel() for p in lit2.parameters()) and fg.offsets[0] == (0, 81)
         # the wrapper bench.py hands to DDP calls training_step like Lightning does
         sm = bench._StepModule(lit)
         assert sm(x0[lo:hi], x1[lo:hi]).dim() == 0 and "train/loss" in lit.logged
