@@ -58,6 +58,28 @@ def build_model(config, remap: bool = True, fused_optimizer: bool = True, **over
     return hydra_lite.instantiate(cfg, remap=remap, fused_optimizer=fused_optimizer, **overrides)
 
 
+def compose_experiment(config_dir: str, overrides=()) -> Dict[str, Any]:
+    """What `@hydra.main(config_path="../configs", config_name="train.yaml")` hands to `train(cfg)` (src/train.py:137-154):
+    the primary config composed with `experiment=...` and the other command-line overrides."""
+    return hydra_lite.compose(config_dir, "train", list(overrides))
+
+
+def train_experiment(config_dir: str, overrides=(), steps: int = 10, batch: Optional[int] = None, device: str = "cuda",
+                     **kw) -> Dict[str, Any]:
+    """`python src/train.py experiment=gray_matter/simple_flow_matching ...` on synthetic tiles: composes the reference's
+    config tree (unmodified), seeds from `cfg.seed`, instantiates `cfg.model` with the B200 drop-ins and runs `steps`
+    training steps at the per-device batch `cfg.data.batch_size // world` (src/data/paired_data_module.py:273-278)."""
+    cfg = hydra_lite.resolve(compose_experiment(config_dir, overrides))
+    if batch is None:
+        from .parallel import per_rank_batch
+        gb = (cfg.get("data") or {}).get("batch_size", 4)
+        batch = per_rank_batch(int(gb), int(kw.pop("world_size", 1)))
+    seed = cfg.get("seed")
+    out = train(cfg["model"], steps=steps, batch=batch, device=device, seed=1984 if seed is None else int(seed), **kw)
+    out["cfg"] = cfg
+    return out
+
+
 def train(config, steps: int = 10, batch: int = 4, size: Optional[int] = None, device: str = "cuda", seed: int = 1984,
           ckpt_path: Optional[str] = None, **overrides) -> Dict[str, Any]:
     torch.manual_seed(seed)  # L.seed_everything(cfg.seed) (src/train.py:55-56)

@@ -241,3 +241,73 @@ def test_euler_graph_registry_is_weak():
     assert len(node._GRAPHS) == n0 - 1
     node.clear_graphs()
     assert len(node._GRAPHS) == 0
+
+
+def _write(path, text):
+    import os
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(text)
+
+
+def test_hydra_lite_composes_defaults_lists_experiments_and_overrides(tmp_path):
+    """The defaults-list composition the reference's `python src/train.py experiment=...` relies on (configs/train.yaml:5-31,
+    configs/experiment/gray_matter/simple_flow_matching.yaml:4-8), on a miniature config tree."""
+    from stain2stain_b200 import hydra_lite
+    d = str(tmp_path)
+    _write(f"{d}/train.yaml", "defaults:\n  - _self_\n  - data: mnist\n  - model: mnist\n  - trainer: gpu\n  - experiment: null\n"
+                              "  - optional local: default\n  - debug: null\nseed: null\ntags: [dev]\ntask_name: train\n")
+    _write(f"{d}/data/mnist.yaml", "batch_size: 128\nname: mnist\n")
+    _write(f"{d}/data/paired.yaml", "batch_size: 6\ndata_dir: ${paths.data_dir}\nname: paired\n")
+    _write(f"{d}/model/mnist.yaml", "_target_: collections.OrderedDict\nlr: 0.1\n")
+    _write(f"{d}/model/cfm.yaml", "_target_: collections.OrderedDict\noptimizer:\n  _target_: collections.OrderedDict\n"
+                                  "  _partial_: true\n  lr: 0.001\n  weight_decay: 0.0\nnet:\n  dim: [3, 256, 256]\n")
+    _write(f"{d}/trainer/default.yaml", "max_epochs: 10\naccelerator: cpu\ndevices: 1\n")
+    _write(f"{d}/trainer/gpu.yaml", "defaults:\n  - default\naccelerator: gpu\n")
+    _write(f"{d}/trainer/ddp.yaml", "defaults:\n  - default\nstrategy: ddp\naccelerator: gpu\ndevices: 4\nsync_batchnorm: true\n")
+    _write(f"{d}/experiment/gm/simple.yaml", "# @package _global_\n\ndefaults:\n  - override /data: paired\n  - override /model: cfm\n"
+                                             "  - override /trainer: default.yaml\nseed: 1984\nbatch_size: 32\ntrainer:\n  max_epochs: 200\n"
+                                             "  devices: 4\nmodel:\n  optimizer:\n    lr: 1e-4\n    weight_decay: 1e-5\ndata:\n  batch_size: ${batch_size}\n"
+                                             "tags: [simple]\n")
+    base = hydra_lite.compose(d, "train")
+    assert base["data"]["name"] == "mnist" and base["trainer"] == {"max_epochs": 10, "accelerator": "gpu", "devices": 1}
+    assert base["seed"] is None and "experiment" not in base and "local" not in base
+    cfg = hydra_lite.compose(d, "train", ["experiment=gm/simple", "model.optimizer.lr=0.002", "trainer.devices=8"])
+    assert cfg["data"]["name"] == "paired" and cfg["model"]["net"]["dim"] == [3, 256, 256]       # groups re-selected
+    assert cfg["trainer"]["accelerator"] == "cpu" and cfg["trainer"]["max_epochs"] == 200        # experiment body on top
+    assert cfg["trainer"]["devices"] == 8 and cfg["model"]["optimizer"]["lr"] == 0.002           # value overrides last
+    assert cfg["seed"] == 1984 and cfg["tags"] == ["simple"]                                     # lists are replaced
+    res = hydra_lite.resolve(cfg)
+    assert res["data"]["batch_size"] == 32                                                       # ${batch_size}
+    assert res["data"]["data_dir"] == "${paths.data_dir}"                                        # group not composed: left alone
+    assert res["model"]["optimizer"]["weight_decay"] == "1e-5" or res["model"]["optimizer"]["weight_decay"] == 1e-5
+    cfg2 = hydra_lite.compose(d, "train", ["experiment=gm/simple", "trainer=ddp"])               # command line beats the experiment
+    assert cfg2["trainer"]["strategy"] == "ddp" and cfg2["trainer"]["max_epochs"] == 200 and cfg2["trainer"]["devices"] == 4
+    model = hydra_lite.instantiate(res["model"])
+    assert model["optimizer"].keywords["weight_decay"] == 1e-5 and model["optimizer"].keywords["lr"] == 0.002
+
+
+def test_hydra_lite_composes_the_reference_experiment_tree():
+    """`experiment=gray_matter/simple_flow_matching` over the reference's UNMODIFIED configs/ (build container only)."""
+    import os
+
+    import pytest
+    from stain2stain_b200 import hydra_lite
+    cdir = "/root/reference/configs"
+    if not os.path.isdir(cdir):
+        pytest.skip("the reference tree only exists in the build container")
+    cfg = hydra_lite.resolve(hydra_lite.compose(cdir, "train", ["experiment=gray_matter/simple_flow_matching", "trainer=ddp"]))
+    m = cfg["model"]
+    assert m["_target_"] == "src.models.conditional_flow_matching.ConditionalFlowMatchingLitModule"
+    assert m["net"]["_target_"] == "torchcfm.models.unet.UNetModel" and m["net"]["channel_mult"] == [1, 2, 2, 4]
+    assert float(m["optimizer"]["weight_decay"]) == 1e-5 and float(m["optimizer"]["lr"]) == 1e-4   # the experiment's overrides
+    assert cfg["seed"] == 1984 and cfg["data"]["batch_size"] == 32 and cfg["data"]["image_size"] == 256
+    assert cfg["trainer"]["strategy"] == "ddp" and cfg["trainer"]["max_epochs"] == 200
+    # the composed model node builds the B200 drop-ins (meta device: no GPU needed for construction)
+    import torch
+    with torch.device("meta"):
+        lit = hydra_lite.instantiate(m, remap=True, fused_optimizer=True)
+    from stain2stain_b200.lit import ConditionalFlowMatchingLitModule
+    from stain2stain_b200.unet import UNetModel
+    assert isinstance(lit, ConditionalFlowMatchingLitModule) and isinstance(lit.net, UNetModel)
+    assert sum(p.numel() for p in lit.net.parameters()) == 70_954_883
