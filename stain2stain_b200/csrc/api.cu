@@ -1191,15 +1191,19 @@ int s2s_maxpool2x_bwd(const void* x, const void* g, void* dx, int B, int H, int 
 }
 int s2s_bilinear2x(const void* in, void* out, int B, int H, int W, int C, int fmt, void* stream) {
     if (C % 8) return fail(S2S_ERR_INVALID, "bilinear2x: C %% 8 != 0");
-    const long long total = (long long)B * 4 * H * W * (C / 8);
-    bilinear2x_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8, fmt);
+    if (2 * H > 65535 || B > 65535) return fail(S2S_ERR_INVALID, "bilinear2x: H / B too large for the row grid");
+    const int cols = 2 * W * (C / 8);
+    const dim3 grid((cols + 255) / 256 > 8 ? 8 : (cols + 255) / 256, 2 * H, B);
+    S2S_FMT(fmt, F, (bilinear2x_kernel<F><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, H, W, C / 8)));
     LAUNCH_CHECK("bilinear2x_kernel");
     return S2S_OK;
 }
 int s2s_bilinear2x_bwd(const void* g, void* din, int B, int H, int W, int C, int fmt, void* stream) {
     if (C % 8) return fail(S2S_ERR_INVALID, "bilinear2x_bwd: C %% 8 != 0");
-    const long long total = (long long)B * H * W * (C / 8);
-    bilinear2x_bwd_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>((const uint4*)g, (uint4*)din, B, H, W, C / 8, fmt);
+    if (H > 65535 || B > 65535) return fail(S2S_ERR_INVALID, "bilinear2x_bwd: H / B too large for the row grid");
+    const int cols = W * (C / 8);
+    const dim3 grid((cols + 255) / 256 > 8 ? 8 : (cols + 255) / 256, H, B);
+    S2S_FMT(fmt, F, (bilinear2x_bwd_kernel<F><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)g, (uint4*)din, H, W, C / 8)));
     LAUNCH_CHECK("bilinear2x_bwd_kernel");
     return S2S_OK;
 }

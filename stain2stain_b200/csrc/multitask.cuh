@@ -168,59 +168,70 @@ __device__ __forceinline__ void bilin_src(int dst, float scale, int in, int& i0,
     i1 = i0 + (i0 < in - 1 ? 1 : 0);
     w1 = s - (float)i0;
 }
-// out [B, 2H, 2W, C] from in [B, H, W, C]
-__global__ void bilinear2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp,
-                                  int fmt) {
+// out [B, 2H, 2W, C] from in [B, H, W, C].  Grid (x: vector columns of one output row, y: output row, z: sample): the row's
+// two source rows and weight are block-uniform and every index is 32-bit (the first version decoded a flat 64-bit index
+// with three 64-bit divisions per vector and ran at 0.27 of HBM).
+template <int F>
+__global__ void __launch_bounds__(256) bilinear2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W,
+                                                         int vpp) {
     const float sy = (H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
     const float sx = (W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-    const long long total = (long long)B * (2 * H) * (2 * W) * vpp;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vpp);
-        long long r = i / vpp;
-        const int x = (int)(r % (2 * W));  r /= (2 * W);
-        const int y = (int)(r % (2 * H));
-        const int b = (int)(r / (2 * H));
-        int y0, y1, x0, x1;
-        float wy, wx;
-        bilin_src(y, sy, H, y0, y1, wy);
+    const int y = blockIdx.y, b = blockIdx.z;
+    int y0, y1;
+    float wy;
+    bilin_src(y, sy, H, y0, y1, wy);
+    const int cols = 2 * W * vpp;
+    const uint4* r0 = in + ((size_t)b * H + y0) * W * vpp;
+    const uint4* r1 = in + ((size_t)b * H + y1) * W * vpp;
+    uint4* orow = out + ((size_t)b * 2 * H + y) * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) {
+        const int x = i / vpp, v = i - x * vpp;
+        int x0, x1;
+        float wx;
         bilin_src(x, sx, W, x0, x1, wx);
-        const uint4* base = in + (size_t)b * H * W * vpp + v;
         float a[8], c[8], d[8], e8[8], o[8];
-        cvt8_in(__ldg(base + ((size_t)y0 * W + x0) * vpp), fmt, a);
-        cvt8_in(__ldg(base + ((size_t)y0 * W + x1) * vpp), fmt, c);
-        cvt8_in(__ldg(base + ((size_t)y1 * W + x0) * vpp), fmt, d);
-        cvt8_in(__ldg(base + ((size_t)y1 * W + x1) * vpp), fmt, e8);
+        cvt8_in_t<F>(__ldg(r0 + x0 * vpp + v), a);
+        cvt8_in_t<F>(__ldg(r0 + x1 * vpp + v), c);
+        cvt8_in_t<F>(__ldg(r1 + x0 * vpp + v), d);
+        cvt8_in_t<F>(__ldg(r1 + x1 * vpp + v), e8);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
             o[e] = (1.f - wy) * ((1.f - wx) * a[e] + wx * c[e]) + wy * ((1.f - wx) * d[e] + wx * e8[e]);
-        stg_stream(out + i, cvt8_out(o, fmt));
+        stg_stream(orow + i, cvt8_out_t<F>(o));
     }
 }
-// adjoint as a gather: din[b, yi, xi, :] = sum over the output pixels whose footprint touches (yi, xi)
-__global__ void bilinear2x_bwd_kernel(const uint4* __restrict__ g, uint4* __restrict__ din, int B, int H, int W, int vpp,
-                                      int fmt) {
+// adjoint as a gather: din[b, yi, xi, :] = sum over the output pixels whose footprint touches (yi, xi).  Same grid shape
+// (y: input row); the six candidate output rows and their weights are block-uniform.
+template <int F>
+__global__ void __launch_bounds__(256) bilinear2x_bwd_kernel(const uint4* __restrict__ g, uint4* __restrict__ din, int H,
+                                                             int W, int vpp) {
     const float sy = (H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
     const float sx = (W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-    const long long total = (long long)B * H * W * vpp;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(i % vpp);
-        long long r = i / vpp;
-        const int xi = (int)(r % W);  r /= W;
-        const int yi = (int)(r % H);
-        const int b = (int)(r / H);
-        // candidate outputs: src ~ dst / 2 (slightly less), so dst in [2*i - 2, 2*i + 3] covers every contributor
-        float wrow[6], wcol[6];
+    const int yi = blockIdx.y, b = blockIdx.z;
+    // candidate outputs: src ~ dst / 2 (slightly less), so dst in [2*i - 2, 2*i + 3] covers every contributor
+    float wrow[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int yo = 2 * yi - 2 + k;
+        wrow[k] = 0.f;
+        if (yo >= 0 && yo < 2 * H) {
+            int y0, y1;
+            float w;
+            bilin_src(yo, sy, H, y0, y1, w);
+            if (y0 == yi) wrow[k] += 1.f - w;
+            if (y1 == yi) wrow[k] += w;
+        }
+    }
+    const int cols = W * vpp, ocols = 2 * W * vpp;
+    const uint4* gb = g + (size_t)b * 2 * H * ocols;
+    uint4* drow = din + ((size_t)b * H + yi) * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) {
+        const int xi = i / vpp, v = i - xi * vpp;
+        float wcol[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const int yo = 2 * yi - 2 + k, xo = 2 * xi - 2 + k;
-            wrow[k] = wcol[k] = 0.f;
-            if (yo >= 0 && yo < 2 * H) {
-                int y0, y1;
-                float w;
-                bilin_src(yo, sy, H, y0, y1, w);
-                if (y0 == yi) wrow[k] += 1.f - w;
-                if (y1 == yi) wrow[k] += w;
-            }
+            const int xo = 2 * xi - 2 + k;
+            wcol[k] = 0.f;
             if (xo >= 0 && xo < 2 * W) {
                 int x0, x1;
                 float w;
@@ -232,21 +243,21 @@ __global__ void bilinear2x_bwd_kernel(const uint4* __restrict__ g, uint4* __rest
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        const uint4* base = g + (size_t)b * 4 * H * W * vpp + v;
+#pragma unroll
         for (int ky = 0; ky < 6; ++ky) {
-            if (wrow[ky] == 0.f) continue;
-            const int yo = 2 * yi - 2 + ky;
+            if (wrow[ky] == 0.f) continue;  // block-uniform
+            const uint4* grow = gb + (size_t)(2 * yi - 2 + ky) * ocols + v;
+#pragma unroll
             for (int kx = 0; kx < 6; ++kx) {
                 if (wcol[kx] == 0.f) continue;
-                const int xo = 2 * xi - 2 + kx;
                 float f[8];
-                cvt8_in(__ldg(base + ((size_t)yo * (2 * W) + xo) * vpp), fmt, f);
+                cvt8_in_t<F>(__ldg(grow + (2 * xi - 2 + kx) * vpp), f);
                 const float w = wrow[ky] * wcol[kx];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, f[e], acc[e]);
             }
         }
-        stg_stream(din + i, cvt8_out(acc, fmt));
+        stg_stream(drow + i, cvt8_out_t<F>(acc));
     }
 }
 
