@@ -304,6 +304,14 @@ int s2s_seg_loss_bwd(const float* logits, const long long* target, int B, int C,
                      const double* sums, float smooth, float w_dice, float w_ce, const float* gscale, float* dlogits,
                      void* stream);
 
+/* The UNet's output projection (torchcfm UNetModel.out[2] = conv3x3(C -> out_channels)): a 16-bit NHWC
+ * [B,H,W,C] -> out fp32 NCHW [B,Cout,H,W] = bias + conv3x3(a, w_oihw) with the fp32 nn.Conv2d weight itself (converted to the
+ * activation format inside the kernel), Cout <= 8, C % 16 == 0.  Optional fused Euler update: out = axpy_x + axpy_a * (...)
+ * (out may alias axpy_x) -- torchdyn's fixed-step `x + dt * f(t, x)`.  Reads the input once (halo tile in shared memory)
+ * instead of once per filter tap. */
+int s2s_head_conv(const void* a, int B, int H, int W, int C, const float* w_oihw, int Cout, const float* bias, float* out,
+                  const float* axpy_x, float axpy_a, int a_fmt, void* stream);
+
 /* ---- attention core (rows a14, f3) ----------------------------------------------------------------------------------- */
 
 /* torchcfm AttentionBlock's QKVAttentionLegacy / QKVAttention: per (sample, head)

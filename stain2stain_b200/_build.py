@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libs2s_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "attention.cuh", "conv_igemm.cuh", "elementwise.cuh", "linear.cuh", "optim.cuh", "multitask.cuh", "tiles.cuh",
+HEADERS = ["common.cuh", "attention.cuh", "conv_igemm.cuh", "elementwise.cuh", "head_conv.cuh", "linear.cuh", "optim.cuh", "multitask.cuh", "tiles.cuh",
            os.path.join("..", "..", "include", "s2s_b200.h")]
 
 

@@ -101,6 +101,7 @@ SIGNATURES = {
     "s2s_gn_apply_step": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _u64, _vp, _vp, _i, _i, _vp],
     "s2s_adam_multi_step": [_vp, _vp, _i, _d, _d, _d, _d, _d, _i, _vp, _d, _vp],
     "s2s_copy_multi": [_vp, _vp, _i, _vp],
+    "s2s_head_conv": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _i, _vp],
     "s2s_attn_supported": [_i],
     "s2s_attn_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "s2s_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],

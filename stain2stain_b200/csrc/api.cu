@@ -10,6 +10,7 @@
 #include "conv_igemm.cuh"
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "head_conv.cuh"
 #include "linear.cuh"
 #include "multitask.cuh"
 #include "optim.cuh"
@@ -1282,6 +1283,38 @@ int s2s_attn_bwd(const void* qkv, const void* out, const void* d_out, const floa
     else S2S_ATTN_BWD(64);
 #undef S2S_ATTN_BWD
     LAUNCH_CHECK("attn_bwd kernels");
+    return S2S_OK;
+}
+
+int s2s_head_conv(const void* a, int B, int H, int W, int C, const float* w_oihw, int Cout, const float* bias, float* out,
+                  const float* axpy_x, float axpy_a, int a_fmt, void* stream) {
+    if (!a || !w_oihw || !out) return fail(S2S_ERR_INVALID, "head_conv: null argument");
+    if (C % 16 || C > 512 || Cout < 1 || Cout > 8)
+        return fail(S2S_ERR_INVALID, "head_conv: needs C %% 16 == 0, C <= 512, Cout <= 8 (C=%d Cout=%d)", C, Cout);
+    HeadConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = (const uint16_t*)a; p.w = w_oihw; p.bias = bias; p.out = out; p.axpy_x = axpy_x; p.axpy_a = axpy_a;
+    p.B = B; p.H = H; p.W = W; p.C = C; p.Cout = Cout;
+    p.tiles_x = (W + kHeadTW - 1) / kHeadTW;
+    p.tiles_y = (H + kHeadTH - 1) / kHeadTH;
+    p.total_tiles = B * p.tiles_x * p.tiles_y;
+    const size_t smem = (size_t)((kHeadTH + 2) * (kHeadTW + 2) + 72) * (C + 8) * 2;
+    int per_sm = (int)(kSmemBudget / (smem + 1024));
+    if (per_sm < 1) return fail(S2S_ERR_INVALID, "head_conv: tile does not fit in shared memory (C=%d)", C);
+    if (per_sm > 4) per_sm = 4;
+    int grid = num_sms() * per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a_fmt == S2S_FMT_F16) {
+        int rc = set_smem(head_conv_kernel<kFmtF16>, smem);
+        if (rc) return rc;
+        head_conv_kernel<kFmtF16><<<grid, kHeadThreads, smem, st>>>(p);
+    } else {
+        int rc = set_smem(head_conv_kernel<kFmtBF16>, smem);
+        if (rc) return rc;
+        head_conv_kernel<kFmtBF16><<<grid, kHeadThreads, smem, st>>>(p);
+    }
+    LAUNCH_CHECK("head_conv_kernel");
     return S2S_OK;
 }
 

@@ -506,6 +506,27 @@ def convert16(x: torch.Tensor, in_fmt: int, out_fmt: int) -> torch.Tensor:
     return out
 
 
+def head_conv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], axpy_x: Optional[torch.Tensor] = None,
+              axpy_a: float = 0.0, fmt: int = ACT) -> torch.Tensor:
+    """3x3 conv of a 16-bit NHWC tensor to <= 8 channels, fp32 NCHW output, straight from the fp32 OIHW weight; optional fused
+    `out = axpy_x + axpy_a * v` written IN PLACE into axpy_x (the Euler update)."""
+    _nhwc_check(a)
+    B, H, W, Cc = a.shape
+    cout = w.shape[0]
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (Cc, 3, 3)
+    if axpy_x is not None:
+        assert axpy_x.dtype == torch.float32 and axpy_x.is_contiguous() and tuple(axpy_x.shape) == (B, cout, H, W)
+    out = axpy_x if axpy_x is not None else torch.empty((B, cout, H, W), dtype=torch.float32, device=a.device)
+    with _Prof("conv_igemm", 2.0 * B * H * W * cout * Cc * 9):
+        check(_L().s2s_head_conv(ptr(a), B, H, W, Cc, ptr(w), cout, ptr(bias), ptr(out), ptr(axpy_x), float(axpy_a), fmt,
+                                 stream_ptr()), "head_conv")
+    return out
+
+
+def head_conv_supported(c: int, cout: int) -> bool:
+    return c % 16 == 0 and c <= 512 and 1 <= cout <= 8
+
+
 # ---- attention core (csrc/attention.cuh; SURVEY rows a14, f3) ---------------------------------------------------------------
 def attn_supported(ch: int) -> bool:
     return bool(_L().s2s_attn_supported(int(ch)))

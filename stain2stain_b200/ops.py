@@ -154,7 +154,8 @@ def usable_stats(src_stats) -> bool:
 
 class _FusedConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: ConvPlan, n_src: int, n_w: int, residual, stats_box, *tensors):
+    def forward(ctx, plan: ConvPlan, n_src: int, n_w: int, residual, boxes, *tensors):
+        stats_box, twins = boxes if isinstance(boxes, tuple) else (boxes, [None] * n_src)
         srcs = tensors[:n_src]
         weights = tensors[n_src:n_src + n_w]
         biases = [b for b in tensors[n_src + n_w:] if b is not None]
@@ -175,7 +176,10 @@ class _FusedConv(torch.autograd.Function):
         ctx.plan, ctx.n_src, ctx.n_w = plan, n_src, n_w
         ctx.has_res = residual is not None
         ctx.bias_present = [b is not None for b in tensors[n_src + n_w:]]
-        ctx.save_for_backward(*srcs, *weights)
+        # a source whose producer already wrote its bf16 twin is saved AS the twin (the fp16 tensor is not needed again:
+        # dgrad reads only d_out and the weights), so backward has no conversion pass and memory does not grow
+        ctx.twin = [tw is not None and K.ACT != K.GRAD for tw in twins]
+        ctx.save_for_backward(*[tw if has else x for x, tw, has in zip(srcs, twins, ctx.twin)], *weights)
         return out
 
     @staticmethod
@@ -204,7 +208,7 @@ class _FusedConv(torch.autograd.Function):
                     if sum(t.ci_count for t in plan.segs if t.weight == s.weight) != w.shape[1]:
                         d_ws[s.weight].zero_()
                 dw = torch.zeros((s.taps, cout, x.shape[3]), dtype=torch.float32, device=d_out.device)
-                K.conv_wgrad(d_out, K.convert16(x, K.ACT, K.GRAD), s.taps, s.stride, dw)
+                K.conv_wgrad(d_out, x if ctx.twin[s.src] else K.convert16(x, K.ACT, K.GRAD), s.taps, s.stride, dw)
                 K.unpack_wgrad(dw, d_ws[s.weight].view(cout, w.shape[1], -1), 0, s.ci_count, s.ci_begin, 0.0)
             if need[4 + s.src]:
                 wd = plan.packed_dgrad(si, weights)
@@ -233,10 +237,17 @@ def stats_of(t):
     return getattr(t, "_s2s_stats", None)
 
 
+def twin_of(t):
+    """bf16 copy of a forward-format activation written by its producer (a norm kernel's dual-format store): the operand the
+    consuming conv's weight-gradient GEMM needs, so backward does not run a conversion pass over the tensor."""
+    return getattr(t, "_s2s_g16", None)
+
+
 def fused_conv(plan: ConvPlan, srcs: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
                biases: Sequence[Optional[torch.Tensor]], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     box = []
-    return _tag(_FusedConv.apply(plan, len(srcs), len(weights), residual, box, *srcs, *weights, *biases), box)
+    twins = [twin_of(t) for t in srcs] if torch.is_grad_enabled() else [None] * len(srcs)
+    return _tag(_FusedConv.apply(plan, len(srcs), len(weights), residual, (box, twins), *srcs, *weights, *biases), box)
 
 
 # --------------------------------------------------------------------------------------------- GroupNorm (+FiLM+SiLU+dropout, +concat)
@@ -428,6 +439,10 @@ class _HeadConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, w, b, axpy_x, axpy_a):
         cout, cin = w.shape[0], w.shape[1]
+        if K.head_conv_supported(cin, cout):  # dedicated kernel: the input is read once, not once per filter tap
+            out = K.head_conv(a, w.detach(), b.detach(), axpy_x=axpy_x, axpy_a=axpy_a)
+            ctx.save_for_backward(a, w)
+            return out
 
         def make(dst):
             wp = dst if dst is not None else torch.zeros((16, 9 * cin), dtype=T16, device=w.device)
@@ -549,7 +564,7 @@ class _BatchNormRelu(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool,
-                src_stats=None):
+                src_stats=None, twin_box=None):
         B, H, W, C = x.shape
         act = K.ACT_RELU if relu else K.ACT_NONE
         if training:
@@ -563,7 +578,10 @@ class _BatchNormRelu(torch.autograd.Function):
             coef = torch.stack([A, beta.detach() - running_mean * A], dim=1).unsqueeze(0).expand(B, C, 2).contiguous()
             mr = None
         y = torch.empty_like(x)
-        K.gn_apply(x, coef, y, 0, act)
+        y2 = torch.empty_like(x) if (twin_box is not None and K.ACT != K.GRAD) else None
+        K.gn_apply(x, coef, y, 0, act, y2=y2)  # y2: the same values as bf16, the consuming conv's wgrad operand
+        if y2 is not None:
+            twin_box.append(y2)
         ctx.act, ctx.training = act, training
         ctx.save_for_backward(x, coef, mr, gamma)
         return y
@@ -582,15 +600,19 @@ class _BatchNormRelu(torch.autograd.Function):
         pqr = K.bn_bwd_coef(red, mr, gamma.detach(), H * W, dgamma, dbeta)
         dx = torch.empty_like(x)
         K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, ctx.act)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
     if bn.training and bn.track_running_stats:
         bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    return _BatchNormRelu.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bool(bn.training),
-                                float(momentum), float(bn.eps), relu, stats_of(x))
+    box = [] if (bn.training and torch.is_grad_enabled()) else None
+    y = _BatchNormRelu.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bool(bn.training),
+                             float(momentum), float(bn.eps), relu, stats_of(x), box)
+    if box:
+        y._s2s_g16 = box[0]
+    return y
 
 
 class _MaxPool2x(torch.autograd.Function):

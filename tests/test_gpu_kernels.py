@@ -529,3 +529,22 @@ def test_gn_bwd_reduce_bf16_side_copy_equals_convert16():
     k.gn_bwd_reduce(x, gy, coef, mr, red_b, 0, True, x_bf16_out=side)
     assert torch.equal(red_a, red_b)
     assert torch.equal(side.view(torch.int16), k.convert16(x, k.ACT, k.GRAD).view(torch.int16))
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout", [(2, 32, 32, 128, 3), (1, 20, 24, 64, 3), (3, 8, 16, 256, 5), (1, 64, 64, 128, 8)])
+def test_head_conv_kernel_matches_conv2d_and_fused_euler_update(B, H, W, C, Cout):
+    """s2s_head_conv: the C -> <=8 channel output projection from the fp32 weight, fp32 NCHW out, optional x + dt * v."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    a = rb(torch.randn(B, C, H, W, device=DEV, generator=g))
+    w = torch.randn(Cout, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)
+    b = torch.randn(Cout, device=DEV, generator=g) * 0.1
+    ref = F.conv2d(a, rb(w), b, padding=1)  # the kernel rounds the weight to the activation format
+    out = k.head_conv(nhwc(a), w.contiguous(), b)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (B, Cout, H, W)
+    assert rel_l2(out, ref) < 1e-3, rel_l2(out, ref)
+    assert float((out - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
+    x = torch.randn(B, Cout, H, W, device=DEV, generator=g)
+    want = x + 0.02 * ref
+    got = k.head_conv(nhwc(a), w.contiguous(), b, axpy_x=x, axpy_a=0.02)
+    assert got.data_ptr() == x.data_ptr() and torch.allclose(got, want, atol=1e-4, rtol=1e-4)
