@@ -88,6 +88,9 @@ int s2s_conv_fwd_norm(const s2s_conv_src* srcs, const s2s_conv_norm* norms, int 
  * s2s_conv_fwd will pick for these segments (the halo-tiled pair kernel takes stride-1 convs with a 3x3 segment). */
 int s2s_conv_stat_tiles(int Hout, int Wout, int Cout);
 int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout);
+/* _for = _geom unless the experiment switch S2S_EPI_STATS_MINK is set (> 0): then convs with a GEMM K below it answer 0 and
+ * the consumer runs s2s_gn_stats (measured neutral, off by default); _geom answers what the kernel CAN emit regardless. */
+int s2s_conv_stat_tiles_geom(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout);
 
 /* Weight gradient of one conv segment (tcgen05, split-K over pixels, fp32 reductions):
  *   dw[tap][m][n_off + n] += sum_{b,y,x} dy[b,y,x,m] * x[b, y*stride+dy, x*stride+dx, n]

@@ -29,8 +29,14 @@ with torch.no_grad():
     K.PROFILE = []
     net.euler_step_(t, x, 0.02)
     torch.cuda.synchronize()
+    recs = list(K.PROFILE)
     prof = K.profile_summary(K.PROFILE)
     K.PROFILE = None
+    print("per-launch conv records (ms, TFLOP/s algorithmic, GFLOP):")
+    for i, (name, a, b, fl, by, xfl) in enumerate(recs):
+        if name == "conv_igemm":
+            ms = a.elapsed_time(b)
+            print(f"   #{i:3d} {ms:7.3f} ms {fl / ms / 1e9:7.0f} TF/s  alg {fl / 1e9:8.1f} GF  exec {xfl / 1e9:8.1f} GF")
 tot = sum(d["ms"] for d in prof.values())
 print(f"profiled kernels: {tot:.3f} ms")
 for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):

@@ -63,6 +63,7 @@ SIGNATURES = {
                           _i, _i, _vp],
     "s2s_conv_stat_tiles": [_i, _i, _i],
     "s2s_conv_stat_tiles_for": [C.POINTER(ConvSrc), _i, _i, _i, _i],
+    "s2s_conv_stat_tiles_geom": [C.POINTER(ConvSrc), _i, _i, _i, _i],
     "s2s_gn_coef_parts": [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],
     "s2s_conv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp],
     "s2s_unpack_wgrad": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp],

@@ -295,7 +295,17 @@ int s2s_conv_stat_tiles(int Hout, int Wout, int Cout) {
     return tx * ty * mt;
 }
 
-int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout) {
+static int epi_stats_min_k() {  // S2S_EPI_STATS_MINK: smallest GEMM K for which the conv epilogue also emits the statistics
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_EPI_STATS_MINK");
+        v = e ? atoi(e) : 0;  // measured neutral-to-negative at 1800 (same box: 179.1 vs 178.6 ms/step, 24.13 vs 24.22 tiles/s): off
+    }
+    return v;
+}
+
+// geometry only: sub-tiles of the statistics the kernel chosen for these segments CAN emit
+int s2s_conv_stat_tiles_geom(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout) {
     int BN, mt, tx, ty;
     if (halo_eligible(srcs, nsrc, Cout)) {
         halo_geometry(Hout, Wout, Cout, &BN, &mt, &tx, &ty);
@@ -304,6 +314,17 @@ int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wo
     return s2s_conv_stat_tiles(Hout, Wout, Cout);
 }
 
+int s2s_conv_stat_tiles_for(const s2s_conv_src* srcs, int nsrc, int Hout, int Wout, int Cout) {
+    // Experiment switch (S2S_EPI_STATS_MINK, default 0 = off): convs with a short GEMM K are bound by their epilogue (the
+    // 128 -> 128 convs at 256^2, K = 1152, take 1.35 ms with the statistics and 0.84 ms without, a separate statistics pass
+    // 0.18 ms), so such layers could answer "no statistics" and let the consumer run s2s_gn_stats.  Measured on one box,
+    // back to back, the whole step / evaluation did not get faster (the extra pass re-reads tensors the epilogue had for
+    // free under the power cap), so the rule is off.
+    int ktot = 0;
+    for (int s = 0; srcs && s < nsrc; ++s) ktot += srcs[s].taps * ((srcs[s].C + kBlockK - 1) / kBlockK) * kBlockK;
+    if (srcs && ktot < epi_stats_min_k()) return 0;
+    return s2s_conv_stat_tiles_geom(srcs, nsrc, Hout, Wout, Cout);
+}
 
 // A 16-bit NHWC tensor seen through arbitrary pixel strides: [B][H][W][C] with strides (sb, sy, sx) in ELEMENTS.  The
 // phase views of an Upsample conv's output (pixels (2y+py, 2x+px)) are such views; so is any dense tensor.
@@ -477,7 +498,7 @@ static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, in
                          int Cout, const float* bias, const void* residual, void* out_bf16, float* out_f32,
                          const float* axpy_x, float axpy_a, float* stats_out, int a_fmt, int w_fmt, int out_fmt,
                          int res_fmt, void* stream, const s2s_conv_norm* norms, int act) {
-    if (stats_out && (!out_bf16 || axpy_x || s2s_conv_stat_tiles_for(srcs, nsrc, Hout, Wout, Cout) == 0))
+    if (stats_out && (!out_bf16 || axpy_x || s2s_conv_stat_tiles_geom(srcs, nsrc, Hout, Wout, Cout) == 0))
         return fail(S2S_ERR_INVALID, "conv_fwd: epilogue statistics need a CTA-pair path (s2s_conv_stat_tiles_for() > 0)");
     if (nsrc < 1 || nsrc > kMaxSeg) return fail(S2S_ERR_INVALID, "conv_fwd: nsrc = %d (1..%d)", nsrc, kMaxSeg);
     if (a_fmt != w_fmt)

@@ -283,6 +283,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 const bool in_img = (py < p.Hout) && (px < p.Wout);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
                 for (int ch = 0; ch < nchunks; ++ch) {
+                    // the residual tile's eight 16-byte vectors are requested BEFORE the accumulator is read: loaded one by
+                    // one inside the conversion loop they cost eight serialised memory latencies per 128x64 chunk, which made the
+                    // epilogue 2-3x longer than the chunk's MMAs (conv2 of the identity-skip ResBlocks: 2.3 ms instead of 0.8 ms)
+                    uint4 rres[8];
+                    const bool has_res = p.residual != nullptr;
+                    if (has_res) {
+                        const int nb = n0 + ch * 64;
+                        const bool ok = in_img;
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            p.residual + (((size_t)b * p.Hout + (ok ? py : 0)) * p.Wout + (ok ? px : 0)) * p.Cout + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rres[j] = ok ? ldg_nc16(rp + j) : make_uint4(0, 0, 0, 0);
+                    }
                     uint32_t v0[32], v1[32];
                     tmem_ld_32x32(t_row + ch * 64, v0);
                     tmem_ld_32x32(t_row + ch * 64 + 32, v1);
@@ -294,11 +307,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         if (lane == 0) mbar_arrive(&tempty[as]);
                     }
                     const int nbase = n0 + ch * 64;
-                    uint32_t packed[32];
-                    const uint4* res = nullptr;
-                    if (p.residual && in_img)
-                        res = reinterpret_cast<const uint4*>(p.residual +
-                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
+                    const bool res = has_res && in_img;
+                    // staging buffer `ob` was last read by the TMA store issued two chunks ago; the converted vectors go
+                    // straight into it (no register copy of the packed tile: the epilogue is register-bound)
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
                         float f[8];
@@ -309,27 +323,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             if (p.bias) f[e] += __ldg(p.bias + nbase + col);
                         }
                         if (res) {
-                            const uint4 r = __ldg(res + j);
+                            const uint4 r = rres[j];
                             float2 t;
                             t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
                             t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
                             t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
                             t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
                         }
-                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
-                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
-                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
-                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
-                    }
-                    // staging buffer `ob` was last read by the TMA store issued two chunks ago
-                    if (et == 0) tma_store_wait_read<1>();
-                    named_bar_sync(1, 128);
-                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
                         const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
-                        *reinterpret_cast<uint4*>(dst + sw * 16) =
-                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                        *reinterpret_cast<uint4*>(dst + sw * 16) = make_uint4(pack2(f[0], f[1], p.out_fmt), pack2(f[2], f[3], p.out_fmt),
+                                                                              pack2(f[4], f[5], p.out_fmt), pack2(f[6], f[7], p.out_fmt));
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);
@@ -566,6 +569,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 const bool in_img = valid && (py < p.Hout) && (px < p.Wout);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
                 for (int ch = 0; ch < nchunks; ++ch) {
+                    // the residual tile's eight 16-byte vectors are requested BEFORE the accumulator is read: loaded one by
+                    // one inside the conversion loop they cost eight serialised memory latencies per 128x64 chunk, which made the
+                    // epilogue 2-3x longer than the chunk's MMAs (conv2 of the identity-skip ResBlocks: 2.3 ms instead of 0.8 ms)
+                    uint4 rres[8];
+                    const bool has_res = p.residual != nullptr;
+                    if (has_res) {
+                        const int nb = n0 + ch * 64;
+                        const bool ok = in_img;
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            p.residual + (((size_t)b * p.Hout + (ok ? py : 0)) * p.Wout + (ok ? px : 0)) * p.Cout + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rres[j] = ok ? ldg_nc16(rp + j) : make_uint4(0, 0, 0, 0);
+                    }
                     uint32_t v0[32], v1[32];
                     tmem_ld_32x32(t_row + ch * 64, v0);
                     tmem_ld_32x32(t_row + ch * 64 + 32, v1);
@@ -576,13 +592,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                         if (lane == 0) mbar_arrive_leader(&tempty[as]);
                     }
                     const int nbase = n0 + ch * 64;
-                    uint32_t packed[32];
-                    const uint4* res = nullptr;
-                    if (p.residual && in_img)
-                        res = reinterpret_cast<const uint4*>(p.residual +
-                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
+                    const bool res = has_res && in_img;
+                    // staging buffer `ob` was last read by the TMA store issued two chunks ago; the converted vectors go
+                    // straight into it (no register copy of the packed tile: the epilogue is register-bound)
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -591,26 +608,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             if (p.bias) f[e] += __ldg(p.bias + nbase + col);
                         }
                         if (res) {
-                            const uint4 r = __ldg(res + j);
+                            const uint4 r = rres[j];
                             float2 t;
                             t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
                             t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
                             t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
                             t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
                         }
-                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
-                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
-                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
-                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
-                    }
-                    if (et == 0) tma_store_wait_read<1>();
-                    named_bar_sync(1, 128);
-                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int sw = j ^ (row & 7);
-                        *reinterpret_cast<uint4*>(dst + sw * 16) =
-                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                        const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
+                        *reinterpret_cast<uint4*>(dst + sw * 16) = make_uint4(pack2(f[0], f[1], p.out_fmt), pack2(f[2], f[3], p.out_fmt),
+                                                                              pack2(f[4], f[5], p.out_fmt), pack2(f[6], f[7], p.out_fmt));
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);
@@ -1084,6 +1091,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                 const bool in_img = valid && (py < p.Hout) && (px < p.Wout);
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MT * BN + h * BN);
                 for (int ch = 0; ch < nchunks; ++ch) {
+                    // the residual tile's eight 16-byte vectors are requested BEFORE the accumulator is read: loaded one by
+                    // one inside the conversion loop they cost eight serialised memory latencies per 128x64 chunk, which made the
+                    // epilogue 2-3x longer than the chunk's MMAs (conv2 of the identity-skip ResBlocks: 2.3 ms instead of 0.8 ms)
+                    uint4 rres[8];
+                    const bool has_res = p.residual != nullptr;
+                    if (has_res) {
+                        const int nb = n0 + ch * 64;
+                        const bool ok = in_img;
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            p.residual + (((size_t)b * p.Hout + (ok ? py : 0)) * p.Wout + (ok ? px : 0)) * p.Cout + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rres[j] = ok ? ldg_nc16(rp + j) : make_uint4(0, 0, 0, 0);
+                    }
                     uint32_t v0[32], v1[32];
                     tmem_ld_32x32(t_row + ch * 64, v0);
                     tmem_ld_32x32(t_row + ch * 64 + 32, v1);
@@ -1094,13 +1114,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                         if (lane == 0) mbar_arrive_leader(&tempty[as]);
                     }
                     const int nbase = n0 + ch * 64;
-                    uint32_t packed[32];
-                    const uint4* res = nullptr;
-                    if (p.residual && in_img)
-                        res = reinterpret_cast<const uint4*>(p.residual +
-                                                             (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase);
+                    const bool res = has_res && in_img;
+                    // staging buffer `ob` was last read by the TMA store issued two chunks ago; the converted vectors go
+                    // straight into it (no register copy of the packed tile: the epilogue is register-bound)
+                    if (et == 0) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 8; ++j) {  // 8 x (8 channels = 16 B)
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -1109,26 +1130,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                             if (p.bias) f[e] += __ldg(p.bias + nbase + col);
                         }
                         if (res) {
-                            const uint4 r = __ldg(res + j);
+                            const uint4 r = rres[j];
                             float2 t;
                             t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
                             t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
                             t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
                             t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
                         }
-                        packed[j * 4 + 0] = pack2(f[0], f[1], p.out_fmt);
-                        packed[j * 4 + 1] = pack2(f[2], f[3], p.out_fmt);
-                        packed[j * 4 + 2] = pack2(f[4], f[5], p.out_fmt);
-                        packed[j * 4 + 3] = pack2(f[6], f[7], p.out_fmt);
-                    }
-                    if (et == 0) tma_store_wait_read<1>();
-                    named_bar_sync(1, 128);
-                    uint8_t* dst = out_stage + ob * kOutStageBytes + row * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int sw = j ^ (row & 7);
-                        *reinterpret_cast<uint4*>(dst + sw * 16) =
-                            make_uint4(packed[j * 4], packed[j * 4 + 1], packed[j * 4 + 2], packed[j * 4 + 3]);
+                        const int sw = j ^ (row & 7);  // 128 B swizzle: 16 B chunk index XOR (row mod 8)
+                        *reinterpret_cast<uint4*>(dst + sw * 16) = make_uint4(pack2(f[0], f[1], p.out_fmt), pack2(f[2], f[3], p.out_fmt),
+                                                                              pack2(f[4], f[5], p.out_fmt), pack2(f[6], f[7], p.out_fmt));
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);

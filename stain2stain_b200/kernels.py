@@ -213,7 +213,9 @@ def conv_fwd(srcs: Sequence[Tuple[torch.Tensor, int, int]], w_packed: torch.Tens
     macs = exec_macs if alg_macs is None else float(alg_macs)
     stats = None
     if want_stats and not out_f32 and axpy_x is None and EPI_STATS:
-        nt = int(_L().s2s_conv_stat_tiles_for(arr, len(srcs), hout, wout, cout))
+        # want_stats == "force": whenever the kernel can emit them (tests); True: unless the conv is epilogue-bound (short K)
+        fn = _L().s2s_conv_stat_tiles_geom if want_stats == "force" else _L().s2s_conv_stat_tiles_for
+        nt = int(fn(arr, len(srcs), hout, wout, cout))
         if nt > 0:
             stats = torch.empty((B, nt, cout, 2), dtype=torch.float32, device=dev)
     if norms is not None:

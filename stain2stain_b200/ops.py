@@ -870,6 +870,7 @@ class ResBlockCfg:
     groups: int = 32
     eps: float = 1e-5
     plan1_multi: Optional[ConvPlan] = None  # inference: conv 1 over the RAW sources, one 3x3 segment per source
+    plan2_id: Optional[ConvPlan] = None     # identity skip as a 1x1 GEMM segment with the identity matrix (see _identity_weight)
 
 
 # test hook: when a list, every training-mode ResBlock appends its dropout keep bits (uint8 [B,H,W,C/8], bit j of byte
@@ -883,6 +884,21 @@ def _wgrad_to(d_out, x_g, taps: int, stride: int, d_w_view, n_begin: int):
     dw = torch.zeros((taps, cout, cq), dtype=torch.float32, device=d_out.device)
     K.conv_wgrad(d_out, x_g, taps, stride, dw)
     K.unpack_wgrad(dw, d_w_view, 0, cq, n_begin, 0.0)
+
+
+_EYES: Dict[tuple, torch.Tensor] = {}
+
+
+def _identity_weight(c: int, device) -> torch.Tensor:
+    """fp32 [C, C, 1, 1] identity "conv weight".  An identity skip `x + h` is run as one more 1x1 GEMM segment of conv 2 over the
+    raw block input with this matrix: 1.0 and 0.0 are exact in the 16-bit operand format and the products accumulate in fp32,
+    so the result equals adding x in the epilogue up to fp32 summation order -- but the epilogue's pixel-strided 16-byte residual loads made
+    conv 2 of the 128-channel 256^2 blocks take 2.0-2.3 ms instead of 0.85 ms, while the extra segment costs +11 % MMAs."""
+    key = (c, str(device))
+    eye = _EYES.get(key)
+    if eye is None:
+        eye = _EYES[key] = torch.eye(c, dtype=torch.float32, device=device).reshape(c, c, 1, 1).contiguous()
+    return eye
 
 
 class _ResBlockFn(torch.autograd.Function):
@@ -968,6 +984,12 @@ class _ResBlockFn(torch.autograd.Function):
             out, out_stats = K.conv_fwd([(a2, 9, 1)] + [(s, 1, 1) for s in srcs], wp, cout, H, W, bias=bias,
                                         want_stats=True,
                                         norms=None if norms2 is None else norms2 + [None] * len(srcs))
+        elif cfg.plan2_id is not None:
+            assert n_src == 1 and ctot == cout
+            wp = cfg.plan2_id.packed_fwd([c2w, _identity_weight(cout, dev)])
+            out, out_stats = K.conv_fwd([(a2, 9, 1), (srcs[0], 1, 1)], wp, cout, H, W, bias=c2b.detach(), want_stats=True,
+                                        norms=None if norms2 is None else norms2 + [None],
+                                        alg_macs=float(B) * H * W * cout * cout * 9)
         else:
             assert n_src == 1 and ctot == cout
             out, out_stats = K.conv_fwd([(a2, 9, 1)], cfg.plan2.packed_fwd([c2w]), cout, H, W, bias=c2b.detach(),

@@ -143,6 +143,8 @@ class ResBlock(TimestepBlock):
         self.skip_connection = nn.Identity() if oc == channels else nn.Conv2d(channels, oc, 1)
         self._plan1 = ConvPlan((Seg(0, 0, 0, channels, 9, 1),), oc)
         self._plan2 = ConvPlan((Seg(0, 0, 0, oc, 9, 1),), oc)
+        # identity skip as a GEMM segment: weight 1 = the constant identity matrix (ops._identity_weight)
+        self._plan2_id = ConvPlan((Seg(0, 0, 0, oc, 9, 1), Seg(1, 1, 0, oc, 1, 1)), oc) if oc == channels else None
         self._skip_plans = {}
         self._cfgs = {}
 
@@ -172,7 +174,8 @@ class ResBlock(TimestepBlock):
                 segs.append(Seg(i, 0, off, w, 9, 1))
                 off += w
             cfg = self._cfgs[widths] = ops.ResBlockCfg(self._plan1, self._plan2_skip(widths) if has_skip else self._plan2,
-                                                       has_skip, plan1_multi=ConvPlan(tuple(segs), self.out_channels))
+                                                       has_skip, plan1_multi=ConvPlan(tuple(segs), self.out_channels),
+                                                       plan2_id=None if has_skip else self._plan2_id)
         params = [gn1.weight, gn1.bias, conv1.weight, conv1.bias, gn2.weight, gn2.bias, conv2.weight, conv2.bias]
         if has_skip:
             params += [self.skip_connection.weight, self.skip_connection.bias]
