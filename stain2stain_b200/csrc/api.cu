@@ -96,6 +96,19 @@ int conv_halo() {  // S2S_CONV_HALO: 0 = off, 1 = halo-tiled A operand (matrix b
     return v;
 }
 
+// Largest GEMM K for which a launch without statistics writes its output with plain 16-byte stores from registers instead of
+// the shared-memory tile + TMA store (S2S_CONV_DIRECT_MAXK; 0 = never).  Short-K launches are bound by their epilogue and the
+// register path removes its barriers and the TMA round trip (1x1 skip-conv dgrad 128 -> 128 at 256^2, B = 64: 0.775 -> 0.546
+// ms); MMA-bound launches get slower with it (pixel-strided stores: the 3x3 dgrad 0.84 -> 0.92 ms), hence the limit.
+int conv_direct_max_k() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_CONV_DIRECT_MAXK");
+        v = e ? atoi(e) : 640;
+    }
+    return v;
+}
+
 int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -412,6 +425,9 @@ static int halo_launch(const HaloSeg* segs, int nseg, const ActView& outv, const
     q.stats = (float2*)stats_out;
     q.stat_tiles = stat_tiles_total > 0 ? stat_tiles_total : tx3 * ty3 * mt3;
     q.stat_off = stat_off;
+    const bool dense_out = outv.sx == Cout && outv.sy == (long long)Wout * Cout && outv.sb == (long long)Hout * Wout * Cout;
+    q.out_direct = (!stats_out && dense_out && (kb3 - kb_first) * kBlockK <= conv_direct_max_k())
+                       ? (uint16_t*)const_cast<void*>(outv.base) : nullptr;
     if (norms) {
         q.prologue = 1;
         q.act = act;
@@ -561,6 +577,7 @@ static int conv_fwd_impl(const s2s_conv_src* srcs, int nsrc, int B, int Hout, in
         q.tiles_y = tiles_y2;
         q.m_tiles = B * q.tiles_x * q.tiles_y;
         q.stats = (float2*)stats_out;
+        q.out_direct = (!stats_out && Ktot <= conv_direct_max_k()) ? (uint16_t*)out_bf16 : nullptr;
         q.stat_tiles = tiles_x2 * tiles_y2 * mt2;
         q.m_pairs = (q.m_tiles + 1) / 2;
         q.n_tiles_n = Cout / BN2;

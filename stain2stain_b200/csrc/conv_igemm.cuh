@@ -380,6 +380,7 @@ struct Conv2Params {
     uint32_t tmem_cols;
     const float* bias;
     const __nv_bfloat16* residual;
+    uint16_t* out_direct;  // non-null: dense NHWC output written with plain 16-byte stores (launches without statistics)
     float2* stats;  // optional [B][stat_tiles][Cout] (sum, sumsq) of the STORED 16-bit outputs per 128-pixel sub-tile:
                     // the GroupNorm statistics of the consumer, taken from the epilogue's staging tile (no extra pass)
     int stat_tiles;
@@ -593,6 +594,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     }
                     const int nbase = n0 + ch * 64;
                     const bool res = has_res && in_img;
+                    if (p.out_direct != nullptr) {
+                        // Launches that need no statistics and write a dense tensor (every dgrad conv, the 1x1 GEMMs) store
+                        // their pixel row straight from registers: 8 x 16 B = the thread's own 128-byte line.  No staging
+                        // tile, no named barriers, no TMA store to wait for -- the four epilogue warps run independently.
+                        // (Through shared memory + TMA the epilogue took ~2800 cycles per 128 x 64 chunk, so every conv with
+                        // K < 1400 was bound by it: the 1x1 skip-conv dgrads ran at 177 TFLOP/s.)
+                        if (in_img) {
+                            uint4* o = reinterpret_cast<uint4*>(p.out_direct + ((((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float f[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int col = j * 8 + e;
+                                    f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                                    if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                                }
+                                if (res) {
+                                    const uint4 r = rres[j];
+                                    float2 t;
+                                    t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                                    t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                                    t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                                    t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
+                                }
+                                o[j] = make_uint4(pack2(f[0], f[1], p.out_fmt), pack2(f[2], f[3], p.out_fmt),
+                                                  pack2(f[4], f[5], p.out_fmt), pack2(f[6], f[7], p.out_fmt));
+                            }
+                        }
+                        continue;
+                    }
                     // staging buffer `ob` was last read by the TMA store issued two chunks ago; the converted vectors go
                     // straight into it (no register copy of the packed tile: the epilogue is register-bound)
                     if (et == 0) tma_store_wait_read<1>();
@@ -725,6 +757,7 @@ struct Conv3Params {
                                // every tap's A descriptor is 1024 B aligned with an 8-row-group stride of exactly 1024 B
     const float* bias;
     const __nv_bfloat16* residual;
+    uint16_t* out_direct;      // non-null: dense NHWC output written with plain 16-byte stores (launches without statistics)
     float2* stats;             // optional per-sub-tile (sum, sumsq) of the stored outputs, as in Conv2Params
     int stat_tiles, stat_off;  // sub-tiles per sample in the statistics buffer; first sub-tile this launch writes (the four
                                // phase launches of an Upsample conv fill one buffer)
@@ -1115,6 +1148,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
                     }
                     const int nbase = n0 + ch * 64;
                     const bool res = has_res && in_img;
+                    if (p.out_direct != nullptr) {
+                        // Launches that need no statistics and write a dense tensor (every dgrad conv, the 1x1 GEMMs) store
+                        // their pixel row straight from registers: 8 x 16 B = the thread's own 128-byte line.  No staging
+                        // tile, no named barriers, no TMA store to wait for -- the four epilogue warps run independently.
+                        // (Through shared memory + TMA the epilogue took ~2800 cycles per 128 x 64 chunk, so every conv with
+                        // K < 1400 was bound by it: the 1x1 skip-conv dgrads ran at 177 TFLOP/s.)
+                        if (in_img) {
+                            uint4* o = reinterpret_cast<uint4*>(p.out_direct + ((((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + nbase));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float f[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int col = j * 8 + e;
+                                    f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                                    if (p.bias) f[e] += __ldg(p.bias + nbase + col);
+                                }
+                                if (res) {
+                                    const uint4 r = rres[j];
+                                    float2 t;
+                                    t = unpack2(r.x, p.res_fmt); f[0] += t.x; f[1] += t.y;
+                                    t = unpack2(r.y, p.res_fmt); f[2] += t.x; f[3] += t.y;
+                                    t = unpack2(r.z, p.res_fmt); f[4] += t.x; f[5] += t.y;
+                                    t = unpack2(r.w, p.res_fmt); f[6] += t.x; f[7] += t.y;
+                                }
+                                o[j] = make_uint4(pack2(f[0], f[1], p.out_fmt), pack2(f[2], f[3], p.out_fmt),
+                                                  pack2(f[4], f[5], p.out_fmt), pack2(f[6], f[7], p.out_fmt));
+                            }
+                        }
+                        continue;
+                    }
                     // staging buffer `ob` was last read by the TMA store issued two chunks ago; the converted vectors go
                     // straight into it (no register copy of the packed tile: the epilogue is register-bound)
                     if (et == 0) tma_store_wait_read<1>();
