@@ -3,7 +3,8 @@
 
 `sample_location_and_conditional_flow(x0, x1, t=None, return_noise=False)` keeps torchcfm's semantics:
 t ~ U(0,1)^B drawn from the CPU default generator and moved, eps ~ N(0, I) drawn on x0's device even when sigma = 0
-(it advances the device RNG exactly like the reference), xt = t x1 + (1-t) x0 + sigma eps, ut = x1 - x0.
+(THIS method advances the device RNG exactly like the reference; the LitModules' fused sigma == 0 training path does not
+call it and draws no eps -- see lit.py), xt = t x1 + (1-t) x0 + sigma eps, ut = x1 - x0.
 The LitModule's training path does not materialise xt/ut at all (they are fused into the stem operand packing and the
 loss kernel); this class exists for API compatibility and for user code that calls it directly.
 """

@@ -7,6 +7,11 @@
 `model_step` = FM sample -> net -> MSE (reference :53-74).  When `net` is this package's UNet and sigma == 0 the
 interpolation `xt = (1-t) x0 + t x1` is fused into the stem's operand packing and `ut = x1 - x0`, the MSE and its
 gradient into one loss kernel; otherwise the generic (reference-shaped) path runs on whatever `net` was given.
+RNG note: torchcfm draws `eps = randn_like(x0)` even when sigma == 0 (it multiplies it by 0); the fused path does not, so
+after a fused `model_step` the DEVICE generator is one `randn` behind the reference's.  `t` -- the only random input of the
+sigma == 0 step -- comes from the CPU default generator exactly as in the reference (`torch.rand(B)`), so losses match for
+equal seeds; code that draws further device randoms afterwards (none on the reference's path) would see a shifted stream.
+Dropout masks come from the engine's own counter-based generator in any case.
 `generate` integrates with `NeuralODE` exactly as the reference does (solver/atol/rtol taken from `self.solver` with
 the same `hasattr` fallbacks, :157-163); `solver="euler"` selects the CUDA-graph fused Euler sampler.
 
@@ -169,7 +174,12 @@ class ConditionalWrapper(nn.Module):
         self.y = y
 
     def forward(self, t, x, **kwargs):
-        return self.model(t, x, y=self.y)
+        # reference :168-173: a 0-dim label broadcasts, a longer label vector is cut to the batch
+        n = x.shape[0]
+        y = self.y.expand(n) if self.y.dim() == 0 else self.y
+        if y.shape[0] != n:
+            y = y[:n]
+        return self.model(t, x, y=y)
 
 
 class ClassConditionalFlowMatchingLitModule(ConditionalFlowMatchingLitModule):

@@ -219,21 +219,23 @@ class NeuralODE(nn.Module):
         self.return_t_eval = return_t_eval
         self.use_cuda_graph = use_cuda_graph
 
-    def _fast(self, t_span):
+    def _fast(self, t_span, x=None):
         net, y, mask = _unwrap_vector_field(self.vf)
         ok = net is not None and self.solver == "euler" and not net.training and _is_uniform(t_span)
+        if ok and y is not None and x is not None and tuple(y.shape) != (x.shape[0],):
+            ok = False  # a wrapper that broadcasts / truncates its labels per call: let it (generic path)
         return (net, y, mask) if ok else (None, None, None)
 
     @torch.no_grad()
     def final_state(self, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
         """State at t_span[-1] without materialising the trajectory (what `generate` actually needs)."""
-        net, y, mask = self._fast(t_span)
+        net, y, mask = self._fast(t_span, x)
         if net is not None:
             return fused_euler(net, x, t_span, y, None, self.use_cuda_graph, extra=mask)
         return self.trajectory(x, t_span)[-1]
 
     def trajectory(self, x: torch.Tensor, t_span: torch.Tensor) -> torch.Tensor:
-        net, y, mask = self._fast(t_span)
+        net, y, mask = self._fast(t_span, x)
         if net is not None and not torch.is_grad_enabled():
             rec = [x.float().clone()]
             fused_euler(net, x, t_span, y, rec, self.use_cuda_graph, extra=mask)

@@ -311,3 +311,29 @@ def test_hydra_lite_composes_the_reference_experiment_tree():
     from stain2stain_b200.unet import UNetModel
     assert isinstance(lit, ConditionalFlowMatchingLitModule) and isinstance(lit.net, UNetModel)
     assert sum(p.numel() for p in lit.net.parameters()) == 70_954_883
+
+
+def test_invalidate_caches_clears_operands_and_graphs():
+    import stain2stain_b200
+    from stain2stain_b200 import neural_ode, ops
+    ops.PACK_CACHE._store[("x",)] = [None, None, [], []]
+    stain2stain_b200.invalidate_caches()
+    assert not ops.PACK_CACHE._store and len(neural_ode._GRAPHS) == 0
+
+
+def test_conditional_wrapper_label_broadcast_and_truncation():
+    """reference class_conditional_flow_matching.py:168-173"""
+    import torch
+    from stain2stain_b200.lit import ConditionalWrapper
+    seen = {}
+
+    class Net(torch.nn.Module):
+        def forward(self, t, x, y=None):
+            seen["y"] = y
+            return x
+    w = ConditionalWrapper(Net(), torch.tensor(2))
+    w(torch.zeros(()), torch.zeros(3, 1))
+    assert seen["y"].tolist() == [2, 2, 2]
+    w = ConditionalWrapper(Net(), torch.tensor([0, 1, 2, 1]))
+    w(torch.zeros(()), torch.zeros(2, 1))
+    assert seen["y"].tolist() == [0, 1]
