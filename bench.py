@@ -26,6 +26,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv and "--impl" in sys.argv:
+    # the CPU arm may use every host core: torch.distributed.run exports OMP_NUM_THREADS=1 to its ranks, and the OpenMP /
+    # MKL runtimes size their pools from the environment when torch is imported -- so undo it BEFORE the import
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
