@@ -80,8 +80,11 @@ def bench_wgrad(B, iters, out):
         del x, dy
 
 
+GN_SHAPES = [(128, 256), (256, 128), (384, 256), (512, 32)]
+
+
 def bench_gn(B, iters, out):
-    for C, H in [(128, 256), (256, 128), (384, 256), (512, 32)]:
+    for C, H in GN_SHAPES:
         HW = H * H
         x = rnd16((B, H, H, C), K.ACT)
         g = rnd16((B, H, H, C), K.GRAD)
@@ -141,9 +144,12 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--gn-shapes", default=None, help="CxH[,CxH...] for the gn group, e.g. 128x256,256x128")
     a = ap.parse_args()
-    global ONCE
+    global ONCE, GN_SHAPES
     ONCE = a.once
+    if a.gn_shapes:
+        GN_SHAPES = [tuple(int(v) for v in t.split("x")) for t in a.gn_shapes.split(",")]
     out = []
     if "conv" in a.what:
         bench_conv(a.batch, a.iters, out)

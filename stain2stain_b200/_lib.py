@@ -126,6 +126,11 @@ def load(build_if_missing: bool = True):
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
+    override = os.environ.get("S2S_LIB_PATH")  # same-box A/B of two builds (scripts/gpu_ab_lib.sh); never set in production
+    if override:
+        if not os.path.exists(override):
+            raise S2SError(f"S2S_LIB_PATH={override} does not exist")
+        path, build_if_missing = override, False
     if build_if_missing and _build.needs_build():
         try:
             _build.build()

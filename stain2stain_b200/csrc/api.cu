@@ -223,6 +223,17 @@ int ew_grid(long long work_items, int threads = kEwThreads) {
 // (register-bound), so the grid B x chunks is made a multiple of 148 * lcm(2,3,4) = 1776 CTAs whenever the tensor is
 // big enough: every wave is full and there is no tail wave (a 2.05-wave grid costs 3 waves).  Depends on (B, HW) only,
 // so that every source of a channel concat is cut into the same pixel chunks (their partial statistics line up).
+// A CTA is never given fewer than 256 pixels (128 below 64^2): with the 111 chunks the wave rule asks for at B = 64, a
+// 64^2 sample was cut into 37-pixel CTAs whose life is one latency chain (coefficients -> loads -> stores) -- 0.29-0.58
+// of the HBM rate at 64^2 / 32^2 against 0.64-0.82 with fat CTAs (profiles/r02_kbench_gn_min_ppc.txt).
+int gn_min_ppc() {  // S2S_GN_MIN_PPC: fewest pixels a CTA of the normalisation kernels is given (experiments)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_GN_MIN_PPC");
+        v = e ? atoi(e) : 0;  // 0 = the measured default below
+    }
+    return v;
+}
 int pick_pix_per_cta(int B, int HW, int /*C*/) {
     const long long wave = (long long)num_sms() * 12;
     long long a = B, b = wave;
@@ -230,6 +241,9 @@ int pick_pix_per_cta(int B, int HW, int /*C*/) {
     const long long base = wave / a;                  // smallest chunk count with (B * chunks) % wave == 0
     long long k = (2 * wave + (long long)B * base - 1) / ((long long)B * base);  // aim at >= 2 * wave CTAs in total
     long long chunks = base * (k < 1 ? 1 : k);
+    const int min_ppc = gn_min_ppc() > 0 ? gn_min_ppc() : (HW >= 4096 ? 256 : 128);
+    const long long max_chunks = HW / min_ppc < 1 ? 1 : HW / min_ppc;
+    if (chunks > max_chunks) chunks = max_chunks;
     long long ppc = (HW + chunks - 1) / chunks;
     if (ppc < 32) ppc = 32;  // tiny tensors: launch latency dominates, keep some work per CTA
     if (ppc > HW) ppc = HW;
@@ -792,7 +806,7 @@ int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev
 
 int s2s_unpack_wgrad(const float* dw, int taps, int M, int ldn, int n_off, int n_count, float* grad, int Cin_total,
                      int n_begin, float beta, void* stream) {
-    const long long total = (long long)M * n_count * taps;
+    const long long total = (long long)M * n_count;  // one thread per (m, n), all taps
     unpack_wgrad_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(dw, taps, M, ldn, n_off, n_count, grad,
                                                                                   Cin_total, n_begin, beta);
     LAUNCH_CHECK("unpack_wgrad_kernel");
@@ -1021,11 +1035,11 @@ int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
-        (gn_bwd_reduce_kernel<SILU, DROP, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(x_bf16_out != nullptr, X16, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+        (gn_bwd_reduce_kernel<SILU, DROP, XF, GF, X16><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
             (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in,
-            (__nv_bfloat16*)x_bf16_out))))));
+            (__nv_bfloat16*)x_bf16_out)))))));
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
 }
@@ -1040,10 +1054,20 @@ int s2s_gn_bwd_reduce(const void* x, const void* g, int ld_g, int B, int HW, int
 int s2s_gn_bwd_coef(const float* red_part, float* red, const float* mean_rstd, const float* gamma, const float* beta,
                     const float* film, int B, int C, int G, int HW, float* pqr, float* dgamma, float* dbeta,
                     float* dfilm, void* stream) {
-    if (G > 64 || C % G) return fail(S2S_ERR_INVALID, "gn_bwd_coef: G = %d, C = %d unsupported", G, C);
-    gn_bwd_coef_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float2*)red_part, s2s_gn_chunks(B, HW), (float2*)red,
-                                                            (const float2*)mean_rstd, gamma, beta, film, C, G, HW,
-                                                            (float4*)pqr, dgamma, dbeta, dfilm);
+    if (G > 64 || C % G || (C & 1)) return fail(S2S_ERR_INVALID, "gn_bwd_coef: G = %d, C = %d unsupported", G, C);
+    if (C > 4096) return fail(S2S_ERR_INVALID, "gn_bwd_coef: C = %d unsupported (<= 4096)", C);
+    const int nchunks = s2s_gn_chunks(B, HW);
+    const int threads = 1024;
+    int slices = threads / (C / 2);
+    if (slices < 1) slices = 1;
+    if (slices > 16) slices = 16;
+    if (slices > nchunks) slices = nchunks;
+    const size_t smem = (size_t)(2 * C) * (1 + slices) * sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(gn_bwd_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gn_bwd_coef_kernel<<<B, threads, smem, (cudaStream_t)stream>>>((const float2*)red_part, nchunks, (float2*)red,
+                                                                   (const float2*)mean_rstd, gamma, beta, film, C, G, HW,
+                                                                   (float4*)pqr, dgamma, dbeta, dfilm, slices);
     LAUNCH_CHECK("gn_bwd_coef_kernel");
     return S2S_OK;
 }

@@ -290,8 +290,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(v);
+    // exact: a bf16 is the upper half of an fp32.  One shift + one mask (the __bfloat1622float2 intrinsic compiles to
+    // PRMT + SHF for the high element: 3 ops per pair in kernels that sit next to the instruction-issue roofline)
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {  // saturating: never produces inf
     uint32_t r;
@@ -323,6 +324,13 @@ __device__ __forceinline__ float silu_f(float z) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(z * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
     return z * r;
+}
+// k * silu(z) from zs = k z:  zs / (1 + 2^(zs * c)),  c = -log2(e) / k   (c = -log2 e: plain silu)
+__device__ __forceinline__ float silu_scaled_f(float zs, float c) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(zs * c));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return zs * r;
 }
 __device__ __forceinline__ float silu_grad_f(float z) {
     float s = 1.0f / (1.0f + __expf(-z));

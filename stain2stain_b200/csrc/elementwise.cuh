@@ -6,6 +6,8 @@
 // (t / vpp) + blockDim / vpp, ... of its CTA's pixel chunk: warps touch whole contiguous pixel rows (coalesced), and
 // the per-channel coefficients of the thread's 8 channels stay in registers for the whole chunk.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace s2s {
@@ -76,7 +78,7 @@ __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t
     }
     return make_uint4(c0, c1, c2, c3);
 }
-__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return min((uint32_t)(p * 65536.0f + 0.5f), 65535u); }
 // keep-mask bits for 8 consecutive elements starting at element index e8*8 (bit j = keep element j)
 __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsigned long long e8, uint32_t thresh16) {
     const uint4 r = philox4x32_7((uint32_t)e8, (uint32_t)(e8 >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -85,6 +87,25 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsig
     m |= ((r.y & 0xffffu) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
     m |= ((r.z & 0xffffu) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
     m |= ((r.w & 0xffffu) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
+    return m;
+}
+
+// the same keep bits, applied to 8 fp32 values on the way (the compare predicates select the values directly; building
+// the byte first and testing its bits again costs two more integer ops per element)
+__device__ __forceinline__ uint32_t dropout_apply8(unsigned long long seed, unsigned long long e8, uint32_t thresh16,
+                                                   float (&f)[8]) {
+    const uint4 r = philox4x32_7((uint32_t)e8, (uint32_t)(e8 >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // high lane: w >= T * 2^16  <=>  (w >> 16) >= T exactly, no extraction; T <= 65535 here (p < 1)
+        const bool k0 = (w[j] & 0xffffu) >= thresh16, k1 = w[j] >= (thresh16 << 16);
+        f[2 * j] = k0 ? f[2 * j] : 0.f;
+        f[2 * j + 1] = k1 ? f[2 * j + 1] : 0.f;
+        m |= (k0 ? 1u : 0u) << (2 * j);
+        m |= (k1 ? 1u : 0u) << (2 * j + 1);
+    }
     return m;
 }
 
@@ -182,16 +203,28 @@ __global__ void upconv_unpack_wgrad_kernel(const float* __restrict__ src, int M,
 }
 
 // [taps][M][ldn] fp32 wgrad buffer -> += into OIHW fp32 gradient.  dst[m][n_begin + n][tap] += src[tap][m][n_off + n]
+// One thread per (m, n): its `taps` reads are coalesced across the warp (n fastest), its `taps` consecutive floats of the
+// OIHW row join the neighbours' into one contiguous run per warp.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int taps, int M, int ldn, int n_off, int n_count,
                                     float* __restrict__ grad, int Cin_total, int n_begin, float beta) {
-    const long long total = (long long)M * n_count * taps;
+    const long long total = (long long)M * n_count;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % taps);
-        const int n = (int)((i / taps) % n_count);
-        const int m = (int)(i / ((long long)taps * n_count));
-        const float v = src[((size_t)tap * M + m) * ldn + n_off + n];
-        float* g = grad + ((size_t)m * Cin_total + n_begin + n) * taps + tap;
-        *g = (beta == 0.f) ? v : fmaf(beta, *g, v);  // beta == 0: the destination may be uninitialised (NaN bit patterns)
+        const int n = (int)(i % n_count);
+        const int m = (int)(i / n_count);
+        float* g = grad + ((size_t)m * Cin_total + n_begin + n) * taps;
+        const float* sp = src + (size_t)m * ldn + n_off + n;
+        if (taps == 9) {
+            float v[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) v[t] = sp[(size_t)t * M * ldn];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) g[t] = (beta == 0.f) ? v[t] : fmaf(beta, g[t], v[t]);
+        } else {
+            for (int t = 0; t < taps; ++t) {
+                const float v = sp[(size_t)t * M * ldn];
+                g[t] = (beta == 0.f) ? v : fmaf(beta, g[t], v);  // beta == 0: the destination may be uninitialised
+            }
+        }
     }
 }
 
@@ -240,6 +273,28 @@ __global__ void patch27_pack_kernel(const float* __restrict__ x0, const float* _
         for (int j = 4; j < 8; ++j) d[j] = z;
     }
 }
+
+// Addressing of the streaming loops.  A thread walks pixels p, p + pstep, ... of its CTA's chunk at a fixed vector slot, so
+// every tensor is ONE byte pointer advanced by a constant step (2 integer ops per tensor and iteration instead of a 64-bit
+// multiply-add chain per access: these kernels sit next to the instruction-issue roofline once the SM clock drops under
+// the power cap of a training step).  kFull (blockDim.x == 256 and every tensor has row length C): the thread's next pixel
+// row is a COMPILE-TIME 256 vectors = 4096 B away (its keep byte 256 B), so the second access of an unrolled iteration is
+// an immediate offset of the same pointer.
+constexpr int kRowStepBytes = kEwThreads * 16;
+template <bool kFull>
+__device__ __forceinline__ const char* row_next(const char* q, size_t step) {
+    return kFull ? q + kRowStepBytes : q + step;
+}
+template <bool kFull>
+__device__ __forceinline__ char* row_next(char* q, size_t step) {
+    return kFull ? q + kRowStepBytes : q + step;
+}
+template <bool kFull>
+__device__ __forceinline__ const uint8_t* mask_next(const uint8_t* q, size_t step) {
+    return kFull ? q + kEwThreads : q + step;
+}
+__device__ __forceinline__ uint4 ldg_stream_b(const char* q) { return ldg_stream(reinterpret_cast<const uint4*>(q)); }
+__device__ __forceinline__ void stg_stream_b(char* q, const uint4& v) { stg_stream(reinterpret_cast<uint4*>(q), v); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
 constexpr int kGnUnroll = 4;
@@ -468,47 +523,74 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
+    // dropout: the 1/(1-p) factor of the kept elements is folded into the affine coefficients (act(z) * k = zs * sigmoid(zs / k)
+    // for SiLU with zs = k z -- only the exponent's constant changes --, relu / identity commute with k > 0): no multiply
+    // per element behind the activation
+    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
+    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
+    const float silu_c = kDrop ? -1.4426950408889634f * (1.f - drop_p) : -1.4426950408889634f;
     float A[8], Bc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const float2 cf = coef[(size_t)b * Ctot + c_off + slot * 8 + e];
-        A[e] = cf.x;
-        Bc[e] = cf.y;
+        A[e] = cf.x * keep_scale;
+        Bc[e] = cf.y * keep_scale;
     }
-    const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
-    __nv_bfloat16* dst = y + (size_t)b * HW * ld_out + c_off + slot * 8;
-    __nv_bfloat16* dst2 = kDual ? y2 + (size_t)b * HW * ld_out + c_off + slot * 8 : nullptr;
-    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
-    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_out >> 3) +
                                        (unsigned long long)((c_off >> 3) + slot);
-    auto body = [&](const uint4& u, int p) {
-        float f[8];
-        cvt8_in_t<XF>(u, f);
+    // one byte pointer per tensor, advanced by a constant step; kFull: the unrolled accesses are immediate offsets
+    // (see row_next)
+    auto run = [&](auto full_c) {
+        constexpr bool kFull = decltype(full_c)::value;
+        const size_t pix0 = (size_t)b * HW + (size_t)(p0 + prow);
+        const char* xp = reinterpret_cast<const char*>(x) + (pix0 * C + slot * 8) * 2;
+        char* yp = reinterpret_cast<char*>(y) + (pix0 * ld_out + c_off + slot * 8) * 2;
+        char* y2p = kDual ? reinterpret_cast<char*>(y2) + (pix0 * ld_out + c_off + slot * 8) * 2 : nullptr;
+        const size_t sx = (size_t)pstep * C * 2, sy = (size_t)pstep * ld_out * 2;
+        unsigned long long e8 = e8_base + (unsigned long long)(p0 + prow) * (unsigned long long)(ld_out >> 3);
+        const unsigned long long se8 = (unsigned long long)pstep * (unsigned long long)(ld_out >> 3);
+        auto body = [&](const uint4& u, char* dst, char* dst2) {
+            float f[8];
+            cvt8_in_t<XF>(u, f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float z = fmaf(f[e], A[e], Bc[e]);
-            f[e] = kAct == kActSilu ? silu_f(z) : (kAct == kActRelu ? fmaxf(z, 0.f) : z);
-        }
-        if (kDrop) {
-            const unsigned long long e8 = e8_base + (unsigned long long)p * (unsigned long long)(ld_out >> 3);
-            const uint32_t m = dropout_keep8(seed, e8, thresh);
-            if (mask_out != nullptr) mask_out[e8] = (uint8_t)m;  // 1 bit / element: backward reads it instead of re-hashing
+            for (int e = 0; e < 8; ++e) {
+                const float z = fmaf(f[e], A[e], Bc[e]);  // kDrop: z * 1/(1-p), see the coefficient load
+                f[e] = kAct == kActSilu ? silu_scaled_f(z, silu_c) : (kAct == kActRelu ? fmaxf(z, 0.f) : z);
+            }
+            if (kDrop) {
+                const uint32_t m = dropout_apply8(seed, e8, thresh, f);
+                if (mask_out != nullptr) mask_out[e8] = (uint8_t)m;  // 1 bit / element: backward reads it instead of re-hashing
+                e8 += se8;
+            }
+            stg_stream_b(dst, cvt8_out_t<YF>(f));
+            if (kDual) stg_stream_b(dst2, cvt8_out_t<kFmtBF16>(f));
+        };
+        int p = p0 + prow;
+        for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {
+            uint4 u[kGnUnroll];
+            const char* q = xp;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1u) ? f[e] * keep_scale : 0.f;
+            for (int i = 0; i < kGnUnroll; ++i) {
+                u[i] = ldg_stream_b(q);
+                q = row_next<kFull>(q, sx);
+            }
+            xp = q;
+#pragma unroll
+            for (int i = 0; i < kGnUnroll; ++i) {
+                body(u[i], yp, y2p);
+                yp = row_next<kFull>(yp, sy);
+                if (kDual) y2p = row_next<kFull>(y2p, sy);
+            }
         }
-        stg_stream(reinterpret_cast<uint4*>(dst + (size_t)p * ld_out), cvt8_out_t<YF>(f));
-        if (kDual) stg_stream(reinterpret_cast<uint4*>(dst2 + (size_t)p * ld_out), cvt8_out_t<kFmtBF16>(f));
+        for (; p < p1; p += pstep) {
+            body(ldg_stream_b(xp), yp, y2p);
+            xp = row_next<kFull>(xp, sx);
+            yp = row_next<kFull>(yp, sy);
+            if (kDual) y2p = row_next<kFull>(y2p, sy);
+        }
     };
-    int p = p0 + prow;
-    for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {
-        uint4 u[kGnUnroll];
-#pragma unroll
-        for (int i = 0; i < kGnUnroll; ++i) u[i] = ldg_stream(src + (size_t)(p + i * pstep) * vpp + slot);
-#pragma unroll
-        for (int i = 0; i < kGnUnroll; ++i) body(u[i], p + i * pstep);
-    }
-    for (; p < p1; p += pstep) body(ldg_stream(src + (size_t)p * vpp + slot), p);
+    if (blockDim.x == kEwThreads && ld_out == C) run(std::true_type{});
+    else run(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm backward
@@ -517,9 +599,9 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
 // forward keeps the two-MUFU exact form because its result is stored with an 11-bit significand.
 // Pass 1 (this kernel): per chunk, (sum_p dz, sum_p dz * xhat) with xhat = (x - mean_g) * rstd_g, accumulated as
 // (sum dz, sum dz*x) in the streaming loop and centred once per channel at the end.
-// Per-thread channel coefficients of z = x*A + Bc.  fp16 activations: held as 4 half2 pairs (z and silu' are then
-// evaluated with packed half2 arithmetic and ONE tanh.approx.f16x2 per two elements -- z only feeds silu', whose
-// result multiplies a bf16 gradient, so 11 significant bits are ample); otherwise 8 + 8 fp32 values.
+// Per-thread channel coefficients of z = x*A + Bc.  fp16 activations: held as 4 half2 pairs of (A/2, Bc/2) (u = z/2 and
+// silu' are then evaluated with packed half2 arithmetic and ONE tanh.approx.f16x2 per two elements -- z only feeds silu',
+// whose result multiplies a bf16 gradient, so 11 significant bits are ample); otherwise 8 + 8 fp32 values.
 template <bool kHalf>
 struct GnZCoef {
     float A[8], Bc[8];
@@ -534,13 +616,13 @@ struct GnZCoef {
 };
 template <>
 struct GnZCoef<true> {
-    __half2 A[4], Bc[4];
+    __half2 A[4], Bc[4];  // halved: u = x * (A/2) + Bc/2 = z/2 (exact scaling by a power of two)
     __device__ __forceinline__ void load(const float2* __restrict__ cf) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float2 c0 = cf[2 * e], c1 = cf[2 * e + 1];
-            A[e] = __floats2half2_rn(c0.x, c1.x);
-            Bc[e] = __floats2half2_rn(c0.y, c1.y);
+            A[e] = __floats2half2_rn(0.5f * c0.x, 0.5f * c1.x);
+            Bc[e] = __floats2half2_rn(0.5f * c0.y, 0.5f * c1.y);
         }
     }
 };
@@ -552,11 +634,13 @@ __device__ __forceinline__ __half2 tanh_approx_h2(__half2 x) {
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&x)));
     return *reinterpret_cast<__half2*>(&r);
 }
-// silu'(z) for two elements in half2: s = 0.5 tanh(z/2) + 0.5 ; s * (1 + z (1 - s))
-__device__ __forceinline__ __half2 silu_grad_h2(__half2 z) {
+// silu'(z) for two elements in half2 from u = z/2, t = tanh(u):  sigmoid = (1 + t)/2 and sigmoid (1 - sigmoid) = (1 - t^2)/4, so
+//   silu'(z) = sigmoid + z sigmoid (1 - sigmoid) = 0.5 (1 + t + u (1 - t^2))       -- three HFMA2 behind the tanh
+__device__ __forceinline__ __half2 silu_grad_h2_u(__half2 u) {
     const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
-    const __half2 s = __hfma2(half, tanh_approx_h2(__hmul2(half, z)), half);
-    return __hmul2(s, __hfma2(z, __hsub2(one, s), one));
+    const __half2 t = tanh_approx_h2(u);
+    const __half2 w = __hfma2(__hneg2(t), t, one);
+    return __hfma2(__hfma2(u, w, t), half, half);
 }
 
 // xf = x as fp32, dz = g * keep/(1-p) * act'(x*A + Bc) for 8 consecutive channels of one pixel
@@ -576,8 +660,8 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
             const uint32_t xs[4] = {xu.x, xu.y, xu.z, xu.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const __half2 z = __hfma2(*reinterpret_cast<const __half2*>(&xs[e]), cf.A[e], cf.Bc[e]);
-                const float2 gr = __half22float2(silu_grad_h2(z));
+                const __half2 u = __hfma2(*reinterpret_cast<const __half2*>(&xs[e]), cf.A[e], cf.Bc[e]);
+                const float2 gr = __half22float2(silu_grad_h2_u(u));
                 dz[2 * e] *= gr.x;
                 dz[2 * e + 1] *= gr.y;
             }
@@ -594,8 +678,10 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
 // kDrop: 0 = no dropout, 1 = keep bits re-generated from the Philox counter, 2 = keep bits read from the stored mask (what the
 // ResBlock node uses).  A compile-time choice: with both paths in one kernel the Philox code's registers made the 64-register
 // variant spill in its main loop (profiles/r02_ncu_norm_attention_summary.txt).
-template <int kAct, int kDrop, int XF, int GF>
-__global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
+// kX16: also write x as bf16 (x_bf16_out).  A template argument because the extra pointer and store pushed the 64-register
+// main loop into local-memory spills; the variant with the side product runs at 3 CTAs per SM instead.
+template <int kAct, int kDrop, int XF, int GF, bool kX16>
+__global__ void __launch_bounds__(kEwThreads, kX16 ? 3 : 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                       int C, int HW, int pix_per_cta,
                                                                       const float2* __restrict__ coef,
@@ -604,7 +690,6 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
                                                                       float drop_p, unsigned long long seed,
                                                                       const uint8_t* __restrict__ mask_in,
                                                                       __nv_bfloat16* __restrict__ x_bf16_out) {
-    constexpr int U = 2;
     __shared__ float red[kEwThreads][17];
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
@@ -613,8 +698,6 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     const int p1 = min(HW, p0 + pix_per_cta);
     GnZCoef<gn_half_path<kAct, XF>()> cf;
     cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
-    const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
-    const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
     const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
     const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
@@ -625,40 +708,46 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
     // stored keep bits: the byte is fetched TOGETHER with the x / g vectors of its pixel (a dependent 1-byte load inside
     // the body exposed a full memory latency per pixel: the dropout variants ran at 0.53 of HBM peak, issue-stalled)
     constexpr bool stored = kDrop == 2;
-    auto mask_at = [&](int p) -> uint32_t {
-        return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
-    };
-    auto body = [&](const uint4& xu, const uint4& gu, uint32_t m, int p) {
-        if (kDrop == 1)
-            m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
-        float xf[8], dz[8];
-        gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
-        // optional side product: x in bf16 (the weight-gradient operand of a 1x1 skip conv over the raw block input) --
-        // +2 B/element here instead of a 4 B/element conversion pass
-        if (x_bf16_out != nullptr)
-            stg_stream(reinterpret_cast<uint4*>(x_bf16_out + ((size_t)b * HW + p) * C + slot * 8), cvt8_out_t<kFmtBF16>(xf));
+    constexpr bool want_x16 = kX16;
+    auto run = [&](auto full_c) {
+        constexpr bool kFull = decltype(full_c)::value;
+        const size_t pix0 = (size_t)b * HW + (size_t)(p0 + prow);
+        const char* xp = reinterpret_cast<const char*>(x) + (pix0 * C + slot * 8) * 2;
+        const char* gp = reinterpret_cast<const char*>(g) + (pix0 * ld_g + c_off + slot * 8) * 2;
+        const uint8_t* mp = stored ? mask_in + e8_base + (size_t)(p0 + prow) * (size_t)(ld_g >> 3) : nullptr;
+        char* xo = want_x16 ? reinterpret_cast<char*>(x_bf16_out) + (pix0 * C + slot * 8) * 2 : nullptr;
+        const size_t sx = (size_t)pstep * C * 2, sg = (size_t)pstep * ld_g * 2, sm = (size_t)pstep * (ld_g >> 3);
+        auto body = [&](const uint4& xu, const uint4& gu, uint32_t m, int p, char* xo_p) {
+            if (kDrop == 1)
+                m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+            float xf[8], dz[8];
+            gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
+            // optional side product: x in bf16 (the weight-gradient operand of a 1x1 skip conv over the raw block input)
+            // -- +2 B/element here instead of a 4 B/element conversion pass
+            if (want_x16) stg_stream_b(xo_p, cvt8_out_t<kFmtBF16>(xf));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            s1[e] += dz[e];
-            s2[e] = fmaf(dz[e], xf[e], s2[e]);
+            for (int e = 0; e < 8; ++e) {
+                s1[e] += dz[e];
+                s2[e] = fmaf(dz[e], xf[e], s2[e]);
+            }
+        };
+        int p = p0 + prow;
+        for (; p + pstep < p1; p += 2 * pstep) {
+            const uint4 xu0 = ldg_stream_b(xp), xu1 = ldg_stream_b(row_next<kFull>(xp, sx));
+            const uint4 gu0 = ldg_stream_b(gp), gu1 = ldg_stream_b(row_next<kFull>(gp, sg));
+            const uint32_t m0 = stored ? (uint32_t)__ldg(mp) : 0xffu;
+            const uint32_t m1 = stored ? (uint32_t)__ldg(mask_next<kFull>(mp, sm)) : 0xffu;
+            body(xu0, gu0, m0, p, xo);
+            body(xu1, gu1, m1, p + pstep, want_x16 ? row_next<kFull>(xo, sx) : nullptr);
+            xp = row_next<kFull>(row_next<kFull>(xp, sx), sx);
+            gp = row_next<kFull>(row_next<kFull>(gp, sg), sg);
+            if (stored) mp = mask_next<kFull>(mask_next<kFull>(mp, sm), sm);
+            if (want_x16) xo = row_next<kFull>(row_next<kFull>(xo, sx), sx);
         }
+        if (p < p1) body(ldg_stream_b(xp), ldg_stream_b(gp), stored ? (uint32_t)__ldg(mp) : 0xffu, p, xo);
     };
-    int p = p0 + prow;
-    for (; p + (U - 1) * pstep < p1; p += U * pstep) {
-        uint4 xu[U], gu[U];
-        uint32_t mk[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
-            gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
-            mk[i] = mask_at(p + i * pstep);
-        }
-#pragma unroll
-        for (int i = 0; i < U; ++i) body(xu[i], gu[i], mk[i], p + i * pstep);
-    }
-    for (; p < p1; p += pstep)
-        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)),
-             mask_at(p), p);
+    if (blockDim.x == kEwThreads && ld_g == C) run(std::true_type{});
+    else run(std::false_type{});
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         red[threadIdx.x][e] = s1[e] * keep_scale;  // dz of the kept elements carries 1/(1-p): applied once per channel here
@@ -682,30 +771,53 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_bwd_reduce_kernel(const __nv
 //   dx = dz * P + x * Q + R,  P = rstd*gamma',  Q = -rstd^2 * m2,  R = -rstd*m1 + mean*rstd^2*m2
 //   m1 = sum_{c in g} gamma'_c S1_c / N,  m2 = sum_{c in g} gamma'_c S2_c / N,  gamma' = gamma * (1 + scale)
 //   dgamma_c += sum_b S2 (1+scale)   dbeta_c += sum_b S1 (1+scale)   dscale_bc = gamma S2 + beta S1   dshift_bc = S1
-__global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchunks,
-                                                          float2* __restrict__ red, const float2* __restrict__ mean_rstd,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const float* __restrict__ film, int C, int G, int HW,
-                                                          float4* __restrict__ pqr, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta, float* __restrict__ dfilm) {
+// The fold over the (up to 111) chunk partials used to be one thread per channel walking its column four loads at a
+// time -- a chain of ~28 dependent global-memory round trips, 20 us per call and 51 calls per training step.  Now, as in
+// gn_coef_parts: the chunk range is cut into `slices` walked by different threads, two channels (one 16-byte load) per
+// thread, eight loads in flight, slice partials folded in a fixed order in shared memory (deterministic).
+__global__ void __launch_bounds__(1024) gn_bwd_coef_kernel(const float2* __restrict__ red_part, int nchunks,
+                                                           float2* __restrict__ red, const float2* __restrict__ mean_rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ film, int C, int G, int HW,
+                                                           float4* __restrict__ pqr, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, float* __restrict__ dfilm, int slices) {
+    extern __shared__ float s_dyn[];  // [2C] totals (S1 | S2), then [slices][2C] slice partials
+    float* s_tot = s_dyn;
+    float* s_part = s_dyn + 2 * C;
+    __shared__ float s_m1[64], s_m2[64];
     const int b = blockIdx.x;
     const int cpg = C / G;
-    __shared__ float s_m1[64], s_m2[64];
-    // fold the per-chunk partials (deterministic order) into red[b][c]
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float2* rp = red_part + (size_t)b * nchunks * C + c;
-        float a = 0.f, q = 0.f;
-        int k = 0;
-        for (; k + 4 <= nchunks; k += 4) {
-            const float2 t0 = rp[(size_t)(k + 0) * C], t1 = rp[(size_t)(k + 1) * C];
-            const float2 t2 = rp[(size_t)(k + 2) * C], t3 = rp[(size_t)(k + 3) * C];
-            a += t0.x; q += t0.y; a += t1.x; q += t1.y; a += t2.x; q += t2.y; a += t3.x; q += t3.y;
+    const int half = C >> 1;
+    const int per = (nchunks + slices - 1) / slices;
+    for (int w = threadIdx.x; w < half * slices; w += blockDim.x) {
+        const int pair = w % half, sl = w / half;
+        const int c = 2 * pair;
+        const float4* rp = reinterpret_cast<const float4*>(red_part + (size_t)b * nchunks * C + c);
+        const size_t stride = (size_t)C >> 1;  // float4 units per chunk row
+        const int k0 = sl * per, k1 = min(nchunks, k0 + per);
+        float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+        int k = k0;
+        for (; k + 8 <= k1; k += 8) {
+            float4 t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __ldg(rp + (size_t)(k + i) * stride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a0 += t[i].x; q0 += t[i].y; a1 += t[i].z; q1 += t[i].w;
+            }
         }
-        for (; k < nchunks; ++k) {
-            const float2 t = rp[(size_t)k * C];
-            a += t.x; q += t.y;
+        for (; k < k1; ++k) {
+            const float4 t = __ldg(rp + (size_t)k * stride);
+            a0 += t.x; q0 += t.y; a1 += t.z; q1 += t.w;
         }
-        red[(size_t)b * C + c] = make_float2(a, q);
+        float* dst = s_part + (size_t)sl * 2 * C;
+        dst[c] = a0; dst[c + 1] = a1; dst[C + c] = q0; dst[C + c + 1] = q1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float v = 0.f;
+        for (int sl = 0; sl < slices; ++sl) v += s_part[(size_t)sl * 2 * C + i];
+        s_tot[i] = v;
     }
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -713,9 +825,8 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restri
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
             const float sc = film ? 1.f + film[(size_t)b * 2 * C + c] : 1.f;
             const float gp = gamma[c] * sc;
-            const float2 r = red[(size_t)b * C + c];
-            m1 += gp * r.x;
-            m2 += gp * r.y;
+            m1 += gp * s_tot[c];
+            m2 += gp * s_tot[C + c];
         }
         const float n = (float)cpg * (float)HW;
         s_m1[g] = m1 / n;
@@ -726,7 +837,8 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const float2* __restri
         const int g = c / cpg;
         const float2 mr = mean_rstd[(size_t)b * G + g];
         const float sc = film ? 1.f + film[(size_t)b * 2 * C + c] : 1.f;
-        const float2 r = red[(size_t)b * C + c];
+        const float2 r = make_float2(s_tot[c], s_tot[C + c]);
+        if (red != nullptr) red[(size_t)b * C + c] = r;
         const float P = mr.y * gamma[c] * sc;
         const float Q = -mr.y * mr.y * s_m2[g];
         const float R = -mr.y * s_m1[g] + mr.x * mr.y * mr.y * s_m2[g];
@@ -751,7 +863,6 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
                                                                      __nv_bfloat16* __restrict__ dx, float drop_p,
                                                                      unsigned long long seed,
                                                                      const uint8_t* __restrict__ mask_in) {
-    constexpr int U = 2;
     const int vpp = C >> 3;
     const int slot = threadIdx.x % vpp, prow = threadIdx.x / vpp, pstep = blockDim.x / vpp;
     const int b = blockIdx.y;
@@ -767,10 +878,6 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
         Q[e] = t.y;
         R[e] = t.z;
     }
-    const uint4* xs = reinterpret_cast<const uint4*>(x + (size_t)b * HW * C);
-    const uint4* as = kAdd ? reinterpret_cast<const uint4*>(add + (size_t)b * HW * C) : nullptr;
-    uint4* ds = reinterpret_cast<uint4*>(dx + (size_t)b * HW * C);
-    const __nv_bfloat16* gs = g + (size_t)b * HW * ld_g + c_off + slot * 8;
     const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
     const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
     const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
@@ -780,41 +887,52 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
 #pragma unroll
         for (int e = 0; e < 8; ++e) P[e] *= keep_scale;  // dz only enters through dz * P: 1/(1-p) folded into P
     }
-    auto mask_at = [&](int p) -> uint32_t {
-        return stored ? (uint32_t)__ldg(mask_in + e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3)) : 0xffu;
-    };
-    auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, uint32_t m, int p) {
-        if (kDrop == 1)
-            m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
-        float xf[8], dz[8], o[8];
-        gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
+    auto run = [&](auto full_c) {
+        constexpr bool kFull = decltype(full_c)::value;
+        const size_t pix0 = (size_t)b * HW + (size_t)(p0 + prow);
+        const size_t xoff = (pix0 * C + slot * 8) * 2;
+        const char* xp = reinterpret_cast<const char*>(x) + xoff;
+        const char* ap = kAdd ? reinterpret_cast<const char*>(add) + xoff : nullptr;
+        char* dp = reinterpret_cast<char*>(dx) + xoff;
+        const char* gp = reinterpret_cast<const char*>(g) + (pix0 * ld_g + c_off + slot * 8) * 2;
+        const uint8_t* mp = stored ? mask_in + e8_base + (size_t)(p0 + prow) * (size_t)(ld_g >> 3) : nullptr;
+        const size_t sx = (size_t)pstep * C * 2, sg = (size_t)pstep * ld_g * 2, sm = (size_t)pstep * (ld_g >> 3);
+        auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, uint32_t m, int p, char* dst) {
+            if (kDrop == 1)
+                m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+            float xf[8], dz[8], o[8];
+            gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
-        if (kAdd) {
-            float af[8];
-            cvt8_in_t<GF>(au, af);
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
+            if (kAdd) {
+                float af[8];
+                cvt8_in_t<GF>(au, af);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] += af[e];
+                for (int e = 0; e < 8; ++e) o[e] += af[e];
+            }
+            stg_stream_b(dst, cvt8_out_t<GF>(o));
+        };
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        int p = p0 + prow;
+        for (; p + pstep < p1; p += 2 * pstep) {
+            const uint4 xu0 = ldg_stream_b(xp), xu1 = ldg_stream_b(row_next<kFull>(xp, sx));
+            const uint4 gu0 = ldg_stream_b(gp), gu1 = ldg_stream_b(row_next<kFull>(gp, sg));
+            const uint4 au0 = kAdd ? ldg_stream_b(ap) : zero4, au1 = kAdd ? ldg_stream_b(row_next<kFull>(ap, sx)) : zero4;
+            const uint32_t m0 = stored ? (uint32_t)__ldg(mp) : 0xffu;
+            const uint32_t m1 = stored ? (uint32_t)__ldg(mask_next<kFull>(mp, sm)) : 0xffu;
+            body(xu0, gu0, au0, m0, p, dp);
+            body(xu1, gu1, au1, m1, p + pstep, row_next<kFull>(dp, sx));
+            xp = row_next<kFull>(row_next<kFull>(xp, sx), sx);
+            dp = row_next<kFull>(row_next<kFull>(dp, sx), sx);
+            gp = row_next<kFull>(row_next<kFull>(gp, sg), sg);
+            if (kAdd) ap = row_next<kFull>(row_next<kFull>(ap, sx), sx);
+            if (stored) mp = mask_next<kFull>(mask_next<kFull>(mp, sm), sm);
         }
-        stg_stream(ds + (size_t)p * vpp + slot, cvt8_out_t<GF>(o));
+        if (p < p1)
+            body(ldg_stream_b(xp), ldg_stream_b(gp), kAdd ? ldg_stream_b(ap) : zero4, stored ? (uint32_t)__ldg(mp) : 0xffu, p, dp);
     };
-    int p = p0 + prow;
-    for (; p + (U - 1) * pstep < p1; p += U * pstep) {
-        uint4 xu[U], gu[U], au[U];
-        uint32_t mk[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            xu[i] = ldg_stream(xs + (size_t)(p + i * pstep) * vpp + slot);
-            gu[i] = ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)(p + i * pstep) * ld_g));
-            au[i] = kAdd ? ldg_stream(as + (size_t)(p + i * pstep) * vpp + slot) : make_uint4(0, 0, 0, 0);
-            mk[i] = mask_at(p + i * pstep);
-        }
-#pragma unroll
-        for (int i = 0; i < U; ++i) body(xu[i], gu[i], au[i], mk[i], p + i * pstep);
-    }
-    for (; p < p1; p += pstep)
-        body(ldg_stream(xs + (size_t)p * vpp + slot), ldg_stream(reinterpret_cast<const uint4*>(gs + (size_t)p * ld_g)),
-             kAdd ? ldg_stream(as + (size_t)p * vpp + slot) : make_uint4(0, 0, 0, 0), mask_at(p), p);
+    if (blockDim.x == kEwThreads && ld_g == C) run(std::true_type{});
+    else run(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------------------ resampling
