@@ -455,6 +455,8 @@ def run_multitask(args, rank, world, local):
         mt.SegmentationDecoder(1024, f[:-1][::-1], 5, True), ConditionalFlowMatcher(0.0), num_classes=5,
         solver=functools.partial(NeuralODE, solver="euler"), optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=1e-5),
         scheduler=None, log_images=False).to(dev)
+    if args.sync_bn and world > 1:  # what Lightning does for `sync_batchnorm: True` (configs/trainer/ddp.yaml:9)
+        lit = torch.nn.SyncBatchNorm.convert_sync_batchnorm(lit)
     lit.train()
 
     class Step(torch.nn.Module):
@@ -547,6 +549,8 @@ def run_multitask(args, rank, world, local):
            "data": "synthetic U(-1,1) 3x512x512 tile pairs + 5-class masks, default-init config-M model, seed 1984",
            "config": {"workload": "configs[4]: multi-task multi-class-loss model at 512x512 tiles", "per_gpu_batch": B,
                       "global_batch": B * world, "params": sum(p.numel() for p in lit.parameters()), "parallelism": f"dp{world}",
+                      "batchnorm": "SyncBatchNorm (statistics over all ranks: 2 x 26 all-reduces of [C, 2] floats per step)"
+                                   if (args.sync_bn and world > 1) else "per-rank batch statistics (plain strategy: ddp)",
                       "step_launch": "eager launches, torch DDP" if args.no_graph else
                                      "CUDA-graph replay (+ one flat gradient all-reduce between two graphs at N > 1)"},
            "loss": float(loss.detach()), "gpu_launches": launches,
@@ -668,6 +672,8 @@ def main():
     ap.add_argument("--sample-tiles", type=int, default=0,
                     help="tiles of the sampling record over ALL ranks (default 512 per GPU: 4096 on 8 GPUs = configs[2])")
     ap.add_argument("--sample-batch", type=int, default=64, help="sampling micro-batch inside the train-mode run")
+    ap.add_argument("--sync-bn", action="store_true", help="multitask mode, N > 1: SyncBatchNorm as under the reference's "
+                    "trainer=ddp (configs/trainer/ddp.yaml:9); default = per-rank statistics as under its experiment configs")
     ap.add_argument("--no-graph", action="store_true", help="train mode: launch the step from Python (torch DDP at N > 1) "
                                                            "instead of replaying CUDA graphs")
     ap.add_argument("--bucket-mb", type=int, default=512,

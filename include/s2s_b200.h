@@ -101,15 +101,16 @@ int s2s_conv_wgrad(const void* dy, int Cm, const void* x, int Cq, int taps, int 
                    float* dw, int ldn, int n_off, int dy_fmt, int x_fmt, void* stream);
 
 /* s2s_pack_conv_weight for many weights in ONE launch (every cached GEMM operand is stale after an optimizer step).
- * jobs_dev: device table of jobs; work_dev: device list of (job index, chunk index) int pairs, one CTA each, a chunk
- * being s2s_pack_chunk() destination elements of the job (total = Cout * ci_count * taps).  The zero padding of the
- * destinations is not touched. */
+ * jobs_dev: device table of jobs; work_dev: device list of (job index, tile index) int pairs, one CTA each, tile index in
+ * [0, s2s_pack_tiles(Cout, ci_count, transpose_flip)) of that job (a tile = 16 destination rows x 64 destination-contiguous
+ * elements x all taps, staged through shared memory so that both the OIHW reads and the operand writes are coalesced).
+ * The zero padding of the destinations is not touched. */
 typedef struct {
     const float* w;
     void* dst16;
     int Cout, Cin, taps, ci_begin, ci_count, ld_k, k_off, transpose_flip, fmt, mode; /* mode: see s2s_pack_conv_weight_mode */
 } s2s_pack_job;
-int s2s_pack_chunk(void);
+int s2s_pack_tiles(int Cout, int ci_count, int transpose_flip);
 int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev, int n_work, void* stream);
 
 /* s2s_pack_conv_weight with a tap-combination mode.  mode 0: plain.  mode 1 + phase (phase = py*2 + px; 3x3 weights):
@@ -282,6 +283,20 @@ int s2s_bn_coef(const float* stats, int B, int nchunks, int C, int HW, const flo
                 float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream);
 int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const float* mean_rstd, const float* gamma,
                     float* pqr, float* dgamma, float* dbeta, void* stream);
+
+/* torch.nn.SyncBatchNorm (what `sync_batchnorm: True` of configs/trainer/ddp.yaml:9 makes Lightning install in place of
+ * every BatchNorm2d): each rank folds its partials to per-channel sums (bn_fold: parts [nparts][C][2] -> sums [C][2], same
+ * fixed order), the host all-reduces the [C][2] sums (+ the element count), and the totals come back as ONE part:
+ *   bn_coef_sums    : sums of ALL ranks, count = global elements per channel -> coef / mean_rstd for the B local samples,
+ *                     running statistics from the global mean / unbiased variance (identical on every rank)
+ *   bn_bwd_coef_sums: all-reduced (sum dz, sum dz*xhat) -> pqr with the global count; the parameter gradients stay LOCAL
+ *                     (torch's SyncBatchNorm does the same, DDP averages them): the two scratch vectors receive the global
+ *                     sums and are discarded by the caller, which takes dgamma / dbeta from its own bn_fold result. */
+int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, void* stream);
+int s2s_bn_coef_sums(const float* sums, int C, long long count, int B, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream);
+int s2s_bn_bwd_coef_sums(const float* sums, int C, long long count, int B, const float* mean_rstd, const float* gamma,
+                         float* pqr, float* dgamma_scratch, float* dbeta_scratch, void* stream);
 
 /* nn.MaxPool2d(2) (shared_encoder.py:32-34) and its backward (gradient to the first maximum in row-major order, as ATen);
  * 16-bit NHWC, H, W = OUTPUT spatial dims. */

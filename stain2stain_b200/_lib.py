@@ -55,7 +55,7 @@ SIGNATURES = {
     "s2s_upconv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "s2s_upconv_unpack_wgrad": [_vp, _i, _i, _vp, _vp],
     "s2s_downconv_dgrad": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp],
-    "s2s_pack_chunk": [],
+    "s2s_pack_tiles": [_i, _i, _i],
     "s2s_pack_conv_weight_multi": [_vp, _vp, _i, _vp],
     "s2s_conv_fwd": [C.POINTER(ConvSrc), _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
     "s2s_conv_norm_fusable": [C.POINTER(ConvSrc), _i, _i],
@@ -92,6 +92,9 @@ SIGNATURES = {
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_bn_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "s2s_bn_bwd_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "s2s_bn_fold": [_vp, _i, _i, _vp, _vp],
+    "s2s_bn_coef_sums": [_vp, _i, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "s2s_bn_bwd_coef_sums": [_vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "s2s_maxpool2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "s2s_maxpool2x_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "s2s_bilinear2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -283,8 +283,7 @@ int s2s_pack_conv_weight_mode(const float* w, int Cout, int Cin, int taps, int c
     PackJob jb;
     jb.w = w; jb.dst = (uint16_t*)dst; jb.Cout = Cout; jb.Cin = Cin; jb.taps = taps; jb.ci_begin = ci_begin;
     jb.ci_count = ci_count; jb.ld_k = ld_k; jb.k_off = k_off; jb.transpose_flip = transpose_flip; jb.fmt = fmt; jb.mode = mode;
-    const long long total = (long long)Cout * ci_count * (mode == 0 ? taps : 4);
-    pack_conv_weight_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(jb);
+    pack_conv_weight_kernel<<<pack_tile_count(Cout, ci_count, transpose_flip), 256, 0, (cudaStream_t)stream>>>(jb);
     LAUNCH_CHECK("pack_conv_weight_kernel");
     return S2S_OK;
 }
@@ -793,7 +792,10 @@ static int wgrad_impl(const ActView& dyv, const void* x, int Cq, int taps, unsig
     return S2S_OK;
 }
 
-int s2s_pack_chunk(void) { return kPackChunk; }
+int s2s_pack_tiles(int Cout, int ci_count, int transpose_flip) {
+    if (Cout <= 0 || ci_count <= 0) return 0;
+    return pack_tile_count(Cout, ci_count, transpose_flip);
+}
 
 int s2s_pack_conv_weight_multi(const s2s_pack_job* jobs_dev, const int* work_dev, int n_work, void* stream) {
     static_assert(sizeof(s2s_pack_job) == sizeof(PackJob), "ABI struct drifted from the kernel's");
@@ -1232,6 +1234,35 @@ int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const f
     bn_bwd_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
         (const float2*)red, B * nchunks, B, C, (long long)B * HW, (const float2*)mean_rstd, gamma, (float4*)pqr, dgamma,
         dbeta);
+    LAUNCH_CHECK("bn_bwd_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, void* stream) {
+    if (!parts || !sums || nparts <= 0 || C <= 0) return fail(S2S_ERR_INVALID, "bn_fold: bad arguments");
+    bn_fold_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>((const float2*)parts, nparts, C,
+                                                                                            (float2*)sums);
+    LAUNCH_CHECK("bn_fold_kernel");
+    return S2S_OK;
+}
+
+int s2s_bn_coef_sums(const float* sums, int C, long long count, int B, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream) {
+    if (!sums || !gamma || !beta || !coef || !mean_rstd || C <= 0 || count <= 0 || B <= 0)
+        return fail(S2S_ERR_INVALID, "bn_coef_sums: bad arguments");
+    bn_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
+        (const float2*)sums, 1, B, C, count, gamma, beta, eps, momentum, running_mean, running_var, (float2*)coef,
+        (float2*)mean_rstd);
+    LAUNCH_CHECK("bn_coef_kernel");
+    return S2S_OK;
+}
+
+int s2s_bn_bwd_coef_sums(const float* sums, int C, long long count, int B, const float* mean_rstd, const float* gamma,
+                         float* pqr, float* dgamma_scratch, float* dbeta_scratch, void* stream) {
+    if (!sums || !mean_rstd || !gamma || !pqr || !dgamma_scratch || !dbeta_scratch || count <= 0 || B <= 0)
+        return fail(S2S_ERR_INVALID, "bn_bwd_coef_sums: bad arguments");
+    bn_bwd_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
+        (const float2*)sums, 1, B, C, count, (const float2*)mean_rstd, gamma, (float4*)pqr, dgamma_scratch, dbeta_scratch);
     LAUNCH_CHECK("bn_bwd_coef_kernel");
     return S2S_OK;
 }

@@ -130,54 +130,91 @@ __device__ __forceinline__ void phase_range(int parity, int idx, int& lo, int& h
     if (parity == 0) { lo = idx == 0 ? 0 : 1; hi = idx == 0 ? 0 : 2; }
     else             { lo = idx == 0 ? 0 : 2; hi = idx == 0 ? 1 : 2; }
 }
-__device__ __forceinline__ void pack_conv_weight_elem(const PackJob& jb, long long i) {
-    const int ltaps = jb.mode == 0 ? jb.taps : 4;  // logical taps of the packed operand
-    int row, tap, inner;
-    // iterate in destination order so that writes are coalesced
-    if (!jb.transpose_flip) {
-        inner = (int)(i % jb.ci_count);
-        tap = (int)((i / jb.ci_count) % ltaps);
-        row = (int)(i / ((long long)jb.ci_count * ltaps));
+// Work decomposition: tiles of kPackRows destination rows x kPackInner destination-contiguous elements x all (logical)
+// taps.  The source of a tile is a set of CONTIGUOUS runs of the OIHW tensor either way -- forward: per output channel the
+// 64 input channels x taps of the tile; transposed: per output channel (64 of them) the 16 input channels x taps -- so
+// a warp stages one run at a time with coalesced loads into shared memory and the tile leaves as 128-byte rows.  (The
+// element-per-thread kernel this replaces read the transposed operand with one cache line per lane: 0.14 of the HBM rate
+// for the 158 operands of a training step.)
+constexpr int kPackRows = 16, kPackInner = 64;
+constexpr int kPackSmemFloats = kPackInner * (kPackRows * 9 + 1);  // >= kPackRows * (kPackInner * 9 + 1)
+__host__ __device__ inline int pack_tile_count(int Cout, int ci_count, int transpose_flip) {
+    const int rows = transpose_flip ? ci_count : Cout, inner = transpose_flip ? Cout : ci_count;
+    return ((rows + kPackRows - 1) / kPackRows) * ((inner + kPackInner - 1) / kPackInner);
+}
+__device__ __forceinline__ void pack_conv_weight_tile(const PackJob& jb, int tile, float* S) {
+    const bool tf = jb.transpose_flip != 0;
+    const int rows = tf ? jb.ci_count : jb.Cout, inner = tf ? jb.Cout : jb.ci_count;
+    const int tiles_i = (inner + kPackInner - 1) / kPackInner;
+    const int r0 = (tile / tiles_i) * kPackRows, i0 = (tile % tiles_i) * kPackInner;
+    if (r0 >= rows) return;  // (uniform per CTA)
+    const int nr = min(kPackRows, rows - r0), ni = min(kPackInner, inner - i0);
+    const int taps = jb.taps, ltaps = jb.mode == 0 ? taps : 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int pitch = (tf ? kPackRows : kPackInner) * taps + 1;  // odd: conflict-poor strided reads below
+    // forward   : run r = output channel r0 + r, input channels [ci_begin + i0, + ni) x taps
+    // transposed: run c = output channel i0 + c, input channels [ci_begin + r0, + nr) x taps
+    const int n_runs = tf ? ni : nr, run_len = (tf ? nr : ni) * taps;
+    const size_t run0 = tf ? ((size_t)i0 * jb.Cin + jb.ci_begin + r0) * taps : ((size_t)r0 * jb.Cin + jb.ci_begin + i0) * taps;
+    const size_t run_stride = (size_t)jb.Cin * taps;
+    const bool vec_ok = ((run_len | (int)(run_stride & 3) | (int)(run0 & 3)) & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(jb.w) & 15) == 0;  // every run 16-byte aligned, whole float4s
+    if (vec_ok) {
+        const int per = run_len >> 2;  // float4s per run; (run, j) pairs flattened so that all 256 threads load
+        for (int idx = threadIdx.x; idx < n_runs * per; idx += blockDim.x) {
+            const int run = idx / per, j = idx - run * per;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(jb.w + run0 + (size_t)run * run_stride) + j);
+            float* d = S + run * pitch + 4 * j;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
     } else {
-        inner = (int)(i % jb.Cout);
-        tap = (int)((i / jb.Cout) % ltaps);
-        row = (int)(i / ((long long)jb.Cout * ltaps));
+        for (int run = warp; run < n_runs; run += nwarps) {
+            const float* src = jb.w + run0 + (size_t)run * run_stride;
+            for (int j = lane; j < run_len; j += 32) S[run * pitch + j] = __ldg(src + j);
+        }
     }
-    const int co = jb.transpose_flip ? inner : row;
-    const int ci = jb.ci_begin + (jb.transpose_flip ? row : inner);
-    const float* wp = jb.w + ((size_t)co * jb.Cin + ci) * jb.taps;
-    float v;
-    if (jb.mode == 0) {
-        v = wp[jb.transpose_flip ? (jb.taps - 1 - tap) : tap];
-    } else {
+    __syncthreads();
+    auto value = [&](int r, int lt, int il) -> float {
+        const float* sp = tf ? S + il * pitch + r * taps : S + r * pitch + il * taps;
+        if (jb.mode == 0) return sp[tf ? (taps - 1 - lt) : lt];
         const int phase = jb.mode - 1;
         int y0, y1, x0, x1;
-        phase_range(phase >> 1, tap >> 1, y0, y1);
-        phase_range(phase & 1, tap & 1, x0, x1);
-        v = 0.f;
+        phase_range(phase >> 1, lt >> 1, y0, y1);
+        phase_range(phase & 1, lt & 1, x0, x1);
+        float v = 0.f;
         for (int dy = y0; dy <= y1; ++dy)
-            for (int dx = x0; dx <= x1; ++dx) v += wp[dy * 3 + dx];
+            for (int dx = x0; dx <= x1; ++dx) v += sp[dy * 3 + dx];
+        return v;
+    };
+    const bool pair_ok = ((jb.ld_k | jb.k_off | inner) & 1) == 0;  // 32-bit stores of two elements
+    for (int item = warp; item < nr * ltaps; item += nwarps) {
+        const int r = item / ltaps, lt = item - r * ltaps;
+        uint16_t* drow = jb.dst + (size_t)(r0 + r) * jb.ld_k + (size_t)jb.k_off + (size_t)lt * inner + i0;
+        for (int il = 2 * lane; il < ni; il += 64) {
+            const uint16_t a = pack1(value(r, lt, il), jb.fmt);
+            if (il + 1 < ni) {
+                const uint16_t c = pack1(value(r, lt, il + 1), jb.fmt);
+                if (pair_ok) *reinterpret_cast<uint32_t*>(drow + il) = (uint32_t)a | ((uint32_t)c << 16);
+                else { drow[il] = a; drow[il + 1] = c; }
+            } else {
+                drow[il] = a;
+            }
+        }
     }
-    const size_t col = (size_t)jb.k_off + (size_t)tap * (jb.transpose_flip ? jb.Cout : jb.ci_count) + inner;
-    jb.dst[(size_t)row * jb.ld_k + col] = pack1(v, jb.fmt);
 }
-__global__ void pack_conv_weight_kernel(PackJob jb) {
-    const long long total = (long long)jb.Cout * jb.ci_count * (jb.mode == 0 ? jb.taps : 4);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-        pack_conv_weight_elem(jb, i);
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(PackJob jb) {
+    __shared__ float S[kPackSmemFloats];
+    pack_conv_weight_tile(jb, blockIdx.x, S);
 }
 
 // The same packing for MANY weights in one launch (after an optimizer step every cached GEMM operand is stale: 158
-// tensors per training step).  Host uploads a job table + (job, chunk) work list, as for the multi-tensor Adam.
-constexpr int kPackChunk = 16384;
+// tensors per training step).  Host uploads a job table + (job, tile) work list, as for the multi-tensor Adam.
 __global__ void __launch_bounds__(256) pack_conv_weight_multi_kernel(const PackJob* __restrict__ jobs,
                                                                      const int2* __restrict__ work) {
+    __shared__ float S[kPackSmemFloats];
     const int2 wi = work[blockIdx.x];
     const PackJob jb = jobs[wi.x];
-    const long long total = (long long)jb.Cout * jb.ci_count * (jb.mode == 0 ? jb.taps : 4);
-    const long long beg = (long long)wi.y * kPackChunk;
-    const long long end = min(total, beg + kPackChunk);
-    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) pack_conv_weight_elem(jb, i);
+    pack_conv_weight_tile(jb, wi.y, S);
 }
 
 // Weight gradient of the phase-decomposed Upsample conv: src = [16 = phase*4 + ti][M][N] fp32 (what the four phase wgrad

@@ -58,6 +58,35 @@ __global__ void __launch_bounds__(kBnCh * kBnRows) bn_coef_kernel(const float2* 
     }
 }
 
+// SyncBatchNorm (torch.nn.SyncBatchNorm, what Lightning's `sync_batchnorm: True` of configs/trainer/ddp.yaml:9 installs):
+// the per-channel sums of one rank, folded in the same fixed order, so that the host can all-reduce [C][2] floats and hand
+// the totals back to bn_coef_kernel / bn_bwd_coef_kernel as ONE part with the global element count.
+__global__ void __launch_bounds__(kBnCh * kBnRows) bn_fold_kernel(const float2* __restrict__ parts, int nparts, int C,
+                                                                  float2* __restrict__ sums) {
+    __shared__ float s_a[kBnRows][kBnCh + 1], s_q[kBnRows][kBnCh + 1];
+    const int ci = threadIdx.x % kBnCh, r = threadIdx.x / kBnCh;
+    const int c = blockIdx.x * kBnCh + ci;
+    float a = 0.f, q = 0.f;
+    if (c < C)
+        for (int k = r; k < nparts; k += kBnRows) {
+            const float2 t = parts[(size_t)k * C + c];
+            a += t.x;
+            q += t.y;
+        }
+    s_a[r][ci] = a;
+    s_q[r][ci] = q;
+    __syncthreads();
+    if (r == 0 && c < C) {
+        a = q = 0.f;
+#pragma unroll
+        for (int k = 0; k < kBnRows; ++k) {
+            a += s_a[k][ci];
+            q += s_q[k][ci];
+        }
+        sums[c] = make_float2(a, q);
+    }
+}
+
 // red: [B][nchunks][C] (sum dz, sum dz*xhat) partials from gn_bwd_reduce_kernel.
 //   dx = dz*P + x*Q + R,  P = gamma*rstd, Q = -gamma*rstd^2*S2/N, R = -gamma*rstd*S1/N + gamma*mean*rstd^2*S2/N
 //   dgamma += S2, dbeta += S1

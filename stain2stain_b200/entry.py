@@ -75,15 +75,21 @@ def train_experiment(config_dir: str, overrides=(), steps: int = 10, batch: Opti
         gb = (cfg.get("data") or {}).get("batch_size", 4)
         batch = per_rank_batch(int(gb), int(kw.pop("world_size", 1)))
     seed = cfg.get("seed")
+    kw.setdefault("sync_batchnorm", bool((cfg.get("trainer") or {}).get("sync_batchnorm", False)))
     out = train(cfg["model"], steps=steps, batch=batch, device=device, seed=1984 if seed is None else int(seed), **kw)
     out["cfg"] = cfg
     return out
 
 
 def train(config, steps: int = 10, batch: int = 4, size: Optional[int] = None, device: str = "cuda", seed: int = 1984,
-          ckpt_path: Optional[str] = None, **overrides) -> Dict[str, Any]:
+          ckpt_path: Optional[str] = None, sync_batchnorm: bool = False, **overrides) -> Dict[str, Any]:
     torch.manual_seed(seed)  # L.seed_everything(cfg.seed) (src/train.py:55-56)
     model = build_model(config, **overrides).to(device)
+    if sync_batchnorm and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1:
+        # Trainer(sync_batchnorm=True) (configs/trainer/ddp.yaml:9): BatchNorm2d -> SyncBatchNorm; ops.batch_norm_relu then
+        # folds the batch statistics over all ranks.  A no-op for the GroupNorm UNets and in a single process.
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     kind = model_kind(model)
     if size is None:
         size = model.net.image_size if hasattr(model, "net") else 256

@@ -123,7 +123,6 @@ def pack_conv_weight_multi(jobs, table_cache: dict):
     sig = tuple((w.data_ptr(), dst.data_ptr(), k_off, cb, cc, tf, fmt, mode) for (w, dst, k_off, cb, cc, tf, fmt, mode) in jobs)
     hit = table_cache.get(sig)
     if hit is None:
-        chunk = int(_L().s2s_pack_chunk())
         arr = (_lib.PackJob * len(jobs))()
         work = []
         total_bytes = 0.0
@@ -136,7 +135,7 @@ def pack_conv_weight_multi(jobs, table_cache: dict):
                                   int(mode))
             n = cout * cc * (taps if mode == 0 else 4)
             total_bytes += 6.0 * n
-            work.extend((i, c) for c in range((n + chunk - 1) // chunk))
+            work.extend((i, c) for c in range(int(_L().s2s_pack_tiles(cout, cc, int(tf)))))
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().pin_memory()
         w_host = torch.tensor(work, dtype=torch.int32).pin_memory()
         hit = (raw.to(dev, non_blocking=True), w_host.to(dev, non_blocking=True), len(work), total_bytes, (raw, w_host))
@@ -650,6 +649,34 @@ def bn_bwd_coef(red, mr, gamma, HW: int, dgamma, dbeta):
     pqr = torch.empty((B, C, 4), dtype=torch.float32, device=red.device)
     check(_L().s2s_bn_bwd_coef(ptr(red), B, nchunks, C, HW, ptr(mr), ptr(gamma), ptr(pqr), ptr(dgamma), ptr(dbeta),
                                stream_ptr()), "bn_bwd_coef")
+    return pqr
+
+
+def bn_fold(parts):
+    """[B, nchunks, C, 2] partials -> this rank's per-channel sums [C, 2] (SyncBatchNorm: what gets all-reduced)."""
+    B, nchunks, C, _ = parts.shape
+    sums = torch.empty((C, 2), dtype=torch.float32, device=parts.device)
+    check(_L().s2s_bn_fold(ptr(parts), B * nchunks, C, ptr(sums), stream_ptr()), "bn_fold")
+    return sums
+
+
+def bn_coef_sums(sums, count: int, B: int, gamma, beta, eps: float, momentum: float, running_mean, running_var):
+    """bn_coef from all-reduced per-channel sums [C, 2] and the GLOBAL element count per channel."""
+    C = sums.shape[0]
+    coef = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
+    mr = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
+    check(_L().s2s_bn_coef_sums(ptr(sums), C, int(count), B, ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                ptr(running_mean), ptr(running_var), ptr(coef), ptr(mr), stream_ptr()), "bn_coef_sums")
+    return coef, mr
+
+
+def bn_bwd_coef_sums(sums, count: int, B: int, mr, gamma):
+    """pqr [B, C, 4] from all-reduced (sum dz, sum dz*xhat) [C, 2] and the global count."""
+    C = sums.shape[0]
+    pqr = torch.empty((B, C, 4), dtype=torch.float32, device=sums.device)
+    scratch = torch.zeros((2, C), dtype=torch.float32, device=sums.device)
+    check(_L().s2s_bn_bwd_coef_sums(ptr(sums), C, int(count), B, ptr(mr), ptr(gamma), ptr(pqr), ptr(scratch[0]),
+                                    ptr(scratch[1]), stream_ptr()), "bn_bwd_coef_sums")
     return pqr
 
 

@@ -564,15 +564,27 @@ class _BatchNormRelu(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float, relu: bool,
-                src_stats=None, twin_box=None):
+                src_stats=None, twin_box=None, sync_group=None):
         B, H, W, C = x.shape
         act = K.ACT_RELU if relu else K.ACT_NONE
+        ctx.sync_group, ctx.count = None, B * H * W
         if training:
             stats = src_stats  # per-sub-tile partials from the producing conv's epilogue, same [B, n, C, 2] layout
             if stats is None:
                 stats = K.gn_partial_buffer(B, H * W, C, x.device)
                 K.gn_stats(x, stats, 0)
-            coef, mr = K.bn_coef(stats, gamma.detach(), beta.detach(), H * W, eps, momentum, running_mean, running_var)
+            if sync_group is not None:
+                # torch.nn.SyncBatchNorm: statistics over the batches of ALL ranks.  One collective of 2C floats (the
+                # per-channel sums); running statistics come out identical on every rank.  Every rank holds the same number
+                # of samples (DistributedSampler pads to that), so the global count needs no second collective / host sync.
+                import torch.distributed as dist
+                sums = K.bn_fold(stats)
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=sync_group)
+                ctx.sync_group, ctx.count = sync_group, B * H * W * dist.get_world_size(sync_group)
+                coef, mr = K.bn_coef_sums(sums, ctx.count, B, gamma.detach(), beta.detach(), eps, momentum, running_mean,
+                                          running_var)
+            else:
+                coef, mr = K.bn_coef(stats, gamma.detach(), beta.detach(), H * W, eps, momentum, running_mean, running_var)
         else:
             A = gamma.detach() * torch.rsqrt(running_var + eps)
             coef = torch.stack([A, beta.detach() - running_mean * A], dim=1).unsqueeze(0).expand(B, C, 2).contiguous()
@@ -595,12 +607,36 @@ class _BatchNormRelu(torch.autograd.Function):
         B, H, W, C = x.shape
         red = K.gn_partial_buffer(B, H * W, C, x.device)
         K.gn_bwd_reduce(x, g, coef, mr, red, 0, ctx.act)
-        dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
-        dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
-        pqr = K.bn_bwd_coef(red, mr, gamma.detach(), H * W, dgamma, dbeta)
+        if ctx.sync_group is not None:
+            # (sum dz, sum dz*xhat) of all ranks enter dx; the parameter gradients stay local (DDP averages them), as in
+            # torch's SyncBatchNorm backward
+            import torch.distributed as dist
+            local = K.bn_fold(red)
+            total = local.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.sync_group)
+            pqr = K.bn_bwd_coef_sums(total, ctx.count, B, mr, gamma.detach())
+            dgamma, dbeta = local[:, 1].contiguous(), local[:, 0].contiguous()
+        else:
+            dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
+            dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
+            pqr = K.bn_bwd_coef(red, mr, gamma.detach(), H * W, dgamma, dbeta)
         dx = torch.empty_like(x)
         K.gn_bwd_apply(x, g, coef, pqr, 0, None, dx, ctx.act)
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+
+
+def _sync_group_of(bn):
+    """The process group to synchronise batch statistics over, or None.  A module is synchronised exactly when the reference's
+    would be: after `torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)` (what Lightning's `sync_batchnorm: True` --
+    configs/trainer/ddp.yaml:9 -- runs on the LightningModule) the BatchNorm2d children ARE SyncBatchNorm instances; like
+    torch's, they only synchronise in training mode, with an initialised process group of more than one rank."""
+    if not isinstance(bn, torch.nn.SyncBatchNorm) or not bn.training:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
 
 
 def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
@@ -609,7 +645,7 @@ def batch_norm_relu(x, bn: "torch.nn.BatchNorm2d", relu: bool = True):
     momentum = 0.1 if bn.momentum is None else bn.momentum
     box = [] if (bn.training and torch.is_grad_enabled()) else None
     y = _BatchNormRelu.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bool(bn.training),
-                             float(momentum), float(bn.eps), relu, stats_of(x), box)
+                             float(momentum), float(bn.eps), relu, stats_of(x), box, _sync_group_of(bn))
     if box:
         y._s2s_g16 = box[0]
     return y

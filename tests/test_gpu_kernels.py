@@ -548,3 +548,62 @@ def test_head_conv_kernel_matches_conv2d_and_fused_euler_update(B, H, W, C, Cout
     want = x + 0.02 * ref
     got = k.head_conv(nhwc(a), w.contiguous(), b, axpy_x=x, axpy_a=0.02)
     assert got.data_ptr() == x.data_ptr() and torch.allclose(got, want, atol=1e-4, rtol=1e-4)
+
+
+def _expected_pack(k, w, ci_begin, ci_count, transpose_flip, fmt, mode):
+    """The operand layouts of include/s2s_b200.h written with torch indexing (bit-exact: one rounding fp32 -> 16 bit)."""
+    cout, cin = w.shape[:2]
+    taps = w[0, 0].numel()
+    w3 = w.reshape(cout, cin, taps)[:, ci_begin:ci_begin + ci_count]          # [co, ci, tap]
+    if mode == 0:
+        lt = w3.flip(2) if transpose_flip else w3
+    else:
+        ph = mode - 1
+        rng = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+        w9 = w3.reshape(cout, ci_count, 3, 3)
+        cols = []
+        for ti in range(4):
+            ys, xs = rng[(ph >> 1, ti >> 1)], rng[(ph & 1, ti & 1)]
+            acc = torch.zeros(cout, ci_count, device=w.device)
+            for y in ys:             # same summation order as the kernel (dy outer, dx inner), fp32
+                for x in xs:
+                    acc = acc + w9[:, :, y, x]
+            cols.append(acc)
+        lt = torch.stack(cols, dim=2)                                          # [co, ci, 4]
+    if transpose_flip:
+        out = lt.permute(1, 2, 0).reshape(ci_count, -1)                       # [ci][tap * Cout + co]
+    else:
+        out = lt.permute(0, 2, 1).reshape(cout, -1)                           # [co][tap * ci_count + ci]
+    return k.from_float(out.contiguous(), fmt)
+
+
+@pytest.mark.parametrize("cout,cin,taps,ci_begin,ci_count", [(128, 128, 9, 0, 128), (96, 72, 9, 8, 40), (64, 200, 1, 64, 136),
+                                                             (40, 24, 9, 0, 24), (256, 384, 9, 128, 256), (1024, 512, 1, 0, 512)])
+def test_pack_conv_weight_layouts_bit_exact(cout, cin, taps, ci_begin, ci_count):
+    """s2s_pack_conv_weight(_mode) and the multi-tensor launch: forward / transposed-flipped / phase-summed operands, ragged
+    tile edges (sizes that are no multiples of the 16 x 64 tile), channel segments, non-zero column offsets."""
+    k = K()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    w = torch.randn((cout, cin, 3, 3) if taps == 9 else (cout, cin, 1, 1), device=DEV, generator=g)
+    jobs, expect = [], []
+    for tf in (False, True):
+        for mode in ([0, 1, 2, 3, 4] if taps == 9 else [0]):
+            fmt = k.GRAD if tf else k.ACT
+            ltaps = taps if mode == 0 else 4
+            rows, inner = (ci_count, cout) if tf else (cout, ci_count)
+            k_off = 64
+            single = torch.full((rows + 3, k_off + ltaps * inner + 6), 7, dtype=torch.int16, device=DEV).view(k.T16)
+            multi = single.clone()
+            k.pack_conv_weight(w, single, k_off=k_off, ci_begin=ci_begin, ci_count=ci_count, transpose_flip=tf, fmt=fmt, mode=mode)
+            exp = _expected_pack(k, w, ci_begin, ci_count, tf, fmt, mode)
+            got = single[:rows, k_off:k_off + ltaps * inner]
+            assert torch.equal(got.view(torch.int16), exp.view(torch.int16)), (tf, mode)
+            # nothing outside the operand is written
+            pad = single.clone().view(torch.int16)
+            pad[:rows, k_off:k_off + ltaps * inner] = 7
+            assert bool((pad == 7).all()), (tf, mode)
+            jobs.append((w, multi, k_off, ci_begin, ci_count, tf, fmt, mode))
+            expect.append(single)
+    k.pack_conv_weight_multi(jobs, {})
+    for (_, multi, *_), single in zip(jobs, expect):
+        assert torch.equal(multi.view(torch.int16), single.view(torch.int16))
