@@ -436,6 +436,22 @@ def run_sample(args, rank, world, local):
     return rec
 
 
+def build_multitask_lit(dev):
+    """configs/model/conditional_flow_matching_multitask_multiclass.yaml: features [64..1024], 5 classes, Adam 1e-4 / wd 1e-5."""
+    import functools
+    from stain2stain_b200 import multitask as mt
+    from stain2stain_b200.flow_matching import ConditionalFlowMatcher
+    from stain2stain_b200.neural_ode import NeuralODE
+    from stain2stain_b200.optim import FusedAdam
+    torch.manual_seed(1984)
+    f = [64, 128, 256, 512, 1024]
+    return mt.MultiTaskFlowMatchingLitModule(
+        mt.SharedEncoder(3, f, True), mt.FlowMatchingDecoder(1024, f[:-1][::-1], 3, 256, True),
+        mt.SegmentationDecoder(1024, f[:-1][::-1], 5, True), ConditionalFlowMatcher(0.0), num_classes=5,
+        solver=functools.partial(NeuralODE, solver="euler"), optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=1e-5),
+        scheduler=None, log_images=False).to(dev)
+
+
 def run_multitask(args, rank, world, local):
     """configs[4]: multitask multiclass model (shared encoder + flow / segmentation decoders), 512x512 tiles, train step
     = FM sample -> encoder+flow decoder -> MSE; second encoder pass -> segmentation decoder -> Dice+CE; backward; Adam."""
@@ -448,13 +464,7 @@ def run_multitask(args, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     B, S = args.batch, 512
-    torch.manual_seed(1984)
-    f = [64, 128, 256, 512, 1024]
-    lit = mt.MultiTaskFlowMatchingLitModule(
-        mt.SharedEncoder(3, f, True), mt.FlowMatchingDecoder(1024, f[:-1][::-1], 3, 256, True),
-        mt.SegmentationDecoder(1024, f[:-1][::-1], 5, True), ConditionalFlowMatcher(0.0), num_classes=5,
-        solver=functools.partial(NeuralODE, solver="euler"), optimizer=functools.partial(FusedAdam, lr=1e-4, weight_decay=1e-5),
-        scheduler=None, log_images=False).to(dev)
+    lit = build_multitask_lit(dev)
     if args.sync_bn and world > 1:  # what Lightning does for `sync_batchnorm: True` (configs/trainer/ddp.yaml:9)
         lit = torch.nn.SyncBatchNorm.convert_sync_batchnorm(lit)
     lit.train()

@@ -284,19 +284,25 @@ int s2s_bn_coef(const float* stats, int B, int nchunks, int C, int HW, const flo
 int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const float* mean_rstd, const float* gamma,
                     float* pqr, float* dgamma, float* dbeta, void* stream);
 
-/* torch.nn.SyncBatchNorm (what `sync_batchnorm: True` of configs/trainer/ddp.yaml:9 makes Lightning install in place of
- * every BatchNorm2d): each rank folds its partials to per-channel sums (bn_fold: parts [nparts][C][2] -> sums [C][2], same
- * fixed order), the host all-reduces the [C][2] sums (+ the element count), and the totals come back as ONE part:
- *   bn_coef_sums    : sums of ALL ranks, count = global elements per channel -> coef / mean_rstd for the B local samples,
- *                     running statistics from the global mean / unbiased variance (identical on every rank)
- *   bn_bwd_coef_sums: all-reduced (sum dz, sum dz*xhat) -> pqr with the global count; the parameter gradients stay LOCAL
- *                     (torch's SyncBatchNorm does the same, DDP averages them): the two scratch vectors receive the global
- *                     sums and are discarded by the caller, which takes dgamma / dbeta from its own bn_fold result. */
-int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, void* stream);
-int s2s_bn_coef_sums(const float* sums, int C, long long count, int B, const float* gamma, const float* beta, float eps,
-                     float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream);
-int s2s_bn_bwd_coef_sums(const float* sums, int C, long long count, int B, const float* mean_rstd, const float* gamma,
-                         float* pqr, float* dgamma_scratch, float* dbeta_scratch, void* stream);
+/* Two-level folds and torch.nn.SyncBatchNorm (what `sync_batchnorm: True` of configs/trainer/ddp.yaml:9 makes Lightning
+ * install in place of every BatchNorm2d).
+ *   bn_fold         : parts [nparts][C][2] -> sums [nslices][C][2], slice s = the parts [s*per, (s+1)*per) folded in a fixed
+ *                     order (per = ceil(nparts / nslices); s2s_bn_fold_slices(nparts) is the slice count the host wrappers use:
+ *                     the statistics of a 512^2 layer are 32768 partials per channel, far too many for the C/32 CTAs of the
+ *                     coefficient kernels).  nslices = 1: this rank's per-channel totals, which SyncBatchNorm all-reduces.
+ *   bn_coef_sums    : bn_coef over `nparts` rows of sums with an explicit element count per channel (the GLOBAL count for
+ *                     SyncBatchNorm: coef / mean_rstd for the B local samples, running statistics from the global mean /
+ *                     unbiased variance, identical on every rank)
+ *   bn_bwd_coef_sums: likewise for (sum dz, sum dz*xhat) -> pqr; dgamma / dbeta += the folded sums (SyncBatchNorm callers pass
+ *                     scratch vectors here and take the LOCAL parameter gradients from their own bn_fold result, as torch's
+ *                     SyncBatchNorm does -- DDP averages them). */
+int s2s_bn_fold_slices(int nparts);
+int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, int nslices, void* stream);
+int s2s_bn_coef_sums(const float* sums, int nparts, int C, long long count, int B, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd,
+                     void* stream);
+int s2s_bn_bwd_coef_sums(const float* sums, int nparts, int C, long long count, int B, const float* mean_rstd,
+                         const float* gamma, float* pqr, float* dgamma, float* dbeta, void* stream);
 
 /* nn.MaxPool2d(2) (shared_encoder.py:32-34) and its backward (gradient to the first maximum in row-major order, as ATen);
  * 16-bit NHWC, H, W = OUTPUT spatial dims. */

@@ -14,19 +14,26 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--mode", default="train", choices=["train", "multitask"])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-lit = bench.build_lit(dev)
+g = torch.Generator(device=dev).manual_seed(1)
+if a.mode == "multitask":
+    lit = bench.build_multitask_lit(dev)
+    S = 512
+    batch = (torch.rand(a.batch, 3, S, S, device=dev, generator=g) * 2 - 1, torch.rand(a.batch, 3, S, S, device=dev, generator=g) * 2 - 1,
+             torch.randint(0, 5, (a.batch, 1, S, S), device=dev, generator=g).float())
+else:
+    lit = bench.build_lit(dev)
+    batch = (torch.rand(a.batch, 3, 256, 256, device=dev, generator=g) * 2 - 1,
+             torch.rand(a.batch, 3, 256, 256, device=dev, generator=g) * 2 - 1)
 lit.train()
 opt = lit.configure_optimizers()["optimizer"]
-g = torch.Generator(device=dev).manual_seed(1)
-x0 = torch.rand(a.batch, 3, 256, 256, device=dev, generator=g) * 2 - 1
-x1 = torch.rand(a.batch, 3, 256, 256, device=dev, generator=g) * 2 - 1
 
 
 def step():
     opt.zero_grad(set_to_none=True)
-    loss = lit.training_step((x0, x1), 0)
+    loss = lit.training_step(batch, 0)
     loss.backward()
     opt.step()
 

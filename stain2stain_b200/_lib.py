@@ -92,9 +92,10 @@ SIGNATURES = {
     "s2s_nhwc16_to_nchw_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
     "s2s_bn_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
     "s2s_bn_bwd_coef": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "s2s_bn_fold": [_vp, _i, _i, _vp, _vp],
-    "s2s_bn_coef_sums": [_vp, _i, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
-    "s2s_bn_bwd_coef_sums": [_vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "s2s_bn_fold_slices": [_i],
+    "s2s_bn_fold": [_vp, _i, _i, _vp, _i, _vp],
+    "s2s_bn_coef_sums": [_vp, _i, _i, _ll, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "s2s_bn_bwd_coef_sums": [_vp, _i, _i, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "s2s_maxpool2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "s2s_maxpool2x_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "s2s_bilinear2x": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

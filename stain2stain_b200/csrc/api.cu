@@ -1238,31 +1238,38 @@ int s2s_bn_bwd_coef(const float* red, int B, int nchunks, int C, int HW, const f
     return S2S_OK;
 }
 
-int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, void* stream) {
-    if (!parts || !sums || nparts <= 0 || C <= 0) return fail(S2S_ERR_INVALID, "bn_fold: bad arguments");
-    bn_fold_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>((const float2*)parts, nparts, C,
-                                                                                            (float2*)sums);
+int s2s_bn_fold_slices(int nparts) {  // slices a fold of `nparts` partials is cut into (each at least 256 parts)
+    int s = nparts / 256;
+    return s < 1 ? 1 : (s > 128 ? 128 : s);
+}
+
+int s2s_bn_fold(const float* parts, int nparts, int C, float* sums, int nslices, void* stream) {
+    if (!parts || !sums || nparts <= 0 || C <= 0 || nslices <= 0 || nslices > nparts)
+        return fail(S2S_ERR_INVALID, "bn_fold: bad arguments");
+    dim3 grid((C + kBnCh - 1) / kBnCh, nslices);
+    bn_fold_kernel<<<grid, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>((const float2*)parts, nparts, C, (float2*)sums);
     LAUNCH_CHECK("bn_fold_kernel");
     return S2S_OK;
 }
 
-int s2s_bn_coef_sums(const float* sums, int C, long long count, int B, const float* gamma, const float* beta, float eps,
-                     float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd, void* stream) {
-    if (!sums || !gamma || !beta || !coef || !mean_rstd || C <= 0 || count <= 0 || B <= 0)
+int s2s_bn_coef_sums(const float* sums, int nparts, int C, long long count, int B, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var, float* coef, float* mean_rstd,
+                     void* stream) {
+    if (!sums || !gamma || !beta || !coef || !mean_rstd || C <= 0 || count <= 0 || B <= 0 || nparts <= 0)
         return fail(S2S_ERR_INVALID, "bn_coef_sums: bad arguments");
     bn_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
-        (const float2*)sums, 1, B, C, count, gamma, beta, eps, momentum, running_mean, running_var, (float2*)coef,
+        (const float2*)sums, nparts, B, C, count, gamma, beta, eps, momentum, running_mean, running_var, (float2*)coef,
         (float2*)mean_rstd);
     LAUNCH_CHECK("bn_coef_kernel");
     return S2S_OK;
 }
 
-int s2s_bn_bwd_coef_sums(const float* sums, int C, long long count, int B, const float* mean_rstd, const float* gamma,
-                         float* pqr, float* dgamma_scratch, float* dbeta_scratch, void* stream) {
-    if (!sums || !mean_rstd || !gamma || !pqr || !dgamma_scratch || !dbeta_scratch || count <= 0 || B <= 0)
+int s2s_bn_bwd_coef_sums(const float* sums, int nparts, int C, long long count, int B, const float* mean_rstd,
+                         const float* gamma, float* pqr, float* dgamma, float* dbeta, void* stream) {
+    if (!sums || !mean_rstd || !gamma || !pqr || !dgamma || !dbeta || count <= 0 || B <= 0 || nparts <= 0)
         return fail(S2S_ERR_INVALID, "bn_bwd_coef_sums: bad arguments");
     bn_bwd_coef_kernel<<<(C + kBnCh - 1) / kBnCh, kBnCh * kBnRows, 0, (cudaStream_t)stream>>>(
-        (const float2*)sums, 1, B, C, count, (const float2*)mean_rstd, gamma, (float4*)pqr, dgamma_scratch, dbeta_scratch);
+        (const float2*)sums, nparts, B, C, count, (const float2*)mean_rstd, gamma, (float4*)pqr, dgamma, dbeta);
     LAUNCH_CHECK("bn_bwd_coef_kernel");
     return S2S_OK;
 }
@@ -1303,7 +1310,7 @@ int s2s_bilinear2x_bwd(const void* g, void* din, int B, int H, int W, int C, int
 }
 int s2s_nchw_f32_to_nhwc16_pad(const float* in, void* out, int B, int C, int Cpad, int HW, int fmt, void* stream) {
     if (C > Cpad || Cpad % 8) return fail(S2S_ERR_INVALID, "nchw_f32_to_nhwc16_pad: need C <= Cpad, Cpad %% 8 == 0");
-    const long long total = (long long)B * Cpad * HW;
+    const long long total = (long long)B * (Cpad / 8) * HW;  // one thread per 16-byte vector
     nchw_f32_to_nhwc16_pad_kernel<<<ew_grid(total), kEwThreads, 0, (cudaStream_t)stream>>>(in, (uint16_t*)out, B, C, Cpad, HW, fmt);
     LAUNCH_CHECK("nchw_f32_to_nhwc16_pad_kernel");
     return S2S_OK;

@@ -58,21 +58,34 @@ __global__ void __launch_bounds__(kBnCh * kBnRows) bn_coef_kernel(const float2* 
     }
 }
 
-// SyncBatchNorm (torch.nn.SyncBatchNorm, what Lightning's `sync_batchnorm: True` of configs/trainer/ddp.yaml:9 installs):
-// the per-channel sums of one rank, folded in the same fixed order, so that the host can all-reduce [C][2] floats and hand
-// the totals back to bn_coef_kernel / bn_bwd_coef_kernel as ONE part with the global element count.
+// Fold of many partials in two levels.  The statistics of a 512^2 layer arrive as 2048 sub-tile partials per sample (32768
+// per channel at B = 16) and the coefficient kernels have only C / 32 CTAs: folding there was a serial walk of 51 us on
+// average (36 calls per multitask step).  This kernel cuts the parts into gridDim.y slices, each folded in the same fixed
+// order into sums[slice][C]; the coefficient kernels then fold the slices (deterministic).  With one slice it is the
+// per-rank total SyncBatchNorm all-reduces (torch.nn.SyncBatchNorm, what Lightning's `sync_batchnorm: True` of
+// configs/trainer/ddp.yaml:9 installs): the totals of all ranks come back to the coefficient kernels as ONE part with the
+// global element count.
 __global__ void __launch_bounds__(kBnCh * kBnRows) bn_fold_kernel(const float2* __restrict__ parts, int nparts, int C,
                                                                   float2* __restrict__ sums) {
     __shared__ float s_a[kBnRows][kBnCh + 1], s_q[kBnRows][kBnCh + 1];
     const int ci = threadIdx.x % kBnCh, r = threadIdx.x / kBnCh;
     const int c = blockIdx.x * kBnCh + ci;
+    const int per = (nparts + gridDim.y - 1) / gridDim.y;
+    const int k0 = blockIdx.y * per, k1 = min(nparts, k0 + per);
     float a = 0.f, q = 0.f;
-    if (c < C)
-        for (int k = r; k < nparts; k += kBnRows) {
+    if (c < C) {
+        int k = k0 + r;
+        for (; k + 3 * kBnRows < k1; k += 4 * kBnRows) {  // four independent loads in flight
+            const float2 t0 = parts[(size_t)k * C + c], t1 = parts[(size_t)(k + kBnRows) * C + c];
+            const float2 t2 = parts[(size_t)(k + 2 * kBnRows) * C + c], t3 = parts[(size_t)(k + 3 * kBnRows) * C + c];
+            a += t0.x; q += t0.y; a += t1.x; q += t1.y; a += t2.x; q += t2.y; a += t3.x; q += t3.y;
+        }
+        for (; k < k1; k += kBnRows) {
             const float2 t = parts[(size_t)k * C + c];
             a += t.x;
             q += t.y;
         }
+    }
     s_a[r][ci] = a;
     s_q[r][ci] = q;
     __syncthreads();
@@ -83,7 +96,7 @@ __global__ void __launch_bounds__(kBnCh * kBnRows) bn_fold_kernel(const float2* 
             a += s_a[k][ci];
             q += s_q[k][ci];
         }
-        sums[c] = make_float2(a, q);
+        sums[(size_t)blockIdx.y * C + c] = make_float2(a, q);
     }
 }
 
@@ -199,7 +212,8 @@ __device__ __forceinline__ void bilin_src(int dst, float scale, int in, int& i0,
 }
 // out [B, 2H, 2W, C] from in [B, H, W, C].  Grid (x: vector columns of one output row, y: output row, z: sample): the row's
 // two source rows and weight are block-uniform and every index is 32-bit (the first version decoded a flat 64-bit index
-// with three 64-bit divisions per vector and ran at 0.27 of HBM).
+// with three 64-bit divisions per vector and ran at 0.27 of HBM).  Four rows per CTA instead of one was measured slower
+// (forward 1.50 -> 1.56 ms, adjoint 1.86 -> 2.88 ms per multitask step): the row grid stays.
 template <int F>
 __global__ void __launch_bounds__(256) bilinear2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W,
                                                          int vpp) {
@@ -292,15 +306,28 @@ __global__ void __launch_bounds__(256) bilinear2x_bwd_kernel(const uint4* __rest
 
 // ------------------------------------------------------------------------------------------------ layout glue
 // fp32 NCHW [B, C, HW] -> 16-bit NHWC [B, HW, Cpad] (channels >= C are zero): narrow image-space gradients as GEMM operands
-__global__ void nchw_f32_to_nhwc16_pad_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int B, int C,
-                                              int Cpad, int HW, int fmt) {
-    const long long total = (long long)B * HW * Cpad;
+// Thread = one 16-byte vector (8 channels) of one pixel, consecutive threads = consecutive vectors of the NHWC row: stores are
+// fully coalesced, only the vectors that hold real channels read (the element-per-thread version ran at 0.08 of the HBM rate).
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc16_pad_kernel(const float* __restrict__ in, uint16_t* __restrict__ out,
+                                                                     int B, int C, int Cpad, int HW, int fmt) {
+    const int vpp = Cpad >> 3;
+    const long long total = (long long)B * HW * vpp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cpad);
-        const long long r = i / Cpad;
-        const int p = (int)(r % HW);
-        const int b = (int)(r / HW);
-        out[i] = c < C ? pack1(in[((size_t)b * C + c) * HW + p], fmt) : (uint16_t)0;
+        const int v = (int)(i % vpp);
+        const long long r = i / vpp;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (v * 8 < C) {
+            const int p = (int)(r % HW);
+            const int b = (int)(r / HW);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = v * 8 + e;
+                f[e] = c < C ? __ldg(in + ((size_t)b * C + c) * HW + p) : 0.f;
+            }
+            o = cvt8_out(f, fmt);
+        }
+        reinterpret_cast<uint4*>(out)[i] = o;
     }
 }
 

@@ -634,9 +634,45 @@ def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2  # the `silu` argument of gn_apply / gn_bwd_* is the activation code
 
 
+def bn_fold(parts, slices: int = 1):
+    """[B, nchunks, C, 2] partials -> [slices, C, 2] sums (slices = 1: this rank's per-channel totals, what SyncBatchNorm
+    all-reduces)."""
+    B, nchunks, C, _ = parts.shape
+    sums = torch.empty((slices, C, 2), dtype=torch.float32, device=parts.device)
+    check(_L().s2s_bn_fold(ptr(parts), B * nchunks, C, ptr(sums), slices, stream_ptr()), "bn_fold")
+    return sums
+
+
+def bn_coef_sums(sums, count: int, B: int, gamma, beta, eps: float, momentum: float, running_mean, running_var):
+    """bn_coef from [nparts, C, 2] per-channel sums and an explicit element count per channel (global for SyncBatchNorm)."""
+    nparts, C, _ = sums.shape
+    coef = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
+    mr = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
+    check(_L().s2s_bn_coef_sums(ptr(sums), nparts, C, int(count), B, ptr(gamma), ptr(beta), float(eps), float(momentum),
+                                ptr(running_mean), ptr(running_var), ptr(coef), ptr(mr), stream_ptr()), "bn_coef_sums")
+    return coef, mr
+
+
+def bn_bwd_coef_sums(sums, count: int, B: int, mr, gamma, dgamma=None, dbeta=None):
+    """pqr [B, C, 4] from [nparts, C, 2] sums of (sum dz, sum dz*xhat) and the element count; dgamma / dbeta (fp32 [C], += the
+    folded sums) default to discarded scratch (SyncBatchNorm keeps the LOCAL parameter gradients)."""
+    nparts, C, _ = sums.shape
+    pqr = torch.empty((B, C, 4), dtype=torch.float32, device=sums.device)
+    if dgamma is None:
+        scratch = torch.zeros((2, C), dtype=torch.float32, device=sums.device)
+        dgamma, dbeta = scratch[0], scratch[1]
+    check(_L().s2s_bn_bwd_coef_sums(ptr(sums), nparts, C, int(count), B, ptr(mr), ptr(gamma), ptr(pqr), ptr(dgamma),
+                                    ptr(dbeta), stream_ptr()), "bn_bwd_coef_sums")
+    return pqr
+
+
 def bn_coef(stats, gamma, beta, HW: int, eps: float, momentum: float, running_mean, running_var):
-    """Batch statistics fold of train-mode BatchNorm2d -> (coef [B,C,2], mean_rstd [B,C,2]); updates running stats."""
+    """Batch statistics fold of train-mode BatchNorm2d -> (coef [B,C,2], mean_rstd [B,C,2]); updates running stats.
+    Many partials (the sub-tile statistics of a conv epilogue: 2048 per sample at 512^2) are folded in two levels."""
     B, nchunks, C, _ = stats.shape
+    slices = int(_L().s2s_bn_fold_slices(B * nchunks))
+    if slices > 1:
+        return bn_coef_sums(bn_fold(stats, slices), B * HW, B, gamma, beta, eps, momentum, running_mean, running_var)
     coef = torch.empty((B, C, 2), dtype=torch.float32, device=stats.device)
     mr = torch.empty((B, C, 2), dtype=torch.float32, device=stats.device)
     check(_L().s2s_bn_coef(ptr(stats), B, nchunks, C, HW, ptr(gamma), ptr(beta), float(eps), float(momentum),
@@ -646,37 +682,12 @@ def bn_coef(stats, gamma, beta, HW: int, eps: float, momentum: float, running_me
 
 def bn_bwd_coef(red, mr, gamma, HW: int, dgamma, dbeta):
     B, nchunks, C, _ = red.shape
+    slices = int(_L().s2s_bn_fold_slices(B * nchunks))
+    if slices > 1:
+        return bn_bwd_coef_sums(bn_fold(red, slices), B * HW, B, mr, gamma, dgamma, dbeta)
     pqr = torch.empty((B, C, 4), dtype=torch.float32, device=red.device)
     check(_L().s2s_bn_bwd_coef(ptr(red), B, nchunks, C, HW, ptr(mr), ptr(gamma), ptr(pqr), ptr(dgamma), ptr(dbeta),
                                stream_ptr()), "bn_bwd_coef")
-    return pqr
-
-
-def bn_fold(parts):
-    """[B, nchunks, C, 2] partials -> this rank's per-channel sums [C, 2] (SyncBatchNorm: what gets all-reduced)."""
-    B, nchunks, C, _ = parts.shape
-    sums = torch.empty((C, 2), dtype=torch.float32, device=parts.device)
-    check(_L().s2s_bn_fold(ptr(parts), B * nchunks, C, ptr(sums), stream_ptr()), "bn_fold")
-    return sums
-
-
-def bn_coef_sums(sums, count: int, B: int, gamma, beta, eps: float, momentum: float, running_mean, running_var):
-    """bn_coef from all-reduced per-channel sums [C, 2] and the GLOBAL element count per channel."""
-    C = sums.shape[0]
-    coef = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
-    mr = torch.empty((B, C, 2), dtype=torch.float32, device=sums.device)
-    check(_L().s2s_bn_coef_sums(ptr(sums), C, int(count), B, ptr(gamma), ptr(beta), float(eps), float(momentum),
-                                ptr(running_mean), ptr(running_var), ptr(coef), ptr(mr), stream_ptr()), "bn_coef_sums")
-    return coef, mr
-
-
-def bn_bwd_coef_sums(sums, count: int, B: int, mr, gamma):
-    """pqr [B, C, 4] from all-reduced (sum dz, sum dz*xhat) [C, 2] and the global count."""
-    C = sums.shape[0]
-    pqr = torch.empty((B, C, 4), dtype=torch.float32, device=sums.device)
-    scratch = torch.zeros((2, C), dtype=torch.float32, device=sums.device)
-    check(_L().s2s_bn_bwd_coef_sums(ptr(sums), C, int(count), B, ptr(mr), ptr(gamma), ptr(pqr), ptr(scratch[0]),
-                                    ptr(scratch[1]), stream_ptr()), "bn_bwd_coef_sums")
     return pqr
 
 

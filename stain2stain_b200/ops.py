@@ -611,11 +611,11 @@ class _BatchNormRelu(torch.autograd.Function):
             # (sum dz, sum dz*xhat) of all ranks enter dx; the parameter gradients stay local (DDP averages them), as in
             # torch's SyncBatchNorm backward
             import torch.distributed as dist
-            local = K.bn_fold(red)
+            local = K.bn_fold(red)  # [1, C, 2]
             total = local.clone()
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.sync_group)
             pqr = K.bn_bwd_coef_sums(total, ctx.count, B, mr, gamma.detach())
-            dgamma, dbeta = local[:, 1].contiguous(), local[:, 0].contiguous()
+            dgamma, dbeta = local[0, :, 1].contiguous(), local[0, :, 0].contiguous()
         else:
             dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
             dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
