@@ -194,7 +194,8 @@ int s2s_gn_apply_step(const void* x, int B, int HW, int C, const float* coef, in
                       int ld_out, int silu, float drop_p, uint64_t seed, const uint64_t* seed_step_dev, void* mask_out,
                       int x_fmt, int y_fmt, void* stream);
 
-/* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g).
+/* Backward of the fused normalisation.  g = dL/dy (bf16 NHWC, row stride ld_g; g_fmt must be S2S_FMT_BF16 for the two
+ * streaming kernels -- gradients are bf16 everywhere in the engine, anything else is refused with S2S_ERR_INVALID).
  *   reduce: red_part[b][chunk][c_off+c] = (sum dz, sum dz*xhat) over the chunk   (fp32 [B][s2s_gn_chunks][Ctot][2])
  *   coef  : folds red_part into red[B][C][2]; pqr[b][c] = (P,Q,R,0); dgamma/dbeta += ...; dfilm[b][2C] = (dscale | dshift)
  *   apply : dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c])                      (bf16 NHWC [B,HW,C]) */

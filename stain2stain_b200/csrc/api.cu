@@ -1037,11 +1037,15 @@ int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(x_bf16_out != nullptr, X16, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    // gradients are bf16 everywhere in the engine (fp32's range, no loss scaling): the fp16-gradient variants of the two
+    // streaming backward kernels were never launched and doubled their 70-odd instantiations
+    if (g_fmt != S2S_FMT_BF16) return fail(S2S_ERR_INVALID, "gn_bwd_reduce: the gradient format must be bf16");
+    constexpr int GF = kFmtBF16;
+    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(x_bf16_out != nullptr, X16, S2S_FMT(x_fmt, XF,
         (gn_bwd_reduce_kernel<SILU, DROP, XF, GF, X16><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
             (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in,
-            (__nv_bfloat16*)x_bf16_out)))))));
+            (__nv_bfloat16*)x_bf16_out))))));
     LAUNCH_CHECK("gn_bwd_reduce_kernel");
     return S2S_OK;
 }
@@ -1081,10 +1085,12 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     if (rc) return rc;
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
-    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, S2S_FMT(g_fmt, GF,
+    if (g_fmt != S2S_FMT_BF16) return fail(S2S_ERR_INVALID, "gn_bwd_apply: the gradient format must be bf16");
+    constexpr int GF = kFmtBF16;
+    S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF,
         (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
-            Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in)))))));
+            Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in))))));
     LAUNCH_CHECK("gn_bwd_apply_kernel");
     return S2S_OK;
 }
