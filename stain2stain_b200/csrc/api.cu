@@ -226,6 +226,12 @@ int ew_grid(long long work_items, int threads = kEwThreads) {
 // A CTA is never given fewer than 256 pixels (128 below 64^2): with the 111 chunks the wave rule asks for at B = 64, a
 // 64^2 sample was cut into 37-pixel CTAs whose life is one latency chain (coefficients -> loads -> stores) -- 0.29-0.58
 // of the HBM rate at 64^2 / 32^2 against 0.64-0.82 with fat CTAs (profiles/r02_kbench_gn_min_ppc.txt).
+// Pixels per thread and loop iteration (= independent 16-byte loads in flight per tensor) of the streaming norm kernels, with
+// the CTAs per SM the register count then allows.  Same-box A/B inside the training step (profiles/r02_ab_gn_unroll.txt):
+//   gn_bwd_apply  2 @ 3 CTAs/SM: 0.82 of HBM   4 @ 2 CTAs/SM: 0.87  <- memory-latency bound, more loads in flight win
+//   gn_bwd_reduce 2 @ 4 CTAs/SM: 0.84          4 @ 3 CTAs/SM: 0.78  <- occupancy wins
+//   gn_apply      4 @ 4 CTAs/SM: 0.90 / 0.85 (dropout)   8 @ 3 CTAs/SM: 0.90 / 0.78
+constexpr int kGnBwdApplyU = 4, kGnBwdReduceU = 2, kGnApplyU = 4;
 int gn_min_ppc() {  // S2S_GN_MIN_PPC: fewest pixels a CTA of the normalisation kernels is given (experiments)
     static int v = -1;
     if (v < 0) {
@@ -1022,7 +1028,7 @@ int s2s_gn_apply_step(const void* x, int B, int HW, int C, const float* coef, in
     const int ppc = pick_pix_per_cta(B, HW, C);
     dim3 grid((HW + ppc - 1) / ppc, B);
     S2S_ACT(silu, SILU, S2S_BOOL(drop_p > 0.f, DROP, S2S_BOOL(y2_bf16 != nullptr, DUAL, S2S_FMT(x_fmt, XF, S2S_FMT(y_fmt, YF,
-        (gn_apply_kernel<SILU, DROP, XF, YF, DUAL><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+        (gn_apply_kernel<SILU, DROP, XF, YF, DUAL, kGnApplyU><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, C, HW, ppc, (const float2*)coef, Ctot, c_off, (__nv_bfloat16*)y,
             (__nv_bfloat16*)y2_bf16, ld_out, drop_p, seed, (uint8_t*)mask_out,
             (const unsigned long long*)seed_step_dev)))))));
@@ -1042,7 +1048,7 @@ int s2s_gn_bwd_reduce_x2(const void* x, const void* g, int ld_g, int B, int HW, 
     if (g_fmt != S2S_FMT_BF16) return fail(S2S_ERR_INVALID, "gn_bwd_reduce: the gradient format must be bf16");
     constexpr int GF = kFmtBF16;
     S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(x_bf16_out != nullptr, X16, S2S_FMT(x_fmt, XF,
-        (gn_bwd_reduce_kernel<SILU, DROP, XF, GF, X16><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+        (gn_bwd_reduce_kernel<SILU, DROP, XF, GF, X16, kGnBwdReduceU><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef,
             (const float2*)mean_rstd, G, Ctot, c_off, (float2*)red, drop_p, seed, (const uint8_t*)mask_in,
             (__nv_bfloat16*)x_bf16_out))))));
@@ -1088,7 +1094,7 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     if (g_fmt != S2S_FMT_BF16) return fail(S2S_ERR_INVALID, "gn_bwd_apply: the gradient format must be bf16");
     constexpr int GF = kFmtBF16;
     S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF,
-        (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
+        (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF, kGnBwdApplyU><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
             Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in))))));
     LAUNCH_CHECK("gn_bwd_apply_kernel");

@@ -546,8 +546,8 @@ __global__ void __launch_bounds__(1024) gn_coef_parts_kernel(const float2* __res
 // kDual: the same values are also written as bf16 to y2 (same geometry) -- the operand the weight-gradient GEMM of the
 // consuming conv needs (its MMA cannot mix fp16 x bf16), produced here for +2 B/element instead of a 4 B/element
 // conversion pass in backward.
-template <int kAct, bool kDrop, int XF, int YF, bool kDual>
-__global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
+template <int kAct, bool kDrop, int XF, int YF, bool kDual, int kU>
+__global__ void __launch_bounds__(kEwThreads, kU > 4 ? 3 : 4) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int C, int HW,
                                                                  int pix_per_cta, const float2* __restrict__ coef,
                                                                  int Ctot, int c_off, __nv_bfloat16* __restrict__ y,
                                                                  __nv_bfloat16* __restrict__ y2, int ld_out,
@@ -605,17 +605,17 @@ __global__ void __launch_bounds__(kEwThreads, 4) gn_apply_kernel(const __nv_bflo
             if (kDual) stg_stream_b(dst2, cvt8_out_t<kFmtBF16>(f));
         };
         int p = p0 + prow;
-        for (; p + (kGnUnroll - 1) * pstep < p1; p += kGnUnroll * pstep) {
-            uint4 u[kGnUnroll];
+        for (; p + (kU - 1) * pstep < p1; p += kU * pstep) {
+            uint4 u[kU];
             const char* q = xp;
 #pragma unroll
-            for (int i = 0; i < kGnUnroll; ++i) {
+            for (int i = 0; i < kU; ++i) {
                 u[i] = ldg_stream_b(q);
                 q = row_next<kFull>(q, sx);
             }
             xp = q;
 #pragma unroll
-            for (int i = 0; i < kGnUnroll; ++i) {
+            for (int i = 0; i < kU; ++i) {
                 body(u[i], yp, y2p);
                 yp = row_next<kFull>(yp, sy);
                 if (kDual) y2p = row_next<kFull>(y2p, sy);
@@ -719,8 +719,8 @@ __device__ __forceinline__ void gn_dz8(const uint4& xu, const uint4& gu, const G
 // variant spill in its main loop (profiles/r02_ncu_norm_attention_summary.txt).
 // kX16: also write x as bf16 (x_bf16_out).  A template argument because the extra pointer and store pushed the 64-register
 // main loop into local-memory spills; the variant with the side product runs at 3 CTAs per SM instead.
-template <int kAct, int kDrop, int XF, int GF, bool kX16>
-__global__ void __launch_bounds__(kEwThreads, kX16 ? 3 : 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
+template <int kAct, int kDrop, int XF, int GF, bool kX16, int kU>
+__global__ void __launch_bounds__(kEwThreads, (kX16 || kU > 2) ? 3 : 4) gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                       int C, int HW, int pix_per_cta,
                                                                       const float2* __restrict__ coef,
@@ -771,19 +771,31 @@ __global__ void __launch_bounds__(kEwThreads, kX16 ? 3 : 4) gn_bwd_reduce_kernel
             }
         };
         int p = p0 + prow;
-        for (; p + pstep < p1; p += 2 * pstep) {
-            const uint4 xu0 = ldg_stream_b(xp), xu1 = ldg_stream_b(row_next<kFull>(xp, sx));
-            const uint4 gu0 = ldg_stream_b(gp), gu1 = ldg_stream_b(row_next<kFull>(gp, sg));
-            const uint32_t m0 = stored ? (uint32_t)__ldg(mp) : 0xffu;
-            const uint32_t m1 = stored ? (uint32_t)__ldg(mask_next<kFull>(mp, sm)) : 0xffu;
-            body(xu0, gu0, m0, p, xo);
-            body(xu1, gu1, m1, p + pstep, want_x16 ? row_next<kFull>(xo, sx) : nullptr);
-            xp = row_next<kFull>(row_next<kFull>(xp, sx), sx);
-            gp = row_next<kFull>(row_next<kFull>(gp, sg), sg);
-            if (stored) mp = mask_next<kFull>(mask_next<kFull>(mp, sm), sm);
-            if (want_x16) xo = row_next<kFull>(row_next<kFull>(xo, sx), sx);
+        for (; p + (kU - 1) * pstep < p1; p += kU * pstep) {
+            uint4 xu[kU], gu[kU];
+            uint32_t mk[kU];
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {  // kFull: the i-th row is an immediate offset of the same pointer
+                xu[i] = ldg_stream_b(xp);
+                gu[i] = ldg_stream_b(gp);
+                mk[i] = stored ? (uint32_t)__ldg(mp) : 0xffu;
+                xp = row_next<kFull>(xp, sx);
+                gp = row_next<kFull>(gp, sg);
+                if (stored) mp = mask_next<kFull>(mp, sm);
+            }
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {
+                body(xu[i], gu[i], mk[i], p + i * pstep, xo);
+                if (want_x16) xo = row_next<kFull>(xo, sx);
+            }
         }
-        if (p < p1) body(ldg_stream_b(xp), ldg_stream_b(gp), stored ? (uint32_t)__ldg(mp) : 0xffu, p, xo);
+        for (; p < p1; p += pstep) {
+            body(ldg_stream_b(xp), ldg_stream_b(gp), stored ? (uint32_t)__ldg(mp) : 0xffu, p, xo);
+            xp = row_next<kFull>(xp, sx);
+            gp = row_next<kFull>(gp, sg);
+            if (stored) mp = mask_next<kFull>(mp, sm);
+            if (want_x16) xo = row_next<kFull>(xo, sx);
+        }
     };
     if (blockDim.x == kEwThreads && ld_g == C) run(std::true_type{});
     else run(std::false_type{});
@@ -892,8 +904,11 @@ __global__ void __launch_bounds__(1024) gn_bwd_coef_kernel(const float2* __restr
 }
 
 // Pass 2: dx[b,p,c] = dz*P + x*Q + R (+ add[b,p,c]) ; 16-bit NHWC.
-template <int kAct, int kDrop, bool kAdd, int XF, int GF>
-__global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
+// kU: pixels per thread and loop iteration = independent 16-byte loads in flight per tensor.  ncu (profiles/
+// r02_ncu_norm_final_summary.txt): 10-14 warps wait on the long scoreboard per issued instruction, the issue slots are 35 %
+// used -- memory-latency bound, so the lever is bytes in flight, not instructions.
+template <int kAct, int kDrop, bool kAdd, int XF, int GF, int kU>
+__global__ void __launch_bounds__(kEwThreads, kU > 2 ? 2 : 3) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      const __nv_bfloat16* __restrict__ g, int ld_g,
                                                                      int C, int HW, int pix_per_cta,
                                                                      const float2* __restrict__ coef,
@@ -953,22 +968,34 @@ __global__ void __launch_bounds__(kEwThreads, 3) gn_bwd_apply_kernel(const __nv_
         };
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         int p = p0 + prow;
-        for (; p + pstep < p1; p += 2 * pstep) {
-            const uint4 xu0 = ldg_stream_b(xp), xu1 = ldg_stream_b(row_next<kFull>(xp, sx));
-            const uint4 gu0 = ldg_stream_b(gp), gu1 = ldg_stream_b(row_next<kFull>(gp, sg));
-            const uint4 au0 = kAdd ? ldg_stream_b(ap) : zero4, au1 = kAdd ? ldg_stream_b(row_next<kFull>(ap, sx)) : zero4;
-            const uint32_t m0 = stored ? (uint32_t)__ldg(mp) : 0xffu;
-            const uint32_t m1 = stored ? (uint32_t)__ldg(mask_next<kFull>(mp, sm)) : 0xffu;
-            body(xu0, gu0, au0, m0, p, dp);
-            body(xu1, gu1, au1, m1, p + pstep, row_next<kFull>(dp, sx));
-            xp = row_next<kFull>(row_next<kFull>(xp, sx), sx);
-            dp = row_next<kFull>(row_next<kFull>(dp, sx), sx);
-            gp = row_next<kFull>(row_next<kFull>(gp, sg), sg);
-            if (kAdd) ap = row_next<kFull>(row_next<kFull>(ap, sx), sx);
-            if (stored) mp = mask_next<kFull>(mask_next<kFull>(mp, sm), sm);
+        for (; p + (kU - 1) * pstep < p1; p += kU * pstep) {
+            uint4 xu[kU], gu[kU], au[kU];
+            uint32_t mk[kU];
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {  // kFull: the i-th row is an immediate offset of the same pointer
+                xu[i] = ldg_stream_b(xp);
+                gu[i] = ldg_stream_b(gp);
+                au[i] = kAdd ? ldg_stream_b(ap) : zero4;
+                mk[i] = stored ? (uint32_t)__ldg(mp) : 0xffu;
+                xp = row_next<kFull>(xp, sx);
+                gp = row_next<kFull>(gp, sg);
+                if (kAdd) ap = row_next<kFull>(ap, sx);
+                if (stored) mp = mask_next<kFull>(mp, sm);
+            }
+#pragma unroll
+            for (int i = 0; i < kU; ++i) {
+                body(xu[i], gu[i], au[i], mk[i], p + i * pstep, dp);
+                dp = row_next<kFull>(dp, sx);
+            }
         }
-        if (p < p1)
+        for (; p < p1; p += pstep) {
             body(ldg_stream_b(xp), ldg_stream_b(gp), kAdd ? ldg_stream_b(ap) : zero4, stored ? (uint32_t)__ldg(mp) : 0xffu, p, dp);
+            xp = row_next<kFull>(xp, sx);
+            gp = row_next<kFull>(gp, sg);
+            dp = row_next<kFull>(dp, sx);
+            if (kAdd) ap = row_next<kFull>(ap, sx);
+            if (stored) mp = mask_next<kFull>(mp, sm);
+        }
     };
     if (blockDim.x == kEwThreads && ld_g == C) run(std::true_type{});
     else run(std::false_type{});
