@@ -232,6 +232,22 @@ int ew_grid(long long work_items, int threads = kEwThreads) {
 //   gn_bwd_reduce 2 @ 4 CTAs/SM: 0.84          4 @ 3 CTAs/SM: 0.78  <- occupancy wins
 //   gn_apply      4 @ 4 CTAs/SM: 0.90 / 0.85 (dropout)   8 @ 3 CTAs/SM: 0.90 / 0.78
 constexpr int kGnBwdApplyU = 4, kGnBwdReduceU = 2, kGnApplyU = 4;
+int gn_bulk() {  // S2S_GN_BULK=0: register-load version of gn_bwd_apply everywhere (A/B; profiles/r02_ab_gn_bulk.txt)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_GN_BULK");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+int gn_bulk_min_hw() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("S2S_GN_BULK_MIN_HW");
+        v = e ? atoi(e) : 16384;
+    }
+    return v;
+}
 int gn_min_ppc() {  // S2S_GN_MIN_PPC: fewest pixels a CTA of the normalisation kernels is given (experiments)
     static int v = -1;
     if (v < 0) {
@@ -1093,6 +1109,22 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     dim3 grid((HW + ppc - 1) / ppc, B);
     if (g_fmt != S2S_FMT_BF16) return fail(S2S_ERR_INVALID, "gn_bwd_apply: the gradient format must be bf16");
     constexpr int GF = kFmtBF16;
+    // inputs streamed through shared memory by bulk copies (TMA unit): contiguous gradients of the large levels only (a channel
+    // slice of the concat gradient needs one copy per pixel row -- measured slower than register loads --, and at <= 64^2 a
+    // CTA lives for too few tiles to amortise the pipeline fill)
+    if (gn_bulk() && vec_threads(C) == kEwThreads && ld_g == C && HW >= gn_bulk_min_hw()) {
+        S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, {
+            auto kern = gn_bwd_apply_bulk_kernel<SILU, DROP, ADD, XF, GF>;
+            const size_t smem = gn_bwd_apply_bulk_smem<ADD>();
+            rc = set_smem(kern, smem);
+            if (rc) return rc;
+            kern<<<grid, kEwThreads, smem, (cudaStream_t)stream>>>(
+                (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,
+                Ctot, c_off, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, drop_p, seed, (const uint8_t*)mask_in);
+        }))));
+        LAUNCH_CHECK("gn_bwd_apply_bulk_kernel");
+        return S2S_OK;
+    }
     S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF,
         (gn_bwd_apply_kernel<SILU, DROP, ADD, XF, GF, kGnBwdApplyU><<<grid, vec_threads(C), 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)g, ld_g, C, HW, ppc, (const float2*)coef, (const float4*)pqr,

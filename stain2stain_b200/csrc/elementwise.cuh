@@ -1001,6 +1001,136 @@ __global__ void __launch_bounds__(kEwThreads, kU > 2 ? 2 : 3) gn_bwd_apply_kerne
     else run(std::false_type{});
 }
 
+// Pass 2 with the inputs streamed through shared memory by 1-D bulk copies (cp.async.bulk, the TMA unit) instead of register
+// loads.  ncu on the register version (profiles/r02_ncu_norm_final_summary.txt): 10-14 warps per issued instruction wait on the
+// long scoreboard, issue slots 35 % used -- the kernel is bound by the bytes it can keep in flight, and every 16 bytes in
+// flight cost four registers of a thread that also holds 32 per-channel coefficients.  Here a CTA keeps kStages tiles of
+// 512 vectors per tensor in flight (kStages * 8 KB * 2-3 tensors) whatever its register count; the consumer threads read
+// their two vectors per tile from shared memory (the same (slot, pixel-row) ownership as above) and release the stage as
+// soon as the data is in registers.  One thread issues: a tensor whose pixel rows are contiguous (row length == C) is one
+// copy per tile, a channel slice of a wider tensor (the concat gradient, row stride ld_g) one copy per pixel row.
+// Requires blockDim.x == 256 (C / 8 divides 256).
+constexpr int kBulkStages = 4;
+constexpr int kBulkTileBytes = 2 * kEwThreads * 16;  // 512 vectors = 8 KB per tensor and stage
+template <bool kAdd>
+constexpr size_t gn_bwd_apply_bulk_smem() { return (size_t)kBulkStages * (kAdd ? 3 : 2) * kBulkTileBytes + 2 * kBulkStages * 8 + 128; }
+
+template <int kAct, int kDrop, bool kAdd, int XF, int GF>
+__global__ void __launch_bounds__(kEwThreads, kAdd ? 2 : 3) gn_bwd_apply_bulk_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ g, int ld_g, int C, int HW, int pix_per_cta,
+    const float2* __restrict__ coef, const float4* __restrict__ pqr, int Ctot, int c_off, const __nv_bfloat16* __restrict__ add,
+    __nv_bfloat16* __restrict__ dx, float drop_p, unsigned long long seed, const uint8_t* __restrict__ mask_in) {
+    constexpr int NT = kAdd ? 3 : 2, S = kBulkStages;
+    extern __shared__ uint8_t bulk_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bulk_smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * NT * kBulkTileBytes);
+    uint64_t* empty = full + S;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kEwThreads);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int vpp = C >> 3;
+    const int slot = tid % vpp, prow = tid / vpp, pstep = kEwThreads / vpp;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    const int tile_pix = 2 * pstep;
+    const int ntiles = (p1 - p0 + tile_pix - 1) / tile_pix;
+    const size_t pix_base = (size_t)b * HW + (size_t)p0;
+    const char* xb = reinterpret_cast<const char*>(x) + pix_base * C * 2;
+    const char* ab = kAdd ? reinterpret_cast<const char*>(add) + pix_base * C * 2 : nullptr;
+    const char* gb = reinterpret_cast<const char*>(g) + (pix_base * ld_g + c_off) * 2;
+    const bool g_rows_contiguous = ld_g == C;
+    auto issue = [&](int t) {  // one thread: the copies of tile t into stage t % S
+        const int s = t % S;
+        const int pix = t * tile_pix, np = min(tile_pix, p1 - p0 - pix);
+        const uint32_t bytes = (uint32_t)np * (uint32_t)C * 2u;
+        uint8_t* st = smem + (size_t)s * NT * kBulkTileBytes;
+        mbar_arrive_expect_tx(&full[s], NT * bytes);
+        bulk_load_1d(st, xb + (size_t)pix * C * 2, bytes, &full[s]);
+        if (g_rows_contiguous) {
+            bulk_load_1d(st + kBulkTileBytes, gb + (size_t)pix * C * 2, bytes, &full[s]);
+        } else {
+            for (int r = 0; r < np; ++r)
+                bulk_load_1d(st + kBulkTileBytes + (size_t)r * C * 2, gb + (size_t)(pix + r) * ld_g * 2, (uint32_t)C * 2u, &full[s]);
+        }
+        if (kAdd) bulk_load_1d(st + 2 * kBulkTileBytes, ab + (size_t)pix * C * 2, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < min(S, ntiles); ++t) issue(t);
+    // per-channel coefficients (while the first tiles fly)
+    GnZCoef<gn_half_path<kAct, XF>()> cf;
+    cf.load(coef + (size_t)b * Ctot + c_off + slot * 8);
+    float P[8], Q[8], R[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float4 t4 = pqr[(size_t)b * Ctot + c_off + slot * 8 + e];
+        P[e] = t4.x;
+        Q[e] = t4.y;
+        R[e] = t4.z;
+    }
+    const uint32_t thresh = kDrop ? dropout_thresh16(drop_p) : 0u;
+    const float keep_scale = kDrop ? 1.f / (1.f - drop_p) : 1.f;
+    if (kDrop != 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) P[e] *= keep_scale;
+    }
+    constexpr bool stored = kDrop == 2;
+    const unsigned long long e8_base = (unsigned long long)b * HW * (unsigned long long)(ld_g >> 3) +
+                                       (unsigned long long)((c_off >> 3) + slot);
+    const size_t mrow = (size_t)(ld_g >> 3);
+    char* dp = reinterpret_cast<char*>(dx) + ((pix_base + prow) * C + slot * 8) * 2;
+    const size_t sx = (size_t)pstep * C * 2;
+    // keep bytes of the stored dropout mask: fetched one tile ahead (two bytes per thread and tile)
+    auto mask_of = [&](int p) -> uint32_t {
+        return (stored && p < p1) ? (uint32_t)__ldg(mask_in + e8_base + (size_t)p * mrow) : 0xffu;
+    };
+    uint32_t mk0 = mask_of(p0 + prow), mk1 = mask_of(p0 + prow + pstep);
+    auto body = [&](const uint4& xu, const uint4& gu, const uint4& au, uint32_t m, int p, char* dst) {
+        if (kDrop == 1) m = dropout_keep8(seed, e8_base + (unsigned long long)p * (unsigned long long)(ld_g >> 3), thresh);
+        float xf[8], dz[8], o[8];
+        gn_dz8<kAct, kDrop != 0, XF, GF>(xu, gu, cf, m, xf, dz);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(dz[e], P[e], fmaf(xf[e], Q[e], R[e]));
+        if (kAdd) {
+            float af[8];
+            cvt8_in_t<GF>(au, af);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += af[e];
+        }
+        stg_stream_b(dst, cvt8_out_t<GF>(o));
+    };
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % S;
+        const uint32_t ph = (uint32_t)(t / S) & 1u;
+        const int p = p0 + t * tile_pix + prow;  // this thread's first pixel of the tile; the second is p + pstep
+        const uint32_t nm0 = mask_of(p + tile_pix), nm1 = mask_of(p + tile_pix + pstep);  // next tile's keep bytes
+        const uint8_t* st = smem + (size_t)s * NT * kBulkTileBytes + (size_t)tid * 16;
+        mbar_wait(&full[s], ph);
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        const uint4 xu0 = *reinterpret_cast<const uint4*>(st), xu1 = *reinterpret_cast<const uint4*>(st + kEwThreads * 16);
+        const uint4 gu0 = *reinterpret_cast<const uint4*>(st + kBulkTileBytes);
+        const uint4 gu1 = *reinterpret_cast<const uint4*>(st + kBulkTileBytes + kEwThreads * 16);
+        const uint4 au0 = kAdd ? *reinterpret_cast<const uint4*>(st + 2 * kBulkTileBytes) : zero4;
+        const uint4 au1 = kAdd ? *reinterpret_cast<const uint4*>(st + 2 * kBulkTileBytes + kEwThreads * 16) : zero4;
+        mbar_arrive(&empty[s]);  // the stage is free as soon as everybody holds its vectors in registers
+        if (tid == 0 && t + S < ntiles) {
+            mbar_wait(&empty[s], ph);
+            issue(t + S);
+        }
+        if (p < p1) body(xu0, gu0, au0, mk0, p, dp);
+        if (p + pstep < p1) body(xu1, gu1, au1, mk1, p + pstep, dp + sx);
+        dp += 2 * sx;
+        mk0 = nm0;
+        mk1 = nm1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ resampling
 // nearest x2 upsample, NHWC bf16: out[b, y, x, :] = in[b, y/2, x/2, :]
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int vpp) {
