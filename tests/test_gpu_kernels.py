@@ -160,7 +160,11 @@ def test_conv_dgrad_via_flipped_pack():
 
 @pytest.mark.parametrize("taps,stride,Cin,Cout,B,H,W", [(9, 1, 128, 128, 2, 32, 32), (9, 1, 64, 256, 1, 16, 48),
                                                        (1, 1, 256, 128, 2, 32, 32), (9, 2, 128, 128, 2, 32, 32),
-                                                       (9, 1, 512, 256, 1, 16, 16), (1, 1, 64, 128, 2, 24, 40)])
+                                                       (9, 1, 512, 256, 1, 16, 16), (1, 1, 64, 128, 2, 24, 40),
+                                                       # 128 output channels, 3x3 stride 1: the tap-pair mode of the CTA-pair
+                                                       # kernel (ragged tiles, Cin = 256 -> N tile 256, Cin = 384 -> 3 x 128)
+                                                       (9, 1, 256, 128, 3, 24, 40), (9, 1, 384, 128, 1, 32, 32),
+                                                       (9, 1, 128, 384, 2, 16, 16)])
 def test_conv_wgrad(taps, stride, Cin, Cout, B, H, W):
     k = K()
     g = torch.Generator(device=DEV).manual_seed(6)
