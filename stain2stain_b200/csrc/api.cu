@@ -1112,7 +1112,7 @@ int s2s_gn_bwd_apply(const void* x, const void* g, int ld_g, int B, int HW, int 
     // inputs streamed through shared memory by bulk copies (TMA unit): contiguous gradients of the large levels only (a channel
     // slice of the concat gradient needs one copy per pixel row -- measured slower than register loads --, and at <= 64^2 a
     // CTA lives for too few tiles to amortise the pipeline fill)
-    if (gn_bulk() && vec_threads(C) == kEwThreads && ld_g == C && HW >= gn_bulk_min_hw()) {
+    if (gn_bulk() && vec_threads(C) == kEwThreads && ld_g == C && c_off == 0 && HW >= gn_bulk_min_hw()) {
         S2S_ACT(silu, SILU, S2S_DROP(drop_p, mask_in, DROP, S2S_BOOL(add != nullptr, ADD, S2S_FMT(x_fmt, XF, {
             auto kern = gn_bwd_apply_bulk_kernel<SILU, DROP, ADD, XF, GF>;
             const size_t smem = gn_bwd_apply_bulk_smem<ADD>();
