@@ -257,7 +257,8 @@ int gn_min_ppc() {  // S2S_GN_MIN_PPC: fewest pixels a CTA of the normalisation 
     return v;
 }
 int pick_pix_per_cta(int B, int HW, int /*C*/) {
-    const long long wave = (long long)num_sms() * 12;
+    // pure geometry: without a device (host-only callers of s2s_gn_chunks, the CPU test tier) the B200's 148 SMs are assumed
+    const long long wave = (long long)(num_sms() > 0 ? num_sms() : 148) * 12;
     long long a = B, b = wave;
     while (b) { long long t = a % b; a = b; b = t; }  // a = gcd(B, wave)
     const long long base = wave / a;                  // smallest chunk count with (B * chunks) % wave == 0

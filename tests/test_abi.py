@@ -75,3 +75,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_host_side_geometry_queries_need_no_gpu():
+    """The work-decomposition queries of the C ABI are pure host arithmetic (no device needed): the chunking of the streaming
+    norm kernels (a function of (B, HW) only, never fewer than 128 / 256 pixels per CTA, covers the sample), the tile count of
+    the weight packing and the slice count of the two-level BatchNorm folds."""
+    from stain2stain_b200 import _lib
+    L = _lib.load()
+    for B, HW in [(64, 256 * 256), (64, 128 * 128), (64, 64 * 64), (64, 32 * 32), (2, 256 * 256), (16, 512 * 512), (1, 16 * 16),
+                  (3, 24 * 40)]:
+        chunks = L.s2s_gn_chunks(B, HW)
+        assert chunks >= 1
+        ppc = -(-HW // chunks)
+        assert chunks * ppc >= HW                                  # the chunks cover the sample
+        assert ppc >= min(HW, 256 if HW >= 4096 else 128) or chunks == 1, (B, HW, chunks)
+        assert L.s2s_gn_chunks(B, HW) == chunks                    # deterministic: concat sources are cut alike
+    # weight packing: tiles of 16 destination rows x 64 destination-contiguous elements
+    assert L.s2s_pack_tiles(128, 128, 0) == 8 * 2 and L.s2s_pack_tiles(128, 128, 1) == 8 * 2
+    assert L.s2s_pack_tiles(96, 40, 0) == 6 * 1 and L.s2s_pack_tiles(96, 40, 1) == 3 * 2
+    assert L.s2s_pack_tiles(0, 40, 0) == 0
+    # two-level folds: at least 256 partials per slice, at most 128 slices
+    assert [L.s2s_bn_fold_slices(n) for n in (1, 255, 256, 1776, 32768, 10 ** 6)] == [1, 1, 1, 6, 128, 128]
