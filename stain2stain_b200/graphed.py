@@ -60,6 +60,7 @@ class GraphedTrainStep:
         self.extras = [torch.zeros(tuple(sh), dtype=dt, device=self.device) for sh, dt in specs]
         self.y = self.extras[-1] if label_shape is not None else None
         self._t_host = torch.zeros(B, dtype=torch.float32).pin_memory()
+        self._t_copied = None  # event behind the last asynchronous H2D copy out of `_t_host`
         self.params = [p for p in lit.parameters() if p.requires_grad]
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.device)
         self.flat_grad = None
@@ -193,8 +194,15 @@ class GraphedTrainStep:
         self.x0.copy_(x0, non_blocking=True)
         self.x1.copy_(x1, non_blocking=True)
         if t is None:
+            # the host may run a step ahead of the device: do not redraw into the staging buffer while the previous
+            # step's copy out of it is still queued (that step would train on the NEXT step's times)
+            if self._t_copied is not None:
+                self._t_copied.synchronize()
             torch.rand(self._t_host.shape, out=self._t_host)
             self.t.copy_(self._t_host, non_blocking=True)
+            if self._t_copied is None:
+                self._t_copied = torch.cuda.Event()
+            self._t_copied.record(torch.cuda.current_stream(self.device))
         else:
             self.t.copy_(t, non_blocking=True)
         if self.y is not None and y is not None:
