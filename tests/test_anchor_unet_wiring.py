@@ -68,7 +68,7 @@ def _walk_unet(sd, t, x, y, *, in_ch, mc, out_ch, nrb, channel_mult, attn_ds, nu
     if t.dim() == 0:
         t = t.repeat(x.shape[0])
     half = mc // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     temb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     emb = F.linear(F.silu(F.linear(temb, P("time_embed.0.weight"), P("time_embed.0.bias"))),
@@ -133,7 +133,7 @@ def _dezero(sd, seed):
     for k, v in sd.items():
         v = v.detach().clone()
         if v.is_floating_point() and float(v.abs().max()) == 0.0:
-            v = torch.randn(v.shape, generator=g) * 0.05
+            v = torch.randn(v.shape, generator=g) * (1.0 / math.sqrt(v[0].numel()) if v.dim() >= 2 else 0.05)
         elif k.endswith(".bias"):
             v = v + torch.randn(v.shape, generator=g) * 0.05
         out[k] = v
@@ -236,3 +236,26 @@ def test_walker_reads_every_tensor_of_config_a_and_counts_70_954_883():
     assert used == set(sd)
     assert [k for k in sd if ".qkv." in k] == ["middle_block.1.qkv.weight", "middle_block.1.qkv.bias"]
     assert sum(math.prod(s) for s in shapes.values()) == 70_954_883
+
+
+@pytest.mark.gpu
+def test_engine_unet_equals_the_state_dict_walker():
+    """The B200 engine against the walker directly (not through the oracle): same gate as the oracle parity tests,
+    velocity rel-L2 <= 1e-2 (16-bit tensor-core operands vs true fp32; TF32 is off, tests/conftest.py)."""
+    from stain2stain_b200.unet import UNetModel
+    cfg = dict(dim=[3, 64, 64], num_channels=64, num_res_blocks=1, attention_resolutions="16,8", dropout=0.0,
+               use_scale_shift_norm=True, num_heads=4, num_head_channels=32, channel_mult=[1, 2, 2, 4])
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    net = UNetModel(**cfg)
+    sd = _dezero(net.state_dict(), seed=5)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    t, x, _ = _inputs(cfg, B=2)
+    t, x = t.to(dev), x.to(dev)
+    want, used = _walk_unet({k: v.to(dev) for k, v in sd.items()}, t, x, None, **_walker_kwargs(cfg))
+    assert used == set(sd)
+    with torch.no_grad():
+        got = net(t, x)
+    rel = float((got.double() - want.double()).norm() / want.double().norm())
+    assert rel <= 1e-2, rel
