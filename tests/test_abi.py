@@ -97,3 +97,29 @@ def test_host_side_geometry_queries_need_no_gpu():
     assert L.s2s_pack_tiles(0, 40, 0) == 0
     # two-level folds: at least 256 partials per slice, at most 128 slices
     assert [L.s2s_bn_fold_slices(n) for n in (1, 255, 256, 1776, 32768, 10 ** 6)] == [1, 1, 1, 6, 128, 128]
+
+
+def test_header_is_plain_c_and_a_c_program_binds_the_library(tmp_path):
+    """The boundary is a C ABI, not a C++ or torch one: include/s2s_b200.h compiles as C99 and a C program linked against
+    the library calls its host-only entry points (what a cgo / JNI / N-API binding of another host language would do)."""
+    from stain2stain_b200 import _build
+    lib = _build.build()
+    src = tmp_path / "bind.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "s2s_b200.h"
+int main(void) {
+    s2s_conv_src s;  /* the structs of the header are plain C aggregates */
+    memset(&s, 0, sizeof s);
+    printf("%d %d %d %d %d %d %zu\n", s2s_abi_version(), s2s_adam_chunk() > 0, s2s_linear_max_jobs() > 0,
+           s2s_attn_supported(32), s2s_attn_supported(48), s2s_gn_chunks(64, 256 * 256), sizeof s);
+    return s2s_last_error() == NULL;
+}
+''')
+    exe = tmp_path / "bind"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-comment", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe),
+                    "-L", os.path.dirname(lib), "-ls2s_b200", "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:5] == ["1", "1", "1", "1", "0"], out
+    assert int(out[5]) >= 1 and int(out[6]) == 24
