@@ -630,28 +630,32 @@ def _use_all_host_threads():
 
 
 def run_reference(args, rank, world):
+    """CPU arm: EXACTLY `--warmup` untimed and `--steps` timed steps of the reference's CPU path (fp32 oracle port), each step a
+    bounded sample of the workload: a batch of 4 tiles (configs[0]) when the run then stays within ~2.5 minutes, else 2 or 1
+    (the per-tile cost of the CPU path does not depend on the batch: 0.097 / 0.095 / 0.100 tiles/s at 1 / 2 / 4 on 8 threads)."""
     if rank != 0:
         return None
     _use_all_host_threads()
-    batch = 4
+    per_tile_s, budget_s = 2.3, 150.0  # measured on the GPU boxes' 16 host threads: 8.9 s per batch-4 step
+    batch = max(1, min(4, int(budget_s / (max(1, args.steps + args.warmup) * per_tile_s))))
     step = _oracle_step_fn(batch)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         step()
-    steps = min(args.steps, 3)
+    steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     v = batch * steps / dt
-    sample = (f"{steps} train steps of batch {batch} (configs[0]) after {min(args.warmup, 1)} warm-up, fp32 oracle "
-              f"restatement of the torchcfm UNet (torchcfm/lightning are not installable here), "
+    sample = (f"{steps} train steps of batch {batch} (configs[0]'s model and step; its batch is 4) after {args.warmup} warm-up, "
+              f"fp32 oracle restatement of the torchcfm UNet (torchcfm/lightning are not installable here), "
               f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores")
     return {"impl": "reference",
             "metric": "256x256 tiles/s, conditional flow-matching train step (FM sample + UNet fwd + MSE + bwd + allreduce + Adam)",
-            "value": v, "unit": "tiles/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
+            "value": v, "unit": "tiles/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic U(-1,1) 3x256x256 tile pairs, seed 1984",
-            "config": {"workload": "configs[1] model on the reference's CPU path (fp32 oracle port), bounded sample: batch 4 "
+            "config": {"workload": f"configs[1] model on the reference's CPU path (fp32 oracle port), bounded sample: batch {batch} "
                                    "per step on rank 0's host cores whatever --gpus is (the CPU path does not use the GPUs; "
                                    "tiles/s of this arm does not depend on N)",
                        "per_step_batch": batch, "threads": torch.get_num_threads()},
